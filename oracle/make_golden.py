@@ -1,0 +1,308 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference.
+
+TEST INFRASTRUCTURE ONLY -- runs in the build container, where
+/root/reference is mounted; the fixtures it writes are committed and are what
+the GPU box (which has no /root/reference) checks against.
+
+    python oracle/make_golden.py            # (re)writes tests/golden/*.npz
+
+What is driven (no edits to the reference; injection points per SURVEY.md
+Appendix A):
+  * env transitions: the real ``Env.step`` of CartPole / Pendulum / QuadPole2D /
+    QuadPole on prescribed float32 raw-action sequences, plus
+    ``Quadrotor._dynamics`` known-answer vectors;
+  * policy: ``GaussianActor_NeuralNetwork.forward/log_prob`` with the standard
+    normal draw replaced by a supplied tensor;
+  * rollouts: ``RolloutManager(use_multiprocessing=False)`` with injected
+    initial states (``reset`` wrapped) and injected noise;
+  * updates: ``GRPO.learn`` / ``PPO.learn`` with ``SGD(lr=1)`` (gradient =
+    theta_before - theta_after) and with ``Adam``.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shims  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def _envs():
+    from environments.cartpole_env import CartPole
+    from environments.pendulum_env import Pendulum
+    from environments.quadrotor_env import QuadPole, QuadPole2D
+    return {0: CartPole, 1: Pendulum, 2: QuadPole2D, 3: QuadPole}
+
+
+STATE_KEYS = {0: ["cartpole"], 1: ["pendulum"], 2: ["quadrotor", "pendulum"], 3: ["quadrotor", "pendulum"]}
+SPLIT = {0: [5], 1: [3], 2: [7, 3], 3: [13, 7]}
+
+
+def set_state(env, kind, vec):
+    """Put a full observation vector into env.state_dict (the layout reset() builds)."""
+    off = 0
+    for key, n in zip(STATE_KEYS[kind], SPLIT[kind]):
+        env.state_dict[key] = np.array(vec[off:off + n], dtype=np.float64)
+        off += n
+    env._initial_state = {k: v.copy() for k, v in env.state_dict.items()}
+    env._steps = 0
+    env._time = 0
+    env._time_balanced = 0
+
+
+def gen_transitions(kind, rng, episodes, scale, max_steps=None, pd=False):
+    """Run episodes of the real env on random raw actions; record every transition."""
+    cls = _envs()[kind]
+    env = cls() if max_steps is None else cls(max_steps=max_steps)
+    rows = {k: [] for k in ["state", "action", "next", "reward", "done", "steps_done", "bal_count"]}
+    for ep in range(episodes):
+        obs, _ = env.reset()
+        bal = 0
+        for t in range(env.max_steps):
+            A = env.action_space.shape[0]
+            if pd and kind == 1:
+                th = np.arctan2(obs[0], obs[1])
+                delta = np.arctan2(np.sin(th - np.pi), np.cos(th - np.pi))
+                a = np.array([-8.0 * delta - 2.0 * obs[2]], dtype=np.float32)
+            else:
+                a = (scale * rng.standard_normal(A)).astype(np.float32)
+            rows["state"].append(np.array(obs, dtype=np.float64))
+            rows["action"].append(a)
+            rows["steps_done"].append(t)
+            rows["bal_count"].append(bal)
+            obs, r, f1, f2, _ = env.step(a)
+            if kind == 1:
+                bal = bal + 1 if obs[1] <= -0.99 else 0
+                assert (bal > 0) == (env._time_balanced > 0)
+            rows["next"].append(np.array(obs, dtype=np.float64))
+            rows["reward"].append(float(r))
+            rows["done"].append(bool(f1 or f2))
+            if f1 or f2:
+                break
+    return {k: np.array(v) for k, v in rows.items()}
+
+
+def gen_quadrotor12(rng):
+    from environments.quadrotor_env import Quadrotor
+    q = Quadrotor()
+    S = rng.uniform(-0.5, 0.5, (64, 12))
+    U = rng.uniform(2.0, 3.0, (64, 4))
+    out = np.stack([np.asarray(q._dynamics(S[i], U[i])) for i in range(64)])
+    return {"state": S, "control": U, "next": out}
+
+
+class Injector:
+    """Feeds injected initial states and noise to the real worker loop."""
+
+    def __init__(self, kind, init_states, noise, E, restart):
+        self.kind, self.init, self.noise, self.E, self.restart = kind, init_states, noise, E, restart
+        self.cur = None  # (worker, episode, t)
+
+    def wrap_env(self, env, worker):
+        inj = self
+        orig_step, orig_restart = env.step, env.restart
+        st = {"ep": -1}
+
+        def reset():
+            st["ep"] += 1
+            ep = min(st["ep"], inj.E - 1)
+            n = worker * inj.E + (0 if inj.restart else ep)
+            set_state(env, inj.kind, inj.init[n])
+            inj.cur = [worker, ep, 0]
+            return env._get_obs(), env._get_info()
+
+        def restart():
+            st["ep"] += 1
+            inj.cur = [worker, min(st["ep"], inj.E - 1), 0]
+            return orig_restart()
+
+        def step(a):
+            out = orig_step(a)
+            inj.cur[2] += 1
+            return out
+
+        env.reset, env.restart, env.step = reset, restart, step
+        return env
+
+    def standard_normal(self, shape, dtype, device):
+        w, e, t = self.cur
+        return torch.from_numpy(self.noise[t, w * self.E + e].copy()).to(dtype).reshape(shape)
+
+
+def make_policy(kind, hidden, cov, seed, critic=False):
+    from policies.actor_critic import GaussianActor_NeuralNetwork, GaussianActorCritic_NeuralNetwork
+    O = {0: 5, 1: 3, 2: 10, 3: 20}[kind]
+    A = {0: 1, 1: 1, 2: 2, 3: 4}[kind]
+    torch.manual_seed(seed)
+    cls = GaussianActorCritic_NeuralNetwork if critic else GaussianActor_NeuralNetwork
+    return cls(O, A, hidden, "ReLU", cov)
+
+
+def policy_arrays(policy):
+    sd = policy.actor.state_dict()
+    keys = sorted({int(k.split(".")[1]) for k in sd})
+    out = {}
+    for i, k in enumerate(keys):
+        out[f"W{i}"] = sd[f"network.{k}.weight"].numpy().copy()
+        out[f"b{i}"] = sd[f"network.{k}.bias"].numpy().copy()
+    if hasattr(policy, "critic"):
+        sd = policy.critic.state_dict()
+        for i, k in enumerate(keys):
+            out[f"cW{i}"] = sd[f"network.{k}.weight"].numpy().copy()
+            out[f"cb{i}"] = sd[f"network.{k}.bias"].numpy().copy()
+    return out
+
+
+def run_rollout(kind, policy, init, noise, G, E, T, restart):
+    import torch.distributions.multivariate_normal as mvn
+    from rollout.rollout_manager import RolloutManager
+    cls = _envs()[kind]
+    inj = Injector(kind, init, noise, E, restart)
+    counter = {"i": -1}
+
+    def env_fn():
+        counter["i"] += 1
+        env = cls(max_steps=T)
+        if counter["i"] == 0:
+            return env  # the manager's own shape-discovery env
+        return inj.wrap_env(env, counter["i"] - 1)
+
+    saved = mvn._standard_normal
+    mvn._standard_normal = inj.standard_normal
+    try:
+        mgr = RolloutManager(env_fn, policy, restart=restart, num_workers=G,
+                             num_episodes_per_worker=E, use_multiprocessing=False)
+        obs, act, rew, ln, mask = mgr.rollout()
+    finally:
+        mvn._standard_normal = saved
+    return obs.numpy(), act.numpy(), rew.numpy(), ln.numpy(), mask.numpy()
+
+
+class Buf:
+    pass
+
+
+def gen_rollout_and_learn(kind, hidden, cov, G, E, T, restart, seed, gamma, eps_clip, noise_scale=1.0):
+    rng = np.random.default_rng(seed)
+    sys.path.insert(0, HERE)
+    import restate
+    policy = make_policy(kind, hidden, cov, seed)
+    A = {0: 1, 1: 1, 2: 2, 3: 4}[kind]
+    n_init = G if restart else G * E
+    init_small = restate.reset_states(kind, n_init, rng)
+    init = np.repeat(init_small, E, axis=0) if restart else init_small
+    noise = (noise_scale * rng.standard_normal((T, G * E, A))).astype(np.float32)
+    obs, act, rew, ln, mask = run_rollout(kind, policy, init, noise, G, E, T, restart)
+    out = dict(kind=kind, hidden=np.array(hidden), cov=np.float32(cov), G=G, E=E, T=T,
+               restart=restart, gamma=gamma, eps_clip=eps_clip, init=init, noise=noise,
+               obs=obs, act=act, rew=rew, len=ln, mask=mask, **policy_arrays(policy))
+
+    # --- log_prob KAT on the rollout's own samples
+    with torch.no_grad():
+        sel = torch.from_numpy(mask).bool()
+        lp, ent = policy.log_prob(torch.from_numpy(obs)[sel], torch.from_numpy(act)[sel])
+    out["logp_valid"] = lp.numpy()
+    out["entropy"] = float(ent.reshape(-1)[0])
+
+    # --- GRPO.learn: gradient through SGD(lr=1), one update
+    from algorithms.grpo import GRPO
+    buf = Buf()
+    buf.group_observations, buf.group_actions = torch.from_numpy(obs), torch.from_numpy(act)
+    buf.group_rewards, buf.group_masks = torch.from_numpy(rew), torch.from_numpy(mask)
+    import copy
+    p1 = copy.deepcopy(policy)
+    before = [p.detach().clone() for p in p1.parameters()]
+    algo = GRPO(eps_clip, 0.0, gamma, p1, torch.optim.SGD(p1.parameters(), lr=1.0), None, updates_per_iter=1)
+    algo.learn(buf)
+    for i, (b, a) in enumerate(zip(before, p1.parameters())):
+        out[f"grpo_grad{i}"] = (b - a.detach()).numpy()
+
+    # --- GRPO.learn with Adam, 3 updates (exercises ratio != 1 and the clip)
+    p2 = copy.deepcopy(policy)
+    algo = GRPO(eps_clip, 0.0, gamma, p2, torch.optim.Adam(p2.parameters(), lr=3e-4), None, updates_per_iter=3)
+    algo.learn(buf)
+    for i, a in enumerate(p2.parameters()):
+        out[f"grpo_adam3_p{i}"] = a.detach().numpy().copy()
+    # a second learn() call on the same buffer: old_policy has been synced (:148)
+    algo.learn(buf)
+    for i, a in enumerate(p2.parameters()):
+        out[f"grpo_adam6_p{i}"] = a.detach().numpy().copy()
+    return out
+
+
+def gen_ppo(kind, hidden, cov, G, E, T, seed, gamma, lam, eps_clip, monte_carlo):
+    """PPO.learn full-batch (batch_size=None), SGD(lr=1) one update and Adam 3 updates."""
+    import copy
+    from algorithms.ppo import PPO
+    rng = np.random.default_rng(seed)
+    import restate
+    policy = make_policy(kind, hidden, cov, seed, critic=True)
+    A = {0: 1, 1: 1, 2: 2, 3: 4}[kind]
+    init = restate.reset_states(kind, G * E, rng)
+    noise = rng.standard_normal((T, G * E, A)).astype(np.float32)
+    obs, act, rew, ln, mask = run_rollout(kind, policy, init, noise, G, E, T, False)
+    out = dict(kind=kind, hidden=np.array(hidden), cov=np.float32(cov), G=G, E=E, T=T, gamma=gamma,
+               lam=lam, eps_clip=eps_clip, monte_carlo=monte_carlo, init=init, noise=noise,
+               obs=obs, act=act, rew=rew, len=ln, mask=mask, **policy_arrays(policy))
+    buf = Buf()
+    buf.group_observations, buf.group_actions = torch.from_numpy(obs), torch.from_numpy(act)
+    buf.group_rewards, buf.group_masks = torch.from_numpy(rew), torch.from_numpy(mask)
+    kw = dict(c1=0.5, kl_coeff=0.5, gamma=gamma, lam=lam, entropy=0.01, batch_size=None, monte_carlo=monte_carlo)
+    p1 = copy.deepcopy(policy)
+    before = [p.detach().clone() for p in p1.parameters()]
+    PPO(eps_clip, p1, torch.optim.SGD(p1.parameters(), lr=1.0), None, 1, **kw).learn(buf)
+    for i, (b, a) in enumerate(zip(before, p1.parameters())):
+        out[f"ppo_grad{i}"] = (b - a.detach()).numpy()
+    p2 = copy.deepcopy(policy)
+    PPO(eps_clip, p2, torch.optim.Adam(p2.parameters(), lr=2e-4), None, 3, **kw).learn(buf)
+    for i, a in enumerate(p2.parameters()):
+        out[f"ppo_adam3_p{i}"] = a.detach().numpy().copy()
+    return out
+
+
+def main():
+    if not ref_shims.available():
+        raise SystemExit("reference not mounted; fixtures can only be regenerated in the build container")
+    ref_shims.install()
+    os.makedirs(OUT, exist_ok=True)
+    rng = np.random.default_rng(20261018)
+
+    # 1. env transitions
+    tr = {}
+    tr[0] = gen_transitions(0, rng, episodes=6, scale=1.0, max_steps=120)
+    pend_a = gen_transitions(1, rng, episodes=2, scale=0.8, max_steps=200)
+    pend_b = gen_transitions(1, rng, episodes=1, scale=0.0, max_steps=200, pd=True)   # reaches 101 balanced steps
+    tr[1] = {k: np.concatenate([pend_a[k], pend_b[k]]) for k in pend_a}
+    tr[2] = gen_transitions(2, rng, episodes=6, scale=1.0, max_steps=150)
+    tr[3] = gen_transitions(3, rng, episodes=6, scale=1.0, max_steps=150)
+    for k, v in tr.items():
+        np.savez_compressed(os.path.join(OUT, f"transitions_env{k}.npz"), **v)
+        print(f"transitions env{k}: {len(v['reward'])} rows, done={int(v['done'].sum())}")
+    np.savez_compressed(os.path.join(OUT, "quadrotor12_dynamics.npz"), **gen_quadrotor12(rng))
+
+    # 2. rollouts + GRPO learn (small shapes; T is the env's max_steps)
+    cases = [
+        ("cartpole", dict(kind=0, hidden=[32, 32], cov=0.5, G=3, E=4, T=40, restart=False, seed=1, gamma=0.5, eps_clip=0.15)),
+        ("pendulum", dict(kind=1, hidden=[64, 64], cov=0.5, G=4, E=4, T=30, restart=True, seed=2, gamma=0.99, eps_clip=0.2)),
+        ("quadpole2d", dict(kind=2, hidden=[32, 32], cov=0.5, G=3, E=3, T=60, restart=True, seed=3, gamma=0.99, eps_clip=0.2)),
+        ("quadpole", dict(kind=3, hidden=[64, 64], cov=0.3, G=3, E=4, T=80, restart=True, seed=4, gamma=0.999, eps_clip=0.2)),
+    ]
+    for name, kw in cases:
+        out = gen_rollout_and_learn(**kw)
+        np.savez_compressed(os.path.join(OUT, f"rollout_grpo_{name}.npz"), **out)
+        print(f"rollout_grpo_{name}: lens={out['len'].reshape(-1).tolist()}")
+
+    # 3. PPO learn
+    for name, mc in (("mc", True), ("gae", False)):
+        out = gen_ppo(kind=2, hidden=[32, 32], cov=0.5, G=2, E=3, T=40, seed=7, gamma=0.99, lam=0.95,
+                      eps_clip=0.2, monte_carlo=mc)
+        np.savez_compressed(os.path.join(OUT, f"ppo_{name}_quadpole2d.npz"), **out)
+        print(f"ppo_{name}: lens={out['len'].reshape(-1).tolist()}")
+
+
+if __name__ == "__main__":
+    main()
