@@ -1,0 +1,217 @@
+/*
+ * trajopt_grpo.h -- C ABI of the B200-native rollout-and-update engine.
+ *
+ * Drop-in boundary for the hot loop of Dyllon-Preston/trajopt-grpo.  The
+ * reference has no FFI; its boundary is a Python object protocol, so each entry
+ * point below names the Python call (reference file:line) it replaces.  The
+ * Python host in trajopt_grpo_b200/ binds these with ctypes (see
+ * INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every function returns an int status: 0 ok, <0 argument/shape error
+ *     (TG_ERR_*), >0 a cudaError_t; tg_last_error() returns the message of the
+ *     last failure on the calling thread;
+ *   - the CALLER allocates every buffer (device pointers unless stated), the
+ *     library never frees caller memory; calls are asynchronous on `stream`
+ *     (a cudaStream_t passed as void*);
+ *   - trajectories are struct-of-arrays with the env index innermost:
+ *     obs[T][O][N], act[T][A][N], rew/logp/adv[T][N]; env n = group*E + episode;
+ *     the host exposes them as strided views of logical shape [G,E,T,.];
+ *   - policy parameters are ONE flat fp32 vector in torch.nn order
+ *     (W0[out][in], b0, W1, b1, ...) -- the layout of
+ *     models/neural_network.py:50-65's Sequential -- so that the gradient is a
+ *     flat vector of the same layout (one NCCL allreduce) and Adam is one launch.
+ *   - there is NO CPU fallback: without an sm_100a device every compute call fails.
+ */
+#ifndef TRAJOPT_GRPO_H
+#define TRAJOPT_GRPO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TG_ABI_VERSION 1
+
+/* status codes */
+#define TG_OK 0
+#define TG_ERR_ARG (-1)         /* null pointer / bad enum */
+#define TG_ERR_SHAPE (-2)       /* dimension out of the supported range */
+#define TG_ERR_UNSUPPORTED (-3) /* configuration the kernels do not cover */
+#define TG_ERR_NO_DEVICE (-4)   /* no CUDA device / not sm_100 */
+
+/* environments (environments/*.py) */
+#define TG_ENV_CARTPOLE 0   /* cartpole_env.py:6-182   obs 5  act 1 */
+#define TG_ENV_PENDULUM 1   /* pendulum_env.py:7-162   obs 3  act 1 */
+#define TG_ENV_QUADPOLE2D 2 /* quadrotor_env.py:867-1223 obs 10 act 2 */
+#define TG_ENV_QUADPOLE 3   /* quadrotor_env.py:353-713  obs 20 act 4 */
+
+/* hidden-layer activations (models/neural_network.py:36-55: torch.nn class name) */
+#define TG_ACT_RELU 0
+#define TG_ACT_TANH 1
+#define TG_ACT_SIGMOID 2
+
+/* arithmetic of the env state */
+#define TG_PREC_F32 0 /* throughput mode: state, dynamics and reward in fp32 */
+#define TG_PREC_F64 1 /* parity mode: float64 state as the reference's numpy envs */
+
+/* advantage modes */
+#define TG_ADV_GRPO 0    /* grpo.py:66-74,108-115: per-group pooled z-score of RTG */
+#define TG_ADV_PPO_MC 1  /* ppo.py:100-111,138-139: RTG - V, global z-scores */
+#define TG_ADV_PPO_GAE 2 /* ppo.py:112-124,138-139 */
+
+#define TG_MAX_LAYERS 8
+#define TG_MAX_WIDTH 256
+#define TG_MAX_OBS 20
+#define TG_MAX_ACT 4
+
+typedef struct tg_ctx tg_ctx; /* opaque: device id, SM count, scratch */
+
+/* Constructor arguments of the reference env classes plus the two integer
+ * thresholds that stand in for its float64 time accumulators:
+ *   time_limit_step : first step count k at which `_time > max_time` fires
+ *                     (cartpole_env.py:153,168; pendulum_env.py:137,154)
+ *   balanced_limit  : consecutive balanced steps at which `_time_balanced > 5`
+ *                     fires (pendulum_env.py:138,155)
+ * Both are computed on the host by replaying the float64 accumulation. */
+typedef struct tg_env_cfg {
+    int32_t kind;            /* TG_ENV_* */
+    int32_t max_steps;       /* T, env.max_steps */
+    double dt;               /* env.timestep */
+    int32_t time_limit_step; /* CartPole, Pendulum */
+    int32_t balanced_limit;  /* Pendulum */
+} tg_env_cfg;
+
+/* models/neural_network.py:36-65 -- n_layers Linear layers, dims[0]=input_dim,
+ * dims[n_layers]=output_dim, one activation for every hidden layer. */
+typedef struct tg_mlp_cfg {
+    int32_t n_layers;
+    int32_t dims[TG_MAX_LAYERS + 1];
+    int32_t activation; /* TG_ACT_* */
+} tg_mlp_cfg;
+
+int tg_abi_version(void);
+const char *tg_last_error(void);
+
+int tg_ctx_create(int device, tg_ctx **out);
+void tg_ctx_destroy(tg_ctx *ctx);
+int tg_ctx_sm_count(const tg_ctx *ctx);
+
+/* dims of an env kind: returns 0 or TG_ERR_ARG */
+int tg_env_dims(int kind, int *obs_dim, int *act_dim);
+
+/* number of fp32 parameters of an MLP in flat torch order */
+int64_t tg_mlp_param_count(const tg_mlp_cfg *mlp);
+
+/* ---- K1: fused policy-in-the-loop rollout ---------------------------------
+ * Replaces RolloutManager.rollout (rollout/rollout_manager.py:85-125) =
+ * G x RolloutWorker.run_episodes (rollout/rollout_worker.py:19-84) =
+ * per step policy.forward (policies/actor_critic.py:107-138) + env.step.
+ *
+ *   init_state : [S][N] (S = obs_dim) float (TG_PREC_F32) or double (TG_PREC_F64)
+ *   params     : flat fp32 policy (actor) parameters, torch order
+ *   cov_diag   : HOST pointer, A floats, diagonal of policy.cov
+ *   noise      : [T][A][N] fp32 standard normals (one [A] slice per policy
+ *                call), or NULL to draw them in-kernel from Philox4x32-10 keyed
+ *                by (seed, env_offset + n, step t) -- tg_noise_fill materialises the
+ *                identical stream; env_offset is the global index of this
+ *                shard's first env, so a sharded run draws the single-GPU stream
+ *   out_obs    : [T][O][N] fp32  observation stored BEFORE acting (rollout_worker.py:53)
+ *   out_act    : [T][A][N] fp32  UNCLIPPED sample (rollout_worker.py:58)
+ *   out_rew    : [T][N]    fp32
+ *   out_logp   : [T][N]    fp32  log pi(a|s) at rollout time (may be NULL)
+ *   out_len    : [N]       int32 episode length (rollout_worker.py:67)
+ *   out_ret    : [N]       fp32  sum of rewards of the episode (may be NULL)
+ * Steps past the end of an episode are written as zeros (rollout_worker.py:64-68).
+ */
+int tg_rollout(tg_ctx *ctx, const tg_env_cfg *env, const tg_mlp_cfg *mlp, int precision,
+               int64_t N, const void *init_state, const float *params, const float *cov_diag,
+               const float *noise, uint64_t seed, int64_t env_offset,
+               float *out_obs, float *out_act, float *out_rew, float *out_logp,
+               int32_t *out_len, float *out_ret, void *stream);
+
+/* Fill noise[T][A][N] with the Philox stream tg_rollout(noise=NULL, seed) uses. */
+int tg_noise_fill(tg_ctx *ctx, uint64_t seed, int64_t env_offset, int64_t N, int T, int A, float *noise,
+                  void *stream);
+
+/* ---- batched single env step -----------------------------------------------
+ * Replaces Env.step (cartpole_env.py:138-182, pendulum_env.py:125-162,
+ * quadrotor_env.py:625-713, 1132-1223) for N independent envs.
+ *   state [S][N] (float|double per precision), raw_action [A][N] fp32,
+ *   steps_done [N] int32 (= env._steps before the call), bal_count [N] int32
+ *   (Pendulum: consecutive balanced steps before the call; may be NULL)
+ *   -> next_state [S][N], reward [N] (same type as state), done [N] int32
+ *   (terminated OR truncated), bal_out [N] int32 (may be NULL)
+ */
+int tg_env_step(tg_ctx *ctx, const tg_env_cfg *env, int precision, int64_t N,
+                const void *state, const float *raw_action, const int32_t *steps_done,
+                const int32_t *bal_count, void *next_state, void *reward, int32_t *done,
+                int32_t *bal_out, void *stream);
+
+/* Quadrotor._dynamics (quadrotor_env.py:113-169): state [12][N], control [4][N]
+ * (both float|double per precision) -> next [12][N]. */
+int tg_quadrotor12_dynamics(tg_ctx *ctx, int precision, int64_t N, double dt,
+                            const void *state, const void *control, void *next, void *stream);
+
+/* ---- policy forward / log-prob over a batch --------------------------------
+ * Replaces GaussianActor_NeuralNetwork.log_prob (policies/actor_critic.py:140-160)
+ * and NeuralNetwork.forward (models/neural_network.py:67-77) for M rows.
+ *   x [K0][M] fp32 (feature-major), act [A][M] or NULL
+ *   -> out_mu [A][M] (or NULL), out_logp [M] (or NULL; needs act and cov_diag)
+ */
+int tg_policy_forward(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t M, const float *x,
+                      const float *params, const float *cov_diag, const float *act,
+                      float *out_mu, float *out_logp, void *stream);
+
+/* ---- K2: reward-to-go + advantages -----------------------------------------
+ * Replaces the RTG loop and per-group normalisation of GRPO.learn
+ * (algorithms/grpo.py:66-74, 108-115) and PPO.learn's MC/GAE + global z-scores
+ * (algorithms/ppo.py:100-139).
+ *   rew [T][N], len [N] int32, values [T][N] or NULL (PPO), N = G*E
+ *   -> out_adv [T][N] (zeros in padding), out_rtg [T][N] or NULL
+ *      (GRPO: raw RTG; PPO: z-scored returns = critic targets)
+ *   workspace: tg_advantage_workspace_bytes(N) bytes of device scratch
+ */
+int64_t tg_advantage_workspace_bytes(int64_t N, int G);
+int tg_advantage(tg_ctx *ctx, int mode, int64_t G, int E, int T, double gamma, double lam,
+                 const float *rew, const int32_t *len, const float *values,
+                 float *out_adv, float *out_rtg, void *workspace, void *stream);
+
+/* ---- K3: clipped-surrogate objective + flat gradient ------------------------
+ * Replaces one iteration of the update loop of GRPO.learn
+ * (algorithms/grpo.py:106-145: J = (1/G) sum_g sum_valid min(rho A, clamp(rho) A),
+ * J.backward()) -- and, with a critic, of PPO.learn (algorithms/ppo.py:147-183).
+ *   obs [T][O][N], act [T][A][N], adv [T][N], old_logp [T][N], len [N]
+ *   params: flat actor parameters
+ *   scale : multiplies the objective (GRPO: 1/G_global; PPO: -1/n_valid)
+ *   kl_coef: weight of mean(exp(old)*(old-lp)) (ppo.py:175-176), 0 for GRPO
+ *   -> out_grad [n_params] fp32 (d objective / d params), out_stats [4] fp32:
+ *      {objective, n_valid, sum ratio, n_clipped}
+ *   workspace: tg_policy_grad_workspace_bytes(ctx, mlp) bytes
+ */
+int64_t tg_policy_grad_workspace_bytes(const tg_ctx *ctx, const tg_mlp_cfg *mlp);
+int tg_policy_grad(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T,
+                   const float *obs, const float *act, const float *adv, const float *old_logp,
+                   const int32_t *len, const float *params, const float *cov_diag,
+                   float eps_clip, float scale, float kl_coef,
+                   float *out_grad, float *out_stats, void *workspace, void *stream);
+
+/* Critic regression gradient (ppo.py:168-169: MSELoss(V(obs), rtg_norm)):
+ *   target [T][N]; scale = c1 / n_valid  -> out_grad [n_params(critic)], out_stats[0] = sum sq err */
+int tg_value_grad(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T,
+                  const float *obs, const float *target, const int32_t *len, const float *params,
+                  float scale, float *out_grad, float *out_stats, void *workspace, void *stream);
+
+/* ---- Adam --------------------------------------------------------------------
+ * torch.optim.Adam defaults as the reference constructs it
+ * (pipelines/cartpole_pipeline_grpo.py:65): p -= lr/(1-b1^t) * m/(sqrt(v)/sqrt(1-b2^t)+eps).
+ * `step` is the 1-based step count AFTER this update. */
+int tg_adam_step(tg_ctx *ctx, int64_t n, float *params, const float *grad, float *exp_avg,
+                 float *exp_avg_sq, int64_t step, double lr, double beta1, double beta2, double eps,
+                 void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRAJOPT_GRPO_H */

@@ -1,0 +1,208 @@
+// K2: reward-to-go + advantage normalisation (include/trajopt_grpo.h: tg_advantage).
+//
+// Layout: rew/adv/rtg/values are [T][N] with the env index innermost, so a warp
+// that owns 32 consecutive envs reads/writes one 128 B row segment per step.
+// Each thread owns one env and runs the reverse discounted scan in a register
+// (the time axis is inherently serial per env); group statistics are combined
+// through shared memory in a fixed order (deterministic), in float64.
+//
+// GRPO (grpo.py:66-74,108-115): rtg[t] = r[t] + gamma*rtg[t+1] over the valid
+// prefix; per group g the pool is every valid (episode, step) pair:
+// A = (rtg - mean(rtg)) / std(rtg + 1e-8), unbiased std.  The scan is done twice
+// (statistics pass, normalise pass) so that only rew is read and adv written:
+// 8 B per slot-step when the second read hits L2, 12 B when it does not.
+#include "tg_common.cuh"
+
+#define ADV_THREADS 128
+
+// rtg recurrence with torch's rounding (separate multiply and add, no FMA)
+TG_D float rtg_step(float r, float gamma, float next) { return __fadd_rn(r, __fmul_rn(gamma, next)); }
+
+__global__ void __launch_bounds__(ADV_THREADS)
+adv_grpo_kernel(int64_t G, int E, int T, int GC, float gamma, const float *__restrict__ rew,
+                const int32_t *__restrict__ len, float *__restrict__ adv, float *__restrict__ rtg_out) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int64_t N = G * (int64_t)E;
+    const int64_t g0 = (int64_t)blockIdx.x * GC;
+    const int ng = (int)min((int64_t)GC, G - g0);
+    const int envs = ng * E;
+    const int64_t n0 = g0 * E;
+    double *sx = reinterpret_cast<double *>(sm_raw);  // [envs] sum rtg
+    double *sy = sx + envs;                           // [envs] sum (rtg+1e-8)
+    double *syy = sy + envs;                          // [envs] sum (rtg+1e-8)^2
+    float *gmean = reinterpret_cast<float *>(syy + envs);  // [GC]
+    float *gstd = gmean + GC;                              // [GC]
+
+    // pass 1: per-env scan + statistics
+    for (int i = threadIdx.x; i < envs; i += ADV_THREADS) {
+        const int64_t n = n0 + i;
+        const int L = len[n];
+        float rtg = 0.0f;
+        double ax = 0.0, ay = 0.0, ayy = 0.0;
+#pragma unroll 4
+        for (int t = L - 1; t >= 0; --t) {
+            rtg = rtg_step(rew[(int64_t)t * N + n], gamma, rtg);
+            const double y = (double)__fadd_rn(rtg, 1e-8f);
+            ax += (double)rtg;
+            ay += y;
+            ayy += y * y;
+        }
+        sx[i] = ax; sy[i] = ay; syy[i] = ayy;
+    }
+    __syncthreads();
+    if (threadIdx.x < ng) {
+        const int g = threadIdx.x;
+        double ax = 0.0, ay = 0.0, ayy = 0.0;
+        int64_t cnt = 0;
+        for (int e = 0; e < E; ++e) {
+            ax += sx[g * E + e]; ay += sy[g * E + e]; ayy += syy[g * E + e];
+            cnt += len[n0 + (int64_t)g * E + e];
+        }
+        const double mean = ax / (double)cnt;                  // cnt==0 -> NaN, as torch.mean of empty
+        const double my = ay / (double)cnt;
+        const double var = (ayy - ay * my) / (double)(cnt - 1);  // unbiased; cnt==1 -> 0/0 = NaN
+        gmean[g] = (float)mean;
+        gstd[g] = (float)sqrt(var > 0.0 || var != var ? var : 0.0);
+    }
+    __syncthreads();
+    // pass 2: rescan and normalise; zero the padding
+    for (int i = threadIdx.x; i < envs; i += ADV_THREADS) {
+        const int64_t n = n0 + i;
+        const int L = len[n];
+        const float mean = gmean[i / E], sd = gstd[i / E];
+        for (int t = T - 1; t >= L; --t) {
+            adv[(int64_t)t * N + n] = 0.0f;
+            if (rtg_out) rtg_out[(int64_t)t * N + n] = 0.0f;
+        }
+        float rtg = 0.0f;
+#pragma unroll 4
+        for (int t = L - 1; t >= 0; --t) {
+            rtg = rtg_step(rew[(int64_t)t * N + n], gamma, rtg);
+            adv[(int64_t)t * N + n] = __fdiv_rn(__fsub_rn(rtg, mean), sd);
+            if (rtg_out) rtg_out[(int64_t)t * N + n] = rtg;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// PPO (ppo.py:93-139): advantages from MC returns or GAE with a critic baseline,
+// then GLOBAL z-scores (unbiased std, +1e-8 on the denominator) of both the
+// advantages and the returns over every valid step.
+//   stage 1: per-env scan -> raw adv/rtg rows + per-block partial sums
+//   stage 2: one block combines the partials in a fixed order -> 4 scalars
+//   stage 3: normalise in place
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(ADV_THREADS)
+adv_ppo_scan_kernel(int64_t N, int T, int gae, float gamma, float gamlam, const float *__restrict__ rew,
+                    const int32_t *__restrict__ len, const float *__restrict__ val, float *__restrict__ adv,
+                    float *__restrict__ rtg_out, double *__restrict__ partial) {
+    __shared__ double red[5][ADV_THREADS];
+    const int64_t n = (int64_t)blockIdx.x * ADV_THREADS + threadIdx.x;
+    double sa = 0, saa = 0, sr = 0, srr = 0, cnt = 0;
+    if (n < N) {
+        const int L = len[n];
+        for (int t = T - 1; t >= L; --t) {
+            adv[(int64_t)t * N + n] = 0.0f;
+            rtg_out[(int64_t)t * N + n] = 0.0f;
+        }
+        float rtg = 0.0f, a_next = 0.0f, v_next = 0.0f;
+        for (int t = L - 1; t >= 0; --t) {
+            const float r = rew[(int64_t)t * N + n];
+            const float v = val[(int64_t)t * N + n];
+            float a, ret;
+            if (!gae) {
+                rtg = rtg_step(r, gamma, rtg);            // ppo.py:103-108
+                ret = rtg;
+                a = __fsub_rn(rtg, v);                    // :111
+            } else {
+                // :114-123 (masks are prefix masks: next value/advantage are 0 past the end)
+                const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(gamma, v_next)), v);
+                a = (t == T - 1) ? __fsub_rn(r, v) : __fadd_rn(delta, __fmul_rn(gamlam, a_next));
+                ret = __fadd_rn(v, a);                    // :124
+                a_next = a;
+                v_next = v;
+            }
+            adv[(int64_t)t * N + n] = a;
+            rtg_out[(int64_t)t * N + n] = ret;
+            sa += a; saa += (double)a * a; sr += ret; srr += (double)ret * ret;
+        }
+        cnt = (double)L;
+    }
+    red[0][threadIdx.x] = sa; red[1][threadIdx.x] = saa; red[2][threadIdx.x] = sr; red[3][threadIdx.x] = srr;
+    red[4][threadIdx.x] = cnt;
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double s = 0.0;
+        for (int i = 0; i < ADV_THREADS; ++i) s += red[threadIdx.x][i];
+        partial[(int64_t)blockIdx.x * 5 + threadIdx.x] = s;
+    }
+}
+
+__global__ void adv_ppo_stats_kernel(int nblocks, const double *__restrict__ partial, float *__restrict__ stats) {
+    // single thread, fixed order: nblocks is N/128, a few thousand adds
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s[5] = {0, 0, 0, 0, 0};
+        for (int b = 0; b < nblocks; ++b)
+            for (int k = 0; k < 5; ++k) s[k] += partial[(int64_t)b * 5 + k];
+        const double n = s[4];
+        const double ma = s[0] / n, mr = s[2] / n;
+        const double va = (s[1] - s[0] * ma) / (n - 1.0), vr = (s[3] - s[2] * mr) / (n - 1.0);
+        stats[0] = (float)ma;
+        stats[1] = (float)sqrt(va > 0.0 || va != va ? va : 0.0);
+        stats[2] = (float)mr;
+        stats[3] = (float)sqrt(vr > 0.0 || vr != vr ? vr : 0.0);
+    }
+}
+
+__global__ void __launch_bounds__(ADV_THREADS)
+adv_ppo_norm_kernel(int64_t N, int T, const int32_t *__restrict__ len, const float *__restrict__ stats,
+                    float *__restrict__ adv, float *__restrict__ rtg) {
+    const int64_t n = (int64_t)blockIdx.x * ADV_THREADS + threadIdx.x;
+    if (n >= N) return;
+    const int L = len[n];
+    const float ma = stats[0], sa = __fadd_rn(stats[1], 1e-8f), mr = stats[2], sr = __fadd_rn(stats[3], 1e-8f);
+    for (int t = 0; t < L; ++t) {
+        const int64_t i = (int64_t)t * N + n;
+        adv[i] = __fdiv_rn(__fsub_rn(adv[i], ma), sa);    // ppo.py:138
+        rtg[i] = __fdiv_rn(__fsub_rn(rtg[i], mr), sr);    // ppo.py:139
+    }
+}
+
+extern "C" int64_t tg_advantage_workspace_bytes(int64_t N, int G) {
+    (void)G;
+    const int64_t blocks = (N + ADV_THREADS - 1) / ADV_THREADS;
+    return blocks * 5 * (int64_t)sizeof(double) + 64;
+}
+
+extern "C" int tg_advantage(tg_ctx *ctx, int mode, int64_t G, int E, int T, double gamma, double lam, const float *rew,
+                            const int32_t *len, const float *values, float *out_adv, float *out_rtg, void *workspace,
+                            void *stream) {
+    TG_REQUIRE(ctx && rew && len && out_adv, TG_ERR_ARG, "tg_advantage: null argument");
+    TG_REQUIRE(G > 0 && E > 0 && T > 0, TG_ERR_SHAPE, "tg_advantage: G, E, T must be positive");
+    TG_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t N = G * (int64_t)E;
+    if (mode == TG_ADV_GRPO) {
+        const int GC = E >= ADV_THREADS ? 1 : ADV_THREADS / E;
+        const size_t smem = (size_t)GC * E * 3 * sizeof(double) + (size_t)GC * 2 * sizeof(float);
+        TG_REQUIRE(smem <= (size_t)ctx->smem_optin, TG_ERR_UNSUPPORTED, "group size %d too large", E);
+        if (smem > 48 * 1024)
+            TG_CUDA(cudaFuncSetAttribute(adv_grpo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)((G + GC - 1) / GC);
+        adv_grpo_kernel<<<grid, ADV_THREADS, smem, st>>>(G, E, T, GC, (float)gamma, rew, len, out_adv, out_rtg);
+        TG_CUDA(cudaGetLastError());
+        return TG_OK;
+    }
+    TG_REQUIRE(mode == TG_ADV_PPO_MC || mode == TG_ADV_PPO_GAE, TG_ERR_ARG, "unknown advantage mode %d", mode);
+    TG_REQUIRE(values && out_rtg && workspace, TG_ERR_ARG, "PPO advantages need values, out_rtg and workspace");
+    const unsigned grid = (unsigned)((N + ADV_THREADS - 1) / ADV_THREADS);
+    double *partial = reinterpret_cast<double *>(workspace);
+    float *stats = reinterpret_cast<float *>(partial + (size_t)grid * 5);
+    adv_ppo_scan_kernel<<<grid, ADV_THREADS, 0, st>>>(N, T, mode == TG_ADV_PPO_GAE, (float)gamma,
+                                                       (float)(gamma * lam), rew, len, values,
+                                                       out_adv, out_rtg, partial);
+    adv_ppo_stats_kernel<<<1, 32, 0, st>>>((int)grid, partial, stats);
+    adv_ppo_norm_kernel<<<grid, ADV_THREADS, 0, st>>>(N, T, len, stats, out_adv, out_rtg);
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}

@@ -1,0 +1,176 @@
+// Context, error reporting, MLP staging layout and the weight pack kernel.
+#include <stdarg.h>
+
+#include "tg_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void tg_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *tg_last_error(void) { return g_err; }
+extern "C" int tg_abi_version(void) { return TG_ABI_VERSION; }
+
+extern "C" int tg_ctx_create(int device, tg_ctx **out) {
+    TG_REQUIRE(out != nullptr, TG_ERR_ARG, "tg_ctx_create: out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        tg_set_error("no CUDA device available (%s); this engine has no CPU fallback",
+                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return TG_ERR_NO_DEVICE;
+    }
+    TG_REQUIRE(device >= 0 && device < count, TG_ERR_ARG, "device %d out of range [0,%d)", device, count);
+    cudaDeviceProp prop;
+    TG_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        tg_set_error("device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
+        return TG_ERR_NO_DEVICE;
+    }
+    tg_ctx *c = new tg_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    c->packed = nullptr;
+    c->packed_cap = 0;
+    *out = c;
+    return TG_OK;
+}
+
+extern "C" void tg_ctx_destroy(tg_ctx *ctx) {
+    if (!ctx) return;
+    if (ctx->packed) {
+        cudaSetDevice(ctx->device);
+        cudaFree(ctx->packed);
+    }
+    delete ctx;
+}
+
+extern "C" int tg_ctx_sm_count(const tg_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+int tg_ctx_reserve_packed(tg_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->packed_cap) return TG_OK;
+    TG_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->packed) {
+        TG_CUDA(cudaDeviceSynchronize());
+        TG_CUDA(cudaFree(ctx->packed));
+        ctx->packed = nullptr;
+        ctx->packed_cap = 0;
+    }
+    TG_CUDA(cudaMalloc(&ctx->packed, bytes));
+    ctx->packed_cap = bytes;
+    return TG_OK;
+}
+
+extern "C" int tg_env_dims(int kind, int *obs_dim, int *act_dim) {
+    static const int O[4] = {5, 3, 10, 20}, A[4] = {1, 1, 2, 4};
+    if (kind < 0 || kind > 3) {
+        tg_set_error("unknown env kind %d", kind);
+        return TG_ERR_ARG;
+    }
+    if (obs_dim) *obs_dim = O[kind];
+    if (act_dim) *act_dim = A[kind];
+    return TG_OK;
+}
+
+extern "C" int64_t tg_mlp_param_count(const tg_mlp_cfg *mlp) {
+    if (!mlp || mlp->n_layers < 1 || mlp->n_layers > TG_MAX_LAYERS) return -1;
+    int64_t n = 0;
+    for (int l = 0; l < mlp->n_layers; ++l) n += (int64_t)mlp->dims[l] * mlp->dims[l + 1] + mlp->dims[l + 1];
+    return n;
+}
+
+int tg_build_layout(const tg_mlp_cfg *mlp, bool with_backward, tg_mlp_layout *out) {
+    TG_REQUIRE(mlp != nullptr, TG_ERR_ARG, "mlp cfg is null");
+    TG_REQUIRE(mlp->n_layers >= 1 && mlp->n_layers <= TG_MAX_LAYERS, TG_ERR_SHAPE, "n_layers %d not in [1,%d]",
+               mlp->n_layers, TG_MAX_LAYERS);
+    TG_REQUIRE(mlp->activation >= 0 && mlp->activation <= 2, TG_ERR_ARG, "unknown activation %d", mlp->activation);
+    const int nl = mlp->n_layers;
+    TG_REQUIRE(mlp->dims[0] >= 1 && mlp->dims[0] <= TG_MAX_WIDTH, TG_ERR_SHAPE, "input dim %d out of range", mlp->dims[0]);
+    TG_REQUIRE(mlp->dims[nl] >= 1 && mlp->dims[nl] <= TG_MAX_ACT, TG_ERR_SHAPE, "output dim %d not in [1,%d]",
+               mlp->dims[nl], TG_MAX_ACT);
+    int maxh = 0, kmax = mlp->dims[0];
+    for (int l = 1; l < nl; ++l) {
+        TG_REQUIRE(mlp->dims[l] >= 1, TG_ERR_SHAPE, "hidden dim must be positive");
+        maxh = mlp->dims[l] > maxh ? mlp->dims[l] : maxh;
+        kmax = mlp->dims[l] > kmax ? mlp->dims[l] : kmax;
+    }
+    TG_REQUIRE(maxh <= TG_MAX_WIDTH, TG_ERR_UNSUPPORTED, "hidden width %d > %d is not supported", maxh, TG_MAX_WIDTH);
+    memset(out, 0, sizeof(*out));
+    out->n_layers = nl;
+    out->act = mlp->activation;
+    out->cfg = maxh <= 64 ? 0 : (maxh <= 128 ? 1 : 2);
+    out->B = out->cfg == 2 ? 64 : 128;
+    out->NT = out->cfg == 0 ? 128 : 256;
+    out->NP = out->cfg == 0 ? 64 : (out->cfg == 1 ? 128 : 256);
+    out->O = mlp->dims[0];
+    out->A = mlp->dims[nl];
+    // hidden outputs are stored for NP (padded) neurons, so the buffers need NP rows
+    out->kmax = nl > 1 ? (out->NP > kmax ? out->NP : kmax) : kmax;
+    int64_t off = 0, flat = 0;
+    for (int l = 0; l < nl; ++l) {
+        tg_layer_layout &L = out->L[l];
+        L.K = mlp->dims[l];
+        L.N = mlp->dims[l + 1];
+        L.flat_w = flat;
+        flat += (int64_t)L.K * L.N + L.N;
+        L.wn = -1;
+        L.KP = out->NP;
+        if (l < nl - 1) {
+            L.wt = off; off += (int64_t)L.K * out->NP;
+            L.bias = off; off += out->NP;
+            if (with_backward && l >= 1) { L.wn = off; off += (int64_t)L.N * out->NP; }
+        } else {
+            L.wt = off; off += tg_round_up(L.N * L.K, 4);
+            L.bias = off; off += 4;
+        }
+    }
+    out->total = off;
+    out->n_params = flat;
+    return TG_OK;
+}
+
+__global__ void pack_kernel(tg_mlp_layout lay, const float *__restrict__ params, float *__restrict__ packed) {
+    const int nl = lay.n_layers, NP = lay.NP;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < lay.total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float v = 0.0f;
+        for (int l = 0; l < nl; ++l) {
+            const tg_layer_layout &L = lay.L[l];
+            const float *Wf = params + L.flat_w;          // [N][K] torch layout
+            const float *bf = Wf + (int64_t)L.N * L.K;
+            if (l < nl - 1) {
+                if (i >= L.wt && i < L.wt + (int64_t)L.K * NP) {
+                    const int k = (int)((i - L.wt) / NP), n = (int)((i - L.wt) % NP);
+                    v = n < L.N ? Wf[(int64_t)n * L.K + k] : 0.0f;
+                } else if (i >= L.bias && i < L.bias + NP) {
+                    const int n = (int)(i - L.bias);
+                    v = n < L.N ? bf[n] : 0.0f;
+                } else if (L.wn >= 0 && i >= L.wn && i < L.wn + (int64_t)L.N * NP) {
+                    const int n = (int)((i - L.wn) / NP), k = (int)((i - L.wn) % NP);
+                    v = k < L.K ? Wf[(int64_t)n * L.K + k] : 0.0f;
+                }
+            } else {
+                if (i >= L.wt && i < L.wt + (int64_t)L.N * L.K) v = Wf[i - L.wt];
+                else if (i >= L.bias && i < L.bias + L.N) v = bf[i - L.bias];
+            }
+        }
+        packed[i] = v;
+    }
+}
+
+int tg_pack_weights(tg_ctx *ctx, const tg_mlp_layout &lay, const float *params, cudaStream_t st) {
+    int rc = tg_ctx_reserve_packed(ctx, (size_t)lay.total * sizeof(float));
+    if (rc) return rc;
+    const int threads = 256;
+    int64_t blocks = (lay.total + threads - 1) / threads;
+    if (blocks > 1024) blocks = 1024;
+    pack_kernel<<<(unsigned)blocks, threads, 0, st>>>(lay, params, ctx->packed);
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}

@@ -1,0 +1,75 @@
+// Shared host/device definitions for the sm_100a engine behind include/trajopt_grpo.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/trajopt_grpo.h"
+
+#define TG_HD __host__ __device__ __forceinline__
+#define TG_D __device__ __forceinline__
+
+// ---- error plumbing ---------------------------------------------------------
+void tg_set_error(const char *fmt, ...);
+#define TG_CUDA(expr)                                                              \
+    do {                                                                           \
+        cudaError_t _e = (expr);                                                   \
+        if (_e != cudaSuccess) {                                                   \
+            tg_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return (int)_e;                                                        \
+        }                                                                          \
+    } while (0)
+#define TG_REQUIRE(cond, code, ...)                                                \
+    do {                                                                           \
+        if (!(cond)) {                                                             \
+            tg_set_error(__VA_ARGS__);                                             \
+            return (code);                                                         \
+        }                                                                          \
+    } while (0)
+
+struct tg_ctx {
+    int device;
+    int sm_count;
+    int smem_optin;  // max dynamic shared memory per block (bytes)
+    float *packed;   // staged (transposed / padded) policy weights, device
+    size_t packed_cap;
+};
+int tg_ctx_reserve_packed(tg_ctx *ctx, size_t bytes);
+
+// ---- MLP tile configurations --------------------------------------------------
+// A CTA advances B environments (rollout) / B samples (update) at a time with NT
+// threads; the hidden GEMMs use an 8x8 register tile per thread, threads laid out
+// (B/8) x (NT/(B/8)), so one pass covers NP = NT/(B/8)*8 neurons.
+//   cfg 0: B=128 NT=128 NP= 64   hidden width <= 64
+//   cfg 1: B=128 NT=256 NP=128   hidden width <= 128
+//   cfg 2: B= 64 NT=256 NP=256   hidden width <= 256
+template <int CFG> struct TileCfg;
+template <> struct TileCfg<0> { static constexpr int B = 128, NT = 128, NP = 64; };
+template <> struct TileCfg<1> { static constexpr int B = 128, NT = 256, NP = 128; };
+template <> struct TileCfg<2> { static constexpr int B = 64, NT = 256, NP = 256; };
+
+// Staged weight layout (built on the device by tg_pack_kernel from the flat
+// torch-order vector).  For every hidden Linear l (input K_l, output N_l<=NP):
+//   Wt[K_l][NP]  k-major copy, zero padded to NP neurons (forward operand)
+//   bias[NP]
+//   Wn[N_l][NPK] n-major copy (torch layout), rows padded to NPK=roundup(K_l,8)... (backward-data operand)
+// and for the output Linear (K_L -> A): Wo[A][K_L] (torch layout) + bo[A] padded to 4.
+struct tg_layer_layout {
+    int K, N;          // true dims
+    int64_t flat_w;    // offset of W (and flat_w + N*K = bias) in the flat vector
+    int64_t wt, bias;  // offsets (floats) in the staged buffer
+    int64_t wn;        // n-major copy [N][KP] (update kernels only), -1 if absent
+    int KP;            // padded K of the n-major copy
+};
+struct tg_mlp_layout {
+    int n_layers, act, cfg, NP, B, NT;
+    int O, A, kmax;  // kmax = max input width over layers (activation buffer rows)
+    tg_layer_layout L[TG_MAX_LAYERS];
+    int64_t total;   // floats in the staged buffer
+    int64_t n_params;
+};
+int tg_build_layout(const tg_mlp_cfg *mlp, bool with_backward, tg_mlp_layout *out);
+int tg_pack_weights(tg_ctx *ctx, const tg_mlp_layout &lay, const float *params, cudaStream_t st);
+
+TG_HD int tg_round_up(int x, int m) { return (x + m - 1) / m * m; }

@@ -1,0 +1,361 @@
+// K1: fused policy-in-the-loop rollout (include/trajopt_grpo.h: tg_rollout),
+// plus the batched single-step kernels (tg_env_step, tg_quadrotor12_dynamics)
+// and the Philox noise materialiser (tg_noise_fill).
+//
+// One CTA advances a tile of B environments through all T steps:
+//   * the staged policy weights are copied ONCE into shared memory by the TMA
+//     bulk engine (cp.async.bulk + mbarrier) and stay resident;
+//   * each environment's state lives in the registers of its owner thread
+//     (threadIdx.x < B) for the whole episode;
+//   * per step: owners publish fp32 obs to shared memory and to the [T][O][N]
+//     trajectory (coalesced: env index innermost), the CTA runs the MLP as
+//     register-tiled fp32 GEMMs over the tile, owners sample the action from
+//     the supplied/Philox noise, integrate the dynamics, and write
+//     act/logp/reward rows;
+//   * finished environments idle (zero rows) until every env of the tile is
+//     done, then the CTA only zero-fills the remaining rows.
+#include <math.h>
+
+#include "tg_env.cuh"
+#include "tg_mlp.cuh"
+
+struct RolloutArgs {
+    EnvParams env;
+    tg_mlp_layout lay;
+    int64_t N;
+    const void *init_state;
+    const float *packed;
+    const float *noise;
+    uint64_t seed;
+    int64_t env_offset;
+    float sd[TG_MAX_ACT], log_norm;
+    float *obs, *act, *rew, *logp, *ret;
+    int32_t *len;
+};
+
+template <int KIND, typename R, int CFG, bool WG>
+__global__ void __launch_bounds__(TileCfg<CFG>::NT) rollout_kernel(const __grid_constant__ RolloutArgs a) {
+    using E = Env<KIND>;
+    constexpr int B = TileCfg<CFG>::B, NT = TileCfg<CFG>::NT, LDX = B + 4;
+    constexpr int S = E::S, A = E::A;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t wbar;
+    float *Ws = reinterpret_cast<float *>(smem_raw);
+    float *Xa = Ws + (WG ? 0 : a.lay.total);
+    float *Xb = Xa + (size_t)a.lay.kmax * LDX;
+    float *P = Xb + (size_t)a.lay.kmax * LDX;
+    const float *W = WG ? a.packed : Ws;
+    if (!WG) stage_weights_tma(Ws, a.packed, a.lay.total, &wbar);
+
+    const int T = a.env.max_steps;
+    const int64_t N = a.N;
+    const int64_t n = (int64_t)blockIdx.x * B + threadIdx.x;
+    const bool owner = threadIdx.x < B;
+    const bool real_env = owner && n < N;
+    bool alive = real_env;
+    R s[S];
+    int steps = 0, bal = 0;
+    float ret = 0.0f;
+    if (real_env) {
+        const R *init = reinterpret_cast<const R *>(a.init_state);
+#pragma unroll
+        for (int i = 0; i < S; ++i) s[i] = init[(int64_t)i * N + n];
+    } else {
+#pragma unroll
+        for (int i = 0; i < S; ++i) s[i] = (R)0;
+    }
+    const int nl = a.lay.n_layers;
+    int t = 0;
+    for (; t < T; ++t) {
+        // 1. publish the observation (stored BEFORE acting, rollout_worker.py:53)
+        if (owner) {
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                const float o = alive ? (float)s[i] : 0.0f;
+                Xa[i * LDX + threadIdx.x] = o;
+                if (real_env) a.obs[((int64_t)t * S + i) * N + n] = o;
+            }
+        }
+        __syncthreads();
+        // 2. hidden layers (ping-pong Xa <-> Xb)
+        float *xin = Xa, *xout = Xb;
+        for (int l = 0; l < nl - 1; ++l) {
+            tile_layer<CFG, 0, WG>(W + a.lay.L[l].wt, W + a.lay.L[l].bias, xin, xout, a.lay.L[l].K, a.lay.act);
+            __syncthreads();
+            float *tmp = xin; xin = xout; xout = tmp;
+        }
+        // 3. output layer -> mean action for the owner's env
+        float mu[A];
+        tile_output_layer<CFG, A, WG>(W + a.lay.L[nl - 1].wt, W + a.lay.L[nl - 1].bias, xin, P, a.lay.L[nl - 1].K, mu);
+        // 4. sample, step the env, write the trajectory rows
+        if (owner) {
+            float act[A], lp = 0.0f, rw = 0.0f;
+            if (alive) {
+                float eps[4];
+                if (a.noise != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < A; ++j) eps[j] = a.noise[((int64_t)t * A + j) * N + n];
+                } else {
+                    philox_normal4(a.seed, (uint64_t)(a.env_offset + n), (uint32_t)t, eps);
+                }
+                float m2 = 0.0f;
+#pragma unroll
+                for (int j = 0; j < A; ++j) {
+                    act[j] = mu[j] + a.sd[j] * eps[j];          // MultivariateNormal.rsample
+                    const float z = (act[j] - mu[j]) / a.sd[j];
+                    m2 += z * z;
+                }
+                lp = -0.5f * m2 - a.log_norm;
+                R r;
+                const bool done = E::template step<R>(s, act, a.env, steps, bal, r);
+                rw = (float)r;
+                ret += rw;
+                steps += 1;
+                alive = !done;
+            } else {
+#pragma unroll
+                for (int j = 0; j < A; ++j) act[j] = 0.0f;
+            }
+            if (real_env) {
+#pragma unroll
+                for (int j = 0; j < A; ++j) a.act[((int64_t)t * A + j) * N + n] = act[j];
+                a.rew[(int64_t)t * N + n] = rw;
+                if (a.logp) a.logp[(int64_t)t * N + n] = lp;
+            }
+        }
+        // 5. tile-wide early exit; also the barrier that protects Xa/Xb/P reuse
+        if (!__syncthreads_or(alive ? 1 : 0)) { ++t; break; }
+    }
+    // zero-fill the rows after every env of the tile finished (rollout_worker.py:64-68 padding)
+    if (real_env) {
+        for (; t < T; ++t) {
+#pragma unroll
+            for (int i = 0; i < S; ++i) a.obs[((int64_t)t * S + i) * N + n] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < A; ++j) a.act[((int64_t)t * A + j) * N + n] = 0.0f;
+            a.rew[(int64_t)t * N + n] = 0.0f;
+            if (a.logp) a.logp[(int64_t)t * N + n] = 0.0f;
+        }
+        a.len[n] = steps;
+        if (a.ret) a.ret[n] = ret;
+    }
+}
+
+template <int KIND, typename R, int CFG, bool WG>
+static int launch_rollout(const RolloutArgs &a, size_t smem, cudaStream_t st) {
+    constexpr int B = TileCfg<CFG>::B, NT = TileCfg<CFG>::NT;
+    auto kern = rollout_kernel<KIND, R, CFG, WG>;
+    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((a.N + B - 1) / B);
+    kern<<<grid, NT, smem, st>>>(a);
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}
+
+template <int KIND, typename R>
+static int dispatch_cfg(const RolloutArgs &a, size_t smem, bool wg, cudaStream_t st) {
+    if (wg) {
+        switch (a.lay.cfg) {
+            case 0: return launch_rollout<KIND, R, 0, true>(a, smem, st);
+            case 1: return launch_rollout<KIND, R, 1, true>(a, smem, st);
+            default: return launch_rollout<KIND, R, 2, true>(a, smem, st);
+        }
+    }
+    switch (a.lay.cfg) {
+        case 0: return launch_rollout<KIND, R, 0, false>(a, smem, st);
+        case 1: return launch_rollout<KIND, R, 1, false>(a, smem, st);
+        default: return launch_rollout<KIND, R, 2, false>(a, smem, st);
+    }
+}
+
+template <int KIND>
+static int dispatch_prec(int precision, const RolloutArgs &a, size_t smem, bool wg, cudaStream_t st) {
+    return precision == TG_PREC_F64 ? dispatch_cfg<KIND, double>(a, smem, wg, st)
+                                    : dispatch_cfg<KIND, float>(a, smem, wg, st);
+}
+
+static int fill_env_params(const tg_env_cfg *env, EnvParams *p) {
+    TG_REQUIRE(env != nullptr, TG_ERR_ARG, "env cfg is null");
+    TG_REQUIRE(env->kind >= 0 && env->kind <= 3, TG_ERR_ARG, "unknown env kind %d", env->kind);
+    TG_REQUIRE(env->max_steps > 0 && env->dt > 0, TG_ERR_SHAPE, "max_steps and dt must be positive");
+    p->dt = env->dt;
+    p->max_steps = env->max_steps;
+    p->time_limit_step = env->time_limit_step;
+    p->balanced_limit = env->balanced_limit;
+    return TG_OK;
+}
+
+extern "C" int tg_rollout(tg_ctx *ctx, const tg_env_cfg *env, const tg_mlp_cfg *mlp, int precision, int64_t N,
+                          const void *init_state, const float *params, const float *cov_diag, const float *noise,
+                          uint64_t seed, int64_t env_offset, float *out_obs, float *out_act, float *out_rew, float *out_logp,
+                          int32_t *out_len, float *out_ret, void *stream) {
+    TG_REQUIRE(ctx && env && mlp && init_state && params && cov_diag && out_obs && out_act && out_rew && out_len,
+               TG_ERR_ARG, "tg_rollout: null argument");
+    TG_REQUIRE(N > 0, TG_ERR_SHAPE, "tg_rollout: N must be positive");
+    TG_REQUIRE(precision == TG_PREC_F32 || precision == TG_PREC_F64, TG_ERR_ARG, "bad precision %d", precision);
+    RolloutArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = fill_env_params(env, &a.env);
+    if (rc) return rc;
+    int O, A;
+    tg_env_dims(env->kind, &O, &A);
+    TG_REQUIRE(mlp->n_layers >= 1 && mlp->dims[0] == O && mlp->dims[mlp->n_layers] == A, TG_ERR_SHAPE,
+               "policy dims (%d -> %d) do not match env obs/act dims (%d/%d)", mlp->dims[0],
+               mlp->dims[mlp->n_layers > 0 ? mlp->n_layers : 0], O, A);
+    rc = tg_build_layout(mlp, false, &a.lay);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    TG_CUDA(cudaSetDevice(ctx->device));
+    rc = tg_pack_weights(ctx, a.lay, params, st);
+    if (rc) return rc;
+    a.N = N;
+    a.init_state = init_state;
+    a.packed = ctx->packed;
+    a.noise = noise;
+    a.seed = seed;
+    a.env_offset = env_offset;
+    double ln = 0.5 * A * log(2.0 * M_PI);
+    for (int j = 0; j < A; ++j) {
+        TG_REQUIRE(cov_diag[j] > 0.0f, TG_ERR_ARG, "cov_diag[%d] must be positive", j);
+        a.sd[j] = sqrtf(cov_diag[j]);                      // cholesky(diag(c)) = diag(sqrt(c)), fp32 as torch
+        ln += (double)logf(a.sd[j]);
+    }
+    a.log_norm = (float)ln;
+    a.obs = out_obs; a.act = out_act; a.rew = out_rew; a.logp = out_logp; a.len = out_len; a.ret = out_ret;
+    const int B = a.lay.B, NT = a.lay.NT;
+    const size_t act_bytes = (2 * (size_t)a.lay.kmax * (B + 4) + (size_t)(NT / B) * TG_MAX_ACT * B) * sizeof(float);
+    size_t smem = act_bytes + (size_t)a.lay.total * sizeof(float);
+    // weights resident in shared memory when they fit next to the activation
+    // tiles; otherwise they stay in global memory (read-only path, L2-resident)
+    const bool wg = smem > (size_t)ctx->smem_optin;
+    if (wg) smem = act_bytes;
+    TG_REQUIRE(smem <= (size_t)ctx->smem_optin, TG_ERR_UNSUPPORTED, "activation tiles need %zu B of shared memory", smem);
+    switch (env->kind) {
+        case TG_ENV_CARTPOLE: return dispatch_prec<TG_ENV_CARTPOLE>(precision, a, smem, wg, st);
+        case TG_ENV_PENDULUM: return dispatch_prec<TG_ENV_PENDULUM>(precision, a, smem, wg, st);
+        case TG_ENV_QUADPOLE2D: return dispatch_prec<TG_ENV_QUADPOLE2D>(precision, a, smem, wg, st);
+        default: return dispatch_prec<TG_ENV_QUADPOLE>(precision, a, smem, wg, st);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// tg_noise_fill
+// ---------------------------------------------------------------------------
+__global__ void noise_fill_kernel(uint64_t seed, int64_t env_offset, int64_t N, int T, int A, float *out) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    if (n >= N) return;
+    float z[4];
+    philox_normal4(seed, (uint64_t)(env_offset + n), (uint32_t)t, z);
+    for (int j = 0; j < A; ++j) out[((int64_t)t * A + j) * N + n] = z[j];
+}
+
+extern "C" int tg_noise_fill(tg_ctx *ctx, uint64_t seed, int64_t env_offset, int64_t N, int T, int A, float *noise,
+                             void *stream) {
+    TG_REQUIRE(ctx && noise, TG_ERR_ARG, "tg_noise_fill: null argument");
+    TG_REQUIRE(N > 0 && T > 0 && T <= 65535 && A >= 1 && A <= 4, TG_ERR_SHAPE, "tg_noise_fill: bad shape");
+    TG_CUDA(cudaSetDevice(ctx->device));
+    dim3 grid((unsigned)((N + 255) / 256), (unsigned)T);
+    noise_fill_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seed, env_offset, N, T, A, noise);
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// tg_env_step: one Env.step for N independent envs
+// ---------------------------------------------------------------------------
+template <int KIND, typename R>
+__global__ void env_step_kernel(EnvParams p, int64_t N, const R *state, const float *raw_action,
+                                const int32_t *steps_done, const int32_t *bal_in, R *next, R *reward, int32_t *done,
+                                int32_t *bal_out) {
+    using E = Env<KIND>;
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    R s[E::S];
+    float a[E::A];
+#pragma unroll
+    for (int i = 0; i < E::S; ++i) s[i] = state[(int64_t)i * N + n];
+#pragma unroll
+    for (int j = 0; j < E::A; ++j) a[j] = raw_action[(int64_t)j * N + n];
+    int bal = bal_in ? bal_in[n] : 0;
+    R r;
+    const bool d = E::template step<R>(s, a, p, steps_done ? steps_done[n] : 0, bal, r);
+#pragma unroll
+    for (int i = 0; i < E::S; ++i) next[(int64_t)i * N + n] = s[i];
+    reward[n] = r;
+    done[n] = d ? 1 : 0;
+    if (bal_out) bal_out[n] = bal;
+}
+
+template <int KIND>
+static int launch_env_step(int precision, const EnvParams &p, int64_t N, const void *state, const float *raw_action,
+                           const int32_t *steps_done, const int32_t *bal, void *next, void *reward, int32_t *done,
+                           int32_t *bal_out, cudaStream_t st) {
+    const unsigned grid = (unsigned)((N + 127) / 128);
+    if (precision == TG_PREC_F64)
+        env_step_kernel<KIND, double><<<grid, 128, 0, st>>>(p, N, (const double *)state, raw_action, steps_done, bal,
+                                                            (double *)next, (double *)reward, done, bal_out);
+    else
+        env_step_kernel<KIND, float><<<grid, 128, 0, st>>>(p, N, (const float *)state, raw_action, steps_done, bal,
+                                                           (float *)next, (float *)reward, done, bal_out);
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}
+
+extern "C" int tg_env_step(tg_ctx *ctx, const tg_env_cfg *env, int precision, int64_t N, const void *state,
+                           const float *raw_action, const int32_t *steps_done, const int32_t *bal_count,
+                           void *next_state, void *reward, int32_t *done, int32_t *bal_out, void *stream) {
+    TG_REQUIRE(ctx && env && state && raw_action && next_state && reward && done, TG_ERR_ARG,
+               "tg_env_step: null argument");
+    TG_REQUIRE(N > 0, TG_ERR_SHAPE, "tg_env_step: N must be positive");
+    TG_REQUIRE(precision == TG_PREC_F32 || precision == TG_PREC_F64, TG_ERR_ARG, "bad precision %d", precision);
+    EnvParams p;
+    int rc = fill_env_params(env, &p);
+    if (rc) return rc;
+    TG_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (env->kind) {
+        case TG_ENV_CARTPOLE:
+            return launch_env_step<TG_ENV_CARTPOLE>(precision, p, N, state, raw_action, steps_done, bal_count,
+                                                    next_state, reward, done, bal_out, st);
+        case TG_ENV_PENDULUM:
+            return launch_env_step<TG_ENV_PENDULUM>(precision, p, N, state, raw_action, steps_done, bal_count,
+                                                    next_state, reward, done, bal_out, st);
+        case TG_ENV_QUADPOLE2D:
+            return launch_env_step<TG_ENV_QUADPOLE2D>(precision, p, N, state, raw_action, steps_done, bal_count,
+                                                      next_state, reward, done, bal_out, st);
+        default:
+            return launch_env_step<TG_ENV_QUADPOLE>(precision, p, N, state, raw_action, steps_done, bal_count,
+                                                    next_state, reward, done, bal_out, st);
+    }
+}
+
+template <typename R>
+__global__ void quadrotor12_kernel(int64_t N, R dt, const R *state, const R *control, R *next) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    R s[12], u[4];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s[i] = state[(int64_t)i * N + n];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[i] = control[(int64_t)i * N + n];
+    quadrotor12_step<R>(s, u, dt);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) next[(int64_t)i * N + n] = s[i];
+}
+
+extern "C" int tg_quadrotor12_dynamics(tg_ctx *ctx, int precision, int64_t N, double dt, const void *state,
+                                       const void *control, void *next, void *stream) {
+    TG_REQUIRE(ctx && state && control && next, TG_ERR_ARG, "tg_quadrotor12_dynamics: null argument");
+    TG_REQUIRE(N > 0, TG_ERR_SHAPE, "N must be positive");
+    TG_CUDA(cudaSetDevice(ctx->device));
+    const unsigned grid = (unsigned)((N + 127) / 128);
+    if (precision == TG_PREC_F64)
+        quadrotor12_kernel<double><<<grid, 128, 0, (cudaStream_t)stream>>>(N, dt, (const double *)state,
+                                                                           (const double *)control, (double *)next);
+    else
+        quadrotor12_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(N, (float)dt, (const float *)state,
+                                                                          (const float *)control, (float *)next);
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}

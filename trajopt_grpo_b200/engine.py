@@ -1,0 +1,224 @@
+"""Tensor-level wrappers over the C ABI (include/trajopt_grpo.h).
+
+Every function takes/returns CUDA torch tensors in the kernels' native
+struct-of-arrays layout (env / sample index innermost) and launches on torch's
+current stream.  PyTorch is plumbing here (device memory and streams); all
+arithmetic happens in the sm_100a kernels behind the ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+OBS_DIM = {L.ENV_CARTPOLE: 5, L.ENV_PENDULUM: 3, L.ENV_QUADPOLE2D: 10, L.ENV_QUADPOLE: 20}
+ACT_DIM = {L.ENV_CARTPOLE: 1, L.ENV_PENDULUM: 1, L.ENV_QUADPOLE2D: 2, L.ENV_QUADPOLE: 4}
+
+_ws_cache: dict = {}
+
+
+def _need(t: torch.Tensor, dtype, name: str, shape=None):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise L.EngineError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise L.EngineError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise L.EngineError(f"{name} must be contiguous")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise L.EngineError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+    return t
+
+
+def _workspace(key, nbytes: int, device) -> torch.Tensor:
+    k = (key, torch.device(device).index)
+    ws = _ws_cache.get(k)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _ws_cache[k] = ws
+    return ws
+
+
+def rollout(kind, max_steps, dt, dims, activation, params, cov_diag, init_state, noise=None, seed=0,
+            want_logp=True, out=None, env_offset=0):
+    """tg_rollout.  init_state [S,N] float32 (throughput) or float64 (parity).
+    Returns dict(obs [T,O,N], act [T,A,N], rew [T,N], logp [T,N], len [N] i32, ret [N])."""
+    lib = L.load()
+    O, A = OBS_DIM[kind], ACT_DIM[kind]
+    T = int(max_steps)
+    if init_state.dtype not in (torch.float32, torch.float64):
+        raise L.EngineError("init_state must be float32 or float64")
+    _need(init_state, init_state.dtype, "init_state")
+    if init_state.shape[0] != O:
+        raise L.EngineError(f"init_state must be [S={O}, N]")
+    N = init_state.shape[1]
+    dev = init_state.device
+    _need(params, torch.float32, "params")
+    if noise is not None:
+        _need(noise, torch.float32, "noise", (T, A, N))
+    if out is None:
+        out = {
+            "obs": torch.empty((T, O, N), dtype=torch.float32, device=dev),
+            "act": torch.empty((T, A, N), dtype=torch.float32, device=dev),
+            "rew": torch.empty((T, N), dtype=torch.float32, device=dev),
+            "logp": torch.empty((T, N), dtype=torch.float32, device=dev) if want_logp else None,
+            "len": torch.empty((N,), dtype=torch.int32, device=dev),
+            "ret": torch.empty((N,), dtype=torch.float32, device=dev),
+        }
+    ecfg = L.env_cfg(kind, T, dt)
+    mcfg = L.mlp_cfg(dims, activation)
+    prec = L.PREC_F64 if init_state.dtype == torch.float64 else L.PREC_F32
+    with torch.cuda.device(dev):
+        rc = lib.tg_rollout(L.ctx(dev), C.byref(ecfg), C.byref(mcfg), prec, N, L.ptr(init_state), L.ptr(params),
+                            L.cov_array(cov_diag), L.ptr(noise), int(seed) & (2 ** 64 - 1), int(env_offset),
+                            L.ptr(out["obs"]),
+                            L.ptr(out["act"]), L.ptr(out["rew"]), L.ptr(out.get("logp")), L.ptr(out["len"]),
+                            L.ptr(out.get("ret")), L.stream_ptr())
+    L.check(rc, "tg_rollout")
+    return out
+
+
+def noise_fill(seed, N, T, A, device=None, env_offset=0):
+    lib = L.load()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = torch.empty((T, A, N), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.tg_noise_fill(L.ctx(dev), int(seed) & (2 ** 64 - 1), int(env_offset), N, T, A, L.ptr(out),
+                                  L.stream_ptr()),
+                "tg_noise_fill")
+    return out
+
+
+def env_step(kind, max_steps, dt, state, raw_action, steps_done=None, bal_count=None):
+    """tg_env_step.  state [S,N] f32|f64, raw_action [A,N] f32 -> (next, reward, done i32, bal i32)."""
+    lib = L.load()
+    O, A = OBS_DIM[kind], ACT_DIM[kind]
+    _need(state, state.dtype, "state")
+    N = state.shape[1]
+    dev = state.device
+    _need(raw_action, torch.float32, "raw_action", (A, N))
+    if steps_done is not None:
+        _need(steps_done, torch.int32, "steps_done", (N,))
+    if bal_count is not None:
+        _need(bal_count, torch.int32, "bal_count", (N,))
+    nxt = torch.empty_like(state)
+    rew = torch.empty((N,), dtype=state.dtype, device=dev)
+    done = torch.empty((N,), dtype=torch.int32, device=dev)
+    bal = torch.empty((N,), dtype=torch.int32, device=dev)
+    ecfg = L.env_cfg(kind, max_steps, dt)
+    prec = L.PREC_F64 if state.dtype == torch.float64 else L.PREC_F32
+    with torch.cuda.device(dev):
+        rc = lib.tg_env_step(L.ctx(dev), C.byref(ecfg), prec, N, L.ptr(state), L.ptr(raw_action), L.ptr(steps_done),
+                             L.ptr(bal_count), L.ptr(nxt), L.ptr(rew), L.ptr(done), L.ptr(bal), L.stream_ptr())
+    L.check(rc, "tg_env_step")
+    return nxt, rew, done, bal
+
+
+def quadrotor12_dynamics(state, control, dt=0.05):
+    lib = L.load()
+    _need(state, state.dtype, "state")
+    _need(control, state.dtype, "control", (4, state.shape[1]))
+    out = torch.empty_like(state)
+    prec = L.PREC_F64 if state.dtype == torch.float64 else L.PREC_F32
+    with torch.cuda.device(state.device):
+        L.check(lib.tg_quadrotor12_dynamics(L.ctx(state.device), prec, state.shape[1], float(dt), L.ptr(state),
+                                            L.ptr(control), L.ptr(out), L.stream_ptr()), "tg_quadrotor12_dynamics")
+    return out
+
+
+def policy_forward(dims, activation, params, x, cov_diag=None, act=None, want_mu=True, want_logp=False):
+    """tg_policy_forward.  x [K0,M] -> (mu [A,M] | None, logp [M] | None)."""
+    lib = L.load()
+    _need(x, torch.float32, "x")
+    M = x.shape[1]
+    A = int(dims[-1])
+    dev = x.device
+    _need(params, torch.float32, "params")
+    mu = torch.empty((A, M), dtype=torch.float32, device=dev) if want_mu else None
+    logp = torch.empty((M,), dtype=torch.float32, device=dev) if want_logp else None
+    if act is not None:
+        _need(act, torch.float32, "act", (A, M))
+    mcfg = L.mlp_cfg(dims, activation)
+    cov = L.cov_array(cov_diag) if cov_diag is not None else None
+    with torch.cuda.device(dev):
+        rc = lib.tg_policy_forward(L.ctx(dev), C.byref(mcfg), M, L.ptr(x), L.ptr(params), cov, L.ptr(act), L.ptr(mu),
+                                   L.ptr(logp), L.stream_ptr())
+    L.check(rc, "tg_policy_forward")
+    return mu, logp
+
+
+def advantage(mode, G, E, T, gamma, lam, rew, length, values=None, want_rtg=False):
+    """tg_advantage.  rew [T,N], length [N] i32 -> (adv [T,N], rtg [T,N] | None)."""
+    lib = L.load()
+    N = G * E
+    _need(rew, torch.float32, "rew", (T, N))
+    _need(length, torch.int32, "len", (N,))
+    dev = rew.device
+    adv = torch.empty_like(rew)
+    need_rtg = want_rtg or mode != L.ADV_GRPO
+    rtg = torch.empty_like(rew) if need_rtg else None
+    if values is not None:
+        _need(values, torch.float32, "values", (T, N))
+    ws = _workspace("adv", lib.tg_advantage_workspace_bytes(N, G), dev)
+    with torch.cuda.device(dev):
+        rc = lib.tg_advantage(L.ctx(dev), mode, G, E, T, float(gamma), float(lam), L.ptr(rew), L.ptr(length),
+                              L.ptr(values), L.ptr(adv), L.ptr(rtg), L.ptr(ws), L.stream_ptr())
+    L.check(rc, "tg_advantage")
+    return adv, rtg
+
+
+def policy_grad(dims, activation, params, cov_diag, obs, act, adv, old_logp, length, eps_clip, scale, kl_scale=0.0,
+                out_grad=None):
+    """tg_policy_grad -> (grad [n_params], stats [4] = objective, n_valid, sum ratio, n_clipped)."""
+    lib = L.load()
+    T, O, N = obs.shape
+    A = act.shape[1]
+    _need(obs, torch.float32, "obs")
+    _need(act, torch.float32, "act", (T, A, N))
+    _need(adv, torch.float32, "adv", (T, N))
+    _need(old_logp, torch.float32, "old_logp", (T, N))
+    _need(length, torch.int32, "len", (N,))
+    _need(params, torch.float32, "params")
+    dev = obs.device
+    mcfg = L.mlp_cfg(dims, activation)
+    grad = torch.empty_like(params) if out_grad is None else out_grad
+    stats = torch.empty((4,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace("grad", lib.tg_policy_grad_workspace_bytes(L.ctx(dev), C.byref(mcfg)), dev)
+        rc = lib.tg_policy_grad(L.ctx(dev), C.byref(mcfg), N, T, L.ptr(obs), L.ptr(act), L.ptr(adv), L.ptr(old_logp),
+                                L.ptr(length), L.ptr(params), L.cov_array(cov_diag), float(eps_clip), float(scale),
+                                float(kl_scale), L.ptr(grad), L.ptr(stats), L.ptr(ws), L.stream_ptr())
+    L.check(rc, "tg_policy_grad")
+    return grad, stats
+
+
+def value_grad(dims, activation, params, obs, target, length, scale, out_grad=None):
+    """tg_value_grad -> (grad [n_params], stats[0] = sum of squared errors, stats[1] = n_valid)."""
+    lib = L.load()
+    T, O, N = obs.shape
+    _need(obs, torch.float32, "obs")
+    _need(target, torch.float32, "target", (T, N))
+    _need(length, torch.int32, "len", (N,))
+    _need(params, torch.float32, "params")
+    dev = obs.device
+    mcfg = L.mlp_cfg(dims, activation)
+    grad = torch.empty_like(params) if out_grad is None else out_grad
+    stats = torch.empty((4,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace("grad", lib.tg_policy_grad_workspace_bytes(L.ctx(dev), C.byref(mcfg)), dev)
+        rc = lib.tg_value_grad(L.ctx(dev), C.byref(mcfg), N, T, L.ptr(obs), L.ptr(target), L.ptr(length),
+                               L.ptr(params), float(scale), L.ptr(grad), L.ptr(stats), L.ptr(ws), L.stream_ptr())
+    L.check(rc, "tg_value_grad")
+    return grad, stats
+
+
+def adam_step(params, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    lib = L.load()
+    for t, nm in ((params, "params"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _need(t, torch.float32, nm, (params.numel(),))
+    with torch.cuda.device(params.device):
+        rc = lib.tg_adam_step(L.ctx(params.device), params.numel(), L.ptr(params), L.ptr(grad), L.ptr(exp_avg),
+                              L.ptr(exp_avg_sq), int(step), float(lr), float(beta1), float(beta2), float(eps),
+                              L.stream_ptr())
+    L.check(rc, "tg_adam_step")
