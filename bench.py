@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""Benchmark of the rollout-and-update hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+A "step" is one training epoch of the reference's loop (pipelines/pipeline.py:163-164):
+`buffer.sample()` (policy-in-the-loop rollout of every env for the full horizon)
+followed by `algorithm.learn(buffer)` (RTG + group-relative advantages +
+`updates_per_iter` clipped-surrogate updates with Adam).  The default workload is
+BASELINE.json configs[1]: Pendulum GRPO, 65,536 envs x 200 steps, group size 16,
+MLP 3-64-64-1, per GPU (weak scaling: every rank runs the full per-GPU shape with
+whole groups; the only collective is the NCCL gradient allreduce).
+
+`value`  : valid env-steps/s of the whole job with the initial states already in HBM.
+`e2e`    : the same through the reference-facing host API (RolloutManager /
+           Rollout_Buffer / GRPO) with HOST initial states copied H2D from pinned
+           memory every step and the episode lengths + mean return read back D2H.
+Extra keys: rollout-only env-steps/s, GRPO updates/s, roofline of the dominant
+kernel, the CPU baseline measured on this box, clocks under load.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: env kind, class, T, group size E, groups per GPU, hidden, cov, gamma, eps, lr, updates, restart
+    "pendulum": dict(kind=1, cls="Pendulum", T=200, E=16, G=4096, hidden=[64, 64], cov=0.5, gamma=0.99, eps=0.2,
+                     lr=5e-4, updates=5, desc="Pendulum GRPO, 65,536 envs x 200-step horizon, group size 16, MLP 64x64"),
+    "cartpole": dict(kind=0, cls="CartPole", T=500, E=10, G=10, hidden=[128, 128, 128, 128], cov=0.5, gamma=0.5,
+                     eps=0.15, lr=3e-4, updates=1, desc="CartPole GRPO (scripts/cartpole_nn_grpo.py defaults)"),
+    "quadpole2d": dict(kind=2, cls="QuadPole2D", T=500, E=16, G=16384, hidden=[128, 128], cov=0.5, gamma=0.99,
+                       eps=0.2, lr=2e-4, updates=2, desc="QuadPole2D GRPO, 262,144 envs x 500 steps, MLP 128x128"),
+    "quadpole": dict(kind=3, cls="QuadPole", T=1000, E=64, G=1024, hidden=[256, 256], cov=0.3, gamma=0.999, eps=0.2,
+                     lr=3e-4, updates=1, desc="3D QuadPole GRPO, 65,536 envs x 1000 steps, group 64, MLP 256x256"),
+}
+OBS = {0: 5, 1: 3, 2: 10, 3: 20}
+ACT = {0: 1, 1: 1, 2: 2, 3: 4}
+
+
+def mlp_macs(dims):
+    return sum(dims[i] * dims[i + 1] for i in range(len(dims) - 1))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: the reference's way (oracle/cpu_port.py), bounded sample of the same workload
+# --------------------------------------------------------------------------------------
+def cpu_leg(w, seed=0, budget_workers=None):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_port
+    import restate as R
+    import torch
+    kind, T = w["kind"], w["T"]
+    rng = np.random.default_rng(seed)
+    dims = [OBS[kind]] + w["hidden"] + [ACT[kind]]
+    torch.manual_seed(seed)
+    Ws, bs = [], []
+    for i in range(len(dims) - 1):
+        lin = torch.nn.Linear(dims[i], dims[i + 1])
+        Ws.append(lin.weight.detach().numpy().copy()); bs.append(lin.bias.detach().numpy().copy())
+    cores = os.cpu_count() or 1
+    G = budget_workers or cores                  # one group per host core
+    E = max(2, min(w["E"], int(3000 // T) or 2))  # ~3k env-steps per worker: a 10-30 s sample
+    cov = [w["cov"]] * ACT[kind]
+    (obs, act, rew, lens, mask), t_roll, procs = cpu_port.rollout_mp(kind, T, R.DEFAULT_DT[kind], Ws, bs, cov, G, E,
+                                                                     True, seed)
+    torch.set_num_threads(cores)
+    t_learn = cpu_port.grpo_learn(obs, act, rew, mask, Ws, bs, cov, w["gamma"], w["eps"], w["updates"], w["lr"])
+    steps = int(lens.sum())
+    return {
+        "value": steps / (t_roll + t_learn), "unit": "env-steps/s", "cores": procs, "kind": "port",
+        "sample": f"{G} groups x {E} episodes x <={T} steps ({steps} valid env-steps) rollout on {procs} worker "
+                  f"processes (OMP_NUM_THREADS=1) + GRPO.learn x{w['updates']} updates on torch-CPU ({cores} threads)",
+        "rollout_env_steps_per_s": steps / t_roll, "rollout_s": t_roll, "learn_s": t_learn,
+        "updates_per_s": w["updates"] / t_learn,
+    }
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        last = cpu_leg(w, seed=i)
+        if i >= args.warmup:
+            vals.append(last["value"])
+    v = float(np.mean(vals))
+    last["value"] = v
+    line = {
+        "impl": "reference", "metric": "policy-in-loop env-steps/sec (rollout + GRPO update epoch)", "value": v,
+        "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": w["desc"], "cpu_sample": last["sample"]},
+        "cpu_baseline": last, "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0,
+                                      "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+    import trajopt_grpo_b200 as tg
+    from trajopt_grpo_b200 import engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    kind, T, E, G = w["kind"], w["T"], w["E"], w["G"]
+    N = G * E
+    O, A = OBS[kind], ACT[kind]
+    dims = [O] + w["hidden"] + [A]
+    P = mlp_macs(dims)
+
+    torch.manual_seed(1234)                      # identical initial weights on every rank
+    policy = tg.GaussianActor_NeuralNetwork(O, A, w["hidden"], "ReLU", w["cov"])
+    opt = torch.optim.Adam(policy.parameters(), lr=w["lr"])
+    algo = tg.GRPO(w["eps"], 0.01, w["gamma"], policy, opt, None, updates_per_iter=w["updates"])
+    env_cls = getattr(tg, w["cls"])
+    mgr = tg.RolloutManager(lambda: env_cls(max_steps=T), policy, restart=True, num_workers=G * world,
+                            num_episodes_per_worker=E, use_multiprocessing=False, seed=7, rank=rank, world_size=world)
+    buf = tg.Rollout_Buffer(mgr)
+    env = mgr.env
+    rng = np.random.default_rng(100 + rank)
+    total = args.warmup + args.steps
+
+    def host_init():
+        s0 = np.repeat(env.sample_initial_states(G, rng), E, axis=0)
+        return torch.from_numpy(np.ascontiguousarray(s0.T)).to(torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        return float(t.item())
+
+    # ---------------- device-resident arm: inputs already in HBM ----------------
+    inits = [host_init().to(dev) for _ in range(total)]
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    phase = {"rollout": [], "adv": [], "update": []}
+    lens_sum = torch.zeros((), dtype=torch.int64, device=dev)
+
+    def one_step_device(i, timed):
+        e = [ev() for _ in range(4)]
+        e[0].record()
+        r = mgr.rollout_device(init_state=inits[i])
+        e[1].record()
+        buf.device_rollout = r
+        # GRPO.learn, with event marks between its phases
+        e[2].record()
+        algo.learn(buf)
+        e[3].record()
+        if timed:
+            phase["rollout"].append((e[0], e[1]))
+            phase["update"].append((e[2], e[3]))
+            lens_sum.add_(r.len.sum())
+
+    for i in range(args.warmup):
+        one_step_device(i, False)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = engine.COUNTERS["launches"]
+    t0, t1 = ev(), ev()
+    t0.record()
+    for i in range(args.warmup, total):
+        one_step_device(i, True)
+    t1.record()
+    barrier()
+    launches = engine.COUNTERS["launches"] - launches0
+    ms_total = max_over_ranks(t0.elapsed_time(t1))
+    valid_steps = sum_over_ranks(float(lens_sum.item()))
+    value = valid_steps / (ms_total * 1e-3)
+    roll_ms = float(np.mean([a.elapsed_time(b) for a, b in phase["rollout"]]))
+    upd_ms = float(np.mean([a.elapsed_time(b) for a, b in phase["update"]]))
+    valid_per_step_rank = float(lens_sum.item()) / args.steps
+
+    # ---------------- dominant-kernel timing: K3 alone, CUDA events on its stream -------------
+    r = buf.device_rollout
+    adv, _ = engine.advantage(0, r.G, r.E, r.T, w["gamma"], 0.0, r.rew, r.len)
+    flat = policy.flat_parameters()
+    k3 = []
+    for i in range(3 + 5):
+        a, b = ev(), ev()
+        a.record()
+        engine.policy_grad(dims, "ReLU", flat, policy.cov_diag, r.obs, r.act, adv, r.logp, r.len, w["eps"], 1.0 / G)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            k3.append(a.elapsed_time(b))
+    k3_ms = float(np.mean(k3))
+    k1 = []
+    for i in range(2 + 3):
+        a, b = ev(), ev()
+        a.record()
+        mgr.rollout_device(init_state=inits[0])
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            k1.append(a.elapsed_time(b))
+    k1_ms = float(np.mean(k1))
+    k2 = []
+    for i in range(2 + 3):
+        a, b = ev(), ev()
+        a.record()
+        engine.advantage(0, r.G, r.E, r.T, w["gamma"], 0.0, r.rew, r.len)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            k2.append(a.elapsed_time(b))
+    k2_ms = float(np.mean(k2))
+    clock_info = clocks.stop() if rank == 0 else None
+
+    # ---------------- end-to-end arm: host buffers in, host scalars out ----------------
+    host_inits = [host_init() for _ in range(total)]
+    h2d = host_inits[0].numel() * 4
+    d2h = N * 4 + 4
+    e2e_steps = torch.zeros((), dtype=torch.int64, device=dev)
+    lens_host = torch.empty(N, dtype=torch.int32).pin_memory()
+
+    def one_step_e2e(i):
+        x = host_inits[i].to(dev, non_blocking=True)                 # H2D of this step's inputs
+        r = mgr.rollout_device(init_state=x)
+        buf.device_rollout = r
+        algo.learn(buf)
+        lens_host.copy_(r.len, non_blocking=True)                    # D2H of the step's results
+        mean_ret = float(r.ret.mean().item())                        # (sync) what Rollout_Buffer.store reports
+        buf.avg_reward.append(mean_ret)
+        return int(lens_host.sum())
+
+    for i in range(args.warmup):
+        one_step_e2e(i)
+    barrier()
+    a, b = ev(), ev()
+    wall0 = time.perf_counter()
+    a.record()
+    n_e2e = 0
+    for i in range(args.warmup, total):
+        n_e2e += one_step_e2e(i)
+    b.record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    e2e_ms = max_over_ranks(max(a.elapsed_time(b), wall * 1e3))
+    e2e_value = sum_over_ranks(float(n_e2e)) / (e2e_ms * 1e-3)
+
+    # ---------------- roofline of the dominant kernel (K3: tg_policy_grad) ----------------
+    fp32_peak = engine.fp32_peak_tflops(dev)
+    # algorithmic FLOPs of one K3 launch = 6*P FLOP per valid step (fwd 2P + bwd 4P), SURVEY 8d
+    k3_flops = 6.0 * P * valid_per_step_rank
+    k1_flops = 2.0 * P * valid_per_step_rank
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roofline = {
+        "kernel": "update_kernel (tg_policy_grad: fused fwd + clipped surrogate + MLP backward)",
+        "bound": "fp32-fma", "achieved": k3_flops / (k3_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+        "frac": k3_flops / (k3_ms * 1e-3) / 1e12 / fp32_peak, "traffic": None,
+        "peak_source": "tg_fp32_peak FFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
+        "frac_of_measured_bf16_tensor_peak": k3_flops / (k3_ms * 1e-3) / 1e12 / peaks.get("bf16_tflops", 1590.0),
+        "ms_per_launch": k3_ms, "flops_per_launch": k3_flops,
+        "others": {
+            "rollout_kernel": {"bound": "fp32-fma", "ms": k1_ms, "achieved_tflops": k1_flops / (k1_ms * 1e-3) / 1e12,
+                               "frac": k1_flops / (k1_ms * 1e-3) / 1e12 / fp32_peak,
+                               "traj_write_gbs": 4.0 * (O + A + 2) * N * T / (k1_ms * 1e-3) / 1e9},
+            "adv_grpo_kernel": {"bound": "hbm", "ms": k2_ms, "achieved_gbs": 8.0 * N * T / (k2_ms * 1e-3) / 1e9,
+                                "peak_gbs": hbm_peak, "frac": 8.0 * N * T / (k2_ms * 1e-3) / 1e9 / hbm_peak},
+        },
+    }
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = cpu_leg(w) if (world == 1 and not args.no_cpu) else None
+    line = {
+        "metric": "policy-in-loop env-steps/sec (rollout + GRPO update epoch)", "value": value, "unit": "env-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "envs_per_gpu": N, "horizon": T, "group_size": E, "mlp": dims,
+                   "updates_per_iter": w["updates"], "precision": "fp32 state + fp32 MLP (throughput mode)",
+                   "l2": "per-step working set %.0f MB > 126 MB L2 (inputs larger than L2, no flush)" %
+                         (4.0 * (O + A + 3) * N * T / 1e6),
+                   "parallelism": f"dp{world} (whole GRPO groups per GPU, NCCL grad allreduce)"},
+        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches,
+        "rollout_env_steps_per_s": valid_per_step_rank * world / (roll_ms * 1e-3),
+        "grpo_updates_per_s": w["updates"] / (upd_ms * 1e-3),
+        "phase_ms": {"rollout": roll_ms, "learn": upd_ms},
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pendulum", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

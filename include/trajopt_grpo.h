@@ -98,6 +98,10 @@ int tg_ctx_create(int device, tg_ctx **out);
 void tg_ctx_destroy(tg_ctx *ctx);
 int tg_ctx_sm_count(const tg_ctx *ctx);
 
+/* Measured FP32 FMA-pipe throughput of the device (TFLOP/s), the roofline of the
+ * register-tiled MLP GEMMs; bench.py reports K1/K3 against it. */
+int tg_fp32_peak(tg_ctx *ctx, double *out_tflops);
+
 /* dims of an env kind: returns 0 or TG_ERR_ARG */
 int tg_env_dims(int kind, int *obs_dim, int *act_dim);
 
@@ -163,6 +167,15 @@ int tg_quadrotor12_dynamics(tg_ctx *ctx, int precision, int64_t N, double dt,
 int tg_policy_forward(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t M, const float *x,
                       const float *params, const float *cov_diag, const float *act,
                       float *out_mu, float *out_logp, void *stream);
+
+/* Same, reading a trajectory in place: obs [T][O][N], act [T][A][N] or NULL,
+ * len [N] or NULL (rows with t >= len[n] are skipped and left unwritten)
+ *   -> out_mu [T][A][N] (or NULL), out_logp [T][N] (or NULL).
+ * Used for the frozen old-policy log-prob (grpo.py:118-119, ppo.py:142-143) and
+ * the critic values over a rollout (ppo.py:93-94). */
+int tg_policy_forward_traj(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, const float *obs,
+                           const float *act, const int32_t *len, const float *params,
+                           const float *cov_diag, float *out_mu, float *out_logp, void *stream);
 
 /* ---- K2: reward-to-go + advantages -----------------------------------------
  * Replaces the RTG loop and per-group normalisation of GRPO.learn

@@ -45,6 +45,7 @@ _SIGS = {
     "tg_ctx_create": (C.c_int, [_i32, C.POINTER(_vp)]),
     "tg_ctx_destroy": (None, [_vp]),
     "tg_ctx_sm_count": (C.c_int, [_vp]),
+    "tg_fp32_peak": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "tg_env_dims": (C.c_int, [_i32, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "tg_mlp_param_count": (_i64, [C.POINTER(MlpCfg)]),
     "tg_rollout": (C.c_int, [_vp, C.POINTER(EnvCfg), C.POINTER(MlpCfg), _i32, _i64, _vp, _vp, C.POINTER(_f), _vp,
@@ -53,6 +54,8 @@ _SIGS = {
     "tg_env_step": (C.c_int, [_vp, C.POINTER(EnvCfg), _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tg_quadrotor12_dynamics": (C.c_int, [_vp, _i32, _i64, _d, _vp, _vp, _vp, _vp]),
     "tg_policy_forward": (C.c_int, [_vp, C.POINTER(MlpCfg), _i64, _vp, _vp, C.POINTER(_f), _vp, _vp, _vp, _vp]),
+    "tg_policy_forward_traj": (C.c_int, [_vp, C.POINTER(MlpCfg), _i64, _i32, _vp, _vp, _vp, _vp, C.POINTER(_f), _vp,
+                                         _vp, _vp]),
     "tg_advantage_workspace_bytes": (_i64, [_i64, _i32]),
     "tg_advantage": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tg_policy_grad_workspace_bytes": (_i64, [_vp, C.POINTER(MlpCfg)]),

@@ -1,0 +1,258 @@
+"""Host-side mirror of algorithms/algorithm.py, grpo.py and ppo.py.
+
+Same constructors, `learn(buffer)`, `save/load/metadata` and `old_policy`
+attribute as the reference; `learn` is a short sequence of kernel launches:
+
+  GRPO.learn (grpo.py:50-148):
+      tg_advantage(GRPO)                         RTG + per-group z-score
+      [tg_policy_forward_traj]                   frozen old-policy log-prob (skipped when
+                                                 the rollout's own log-prob is that value)
+      updates_per_iter x { tg_policy_grad  ->  [NCCL allreduce]  ->  tg_adam_step }
+
+The objective keeps the reference's sign: `J.backward(); optimizer.step()` with a
+minimising optimizer descends on J -- pass `maximize=True` to ascend.
+"""
+from __future__ import annotations
+
+import copy
+import os
+from abc import ABC, abstractmethod
+
+import torch
+
+from . import _lib as L
+from . import engine
+
+
+class Algorithm(ABC):
+    """algorithms/algorithm.py:3-36."""
+
+    def __init__(self):
+        pass
+
+    @abstractmethod
+    def learn(self):
+        pass
+
+    @abstractmethod
+    def metadata(self):
+        return {}
+
+    @abstractmethod
+    def save(self, path: str):
+        pass
+
+    @abstractmethod
+    def load(self, path: str):
+        pass
+
+
+class _FlatOptimizer:
+    """Applies a flat gradient to the policy's flat parameter vector.
+
+    torch.optim.Adam with default flags (what every reference pipeline builds,
+    pipelines/cartpole_pipeline_grpo.py:65) runs as ONE tg_adam_step launch whose
+    moment buffers are aliased into `optimizer.state`, so `optimizer.state_dict()`
+    checkpoints (grpo.py:150-160, ppo.py:207-225) keep working.  Any other
+    optimizer gets `p.grad` views of the flat gradient and its own `step()`.
+    """
+
+    def __init__(self, optimizer, policy):
+        self.opt, self.policy = optimizer, policy
+        self.m = self.v = None
+        self.step_count = 0
+
+    def _params_match_flat(self, flat):
+        groups = self.opt.param_groups
+        if len(groups) != 1:
+            return False
+        off, base = 0, flat.data_ptr()
+        for p in groups[0]["params"]:
+            if p.data_ptr() != base + 4 * off:
+                return False
+            off += p.numel()
+        return off == flat.numel()
+
+    def _fused_adam_ok(self, flat):
+        if type(self.opt) is not torch.optim.Adam or not self._params_match_flat(flat):
+            return False
+        g = self.opt.param_groups[0]
+        return not g.get("amsgrad", False) and not g.get("maximize", False) and g.get("weight_decay", 0) == 0 \
+            and not g.get("capturable", False) and not g.get("differentiable", False)
+
+    def _sync_adam_state(self, flat):
+        if self.m is None or self.m.numel() != flat.numel() or self.m.device != flat.device:
+            self.m, self.v = torch.zeros_like(flat), torch.zeros_like(flat)
+        off = 0
+        for p in self.opt.param_groups[0]["params"]:
+            n = p.numel()
+            st = self.opt.state[p]
+            for key, buf in (("exp_avg", self.m), ("exp_avg_sq", self.v)):
+                view = buf[off:off + n].view(p.shape)
+                cur = st.get(key)
+                if cur is not None and cur.data_ptr() != view.data_ptr():
+                    view.copy_(cur.to(view.device, torch.float32))      # state came from load_state_dict()
+                st[key] = view
+            if "step" in st:
+                self.step_count = max(self.step_count, int(float(st["step"])))
+            off += n
+
+    def step(self, flat, grad):
+        if self._fused_adam_ok(flat):
+            self._sync_adam_state(flat)
+            g = self.opt.param_groups[0]
+            self.step_count += 1
+            engine.adam_step(flat, grad, self.m, self.v, self.step_count, g["lr"], g["betas"][0], g["betas"][1],
+                             g["eps"])
+            stamp = torch.tensor(float(self.step_count))
+            for p in g["params"]:
+                self.opt.state[p]["step"] = stamp
+            return
+        off = 0
+        params = [p for grp in self.opt.param_groups for p in grp["params"]]
+        if sum(p.numel() for p in params) != grad.numel():
+            raise L.EngineError("optimizer parameters do not match the policy's flat parameter vector")
+        for p in params:
+            p.grad = grad[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        self.opt.step()
+
+
+def _dist_world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size()
+    return 1
+
+
+def _rollout_of(buffer):
+    r = getattr(buffer, "device_rollout", None)
+    if r is None:
+        if getattr(buffer, "group_observations", None) is None:
+            raise L.EngineError("buffer holds no rollout: call buffer.sample() or buffer.store(...) first")
+        from .buffers import Rollout_Buffer
+        tmp = Rollout_Buffer.__new__(Rollout_Buffer)
+        tmp.avg_reward = []
+        Rollout_Buffer.store(tmp, buffer.group_observations, buffer.group_actions, buffer.group_rewards,
+                             buffer.group_masks.sum(-1) if getattr(buffer, "group_lengths", None) is None
+                             else buffer.group_lengths, buffer.group_masks)
+        r = tmp.device_rollout
+    return r
+
+
+class GRPO(Algorithm):
+    """algorithms/grpo.py:12-168."""
+
+    def __init__(self, epsilon: float, beta: float, gamma: float, policy, optimizer, ref_model=None,
+                 updates_per_iter: int = 10, *, maximize: bool = False):
+        self.epsilon, self.policy, self.ref_model, self.beta = epsilon, policy, ref_model, beta
+        self.gamma, self.updates_per_iter, self.optimizer = gamma, updates_per_iter, optimizer
+        self.maximize = maximize
+        if ref_model is not None:
+            # grpo.py:129-132 cannot run in the reference either; no oracle for a KL term
+            raise L.EngineError("ref_model is not supported: the reference's KL branch is broken (every config passes None)")
+        self.old_policy = copy.deepcopy(self.policy)                 # grpo.py:48
+        self._synced_tag = policy.param_tag()                        # old_policy == policy at this tag
+        self._flat_opt = _FlatOptimizer(optimizer, policy)
+        self.last_stats = None
+
+    def learn(self, buffer) -> None:
+        r = _rollout_of(buffer)
+        pol = self.policy
+        flat = pol.flat_parameters()
+        old_flat = self.old_policy.flat_parameters()
+        dims, act_name, cov = pol.actor.dims, pol.actor.activation_name, pol.cov_diag
+        world = _dist_world()
+        G_global = r.G * world
+        # grpo.py:66-74, 108-115
+        adv, _ = engine.advantage(L.ADV_GRPO, r.G, r.E, r.T, self.gamma, 0.0, r.rew, r.len)
+        # grpo.py:118-119: log-prob under the frozen old policy.  The rollout kernel already
+        # evaluated it when the rollout was produced by weights identical to old_policy.
+        cur_tag = pol.param_tag()
+        if r.logp is not None and r.policy_tag == cur_tag and self._synced_tag == cur_tag:
+            old_logp = r.logp
+        else:
+            _, old_logp = engine.policy_forward_traj(dims, act_name, old_flat[:flat.numel()].contiguous(), r.obs, cov,
+                                                     r.act, r.len)
+        scale = (-1.0 if self.maximize else 1.0) / G_global         # grpo.py:140 (J /= group_size)
+        for _ in range(self.updates_per_iter):                      # grpo.py:106
+            grad, stats = engine.policy_grad(dims, act_name, flat, cov, r.obs, r.act, adv, old_logp, r.len,
+                                             self.epsilon, scale)
+            if world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(grad)                                # the path's only collective
+            self._flat_opt.step(flat, grad)                         # grpo.py:143-145
+            pol.bump_param_epoch()
+            self.last_stats = stats
+        self.old_policy.load_state_dict(self.policy.state_dict())   # grpo.py:148
+        self._synced_tag = pol.param_tag()
+
+    def save(self, path: str) -> None:
+        torch.save(self.optimizer.state_dict(), os.path.join(path, "optimizer.pth"))
+
+    def load(self, path: str) -> None:
+        self.optimizer.load_state_dict(torch.load(os.path.join(path, "optimizer.pth")))
+
+    def metadata(self):
+        return {"algorithm": "GRPO", "epsilon": self.epsilon, "beta": self.beta,
+                "updates_per_iter": self.updates_per_iter}
+
+
+class PPO(Algorithm):
+    """algorithms/ppo.py:8-225 (full-batch updates: batch_size=None, the shipped pipelines' setting)."""
+
+    def __init__(self, epsilon: float, policy, optimizer, ref_model, updates_per_iter: int, c1: float = 0.5,
+                 kl_coeff: float = 0.5, gamma: float = 0.99, lam: float = 0.95, entropy: float = 0.01,
+                 batch_size: int = 64, monte_carlo: bool = True):
+        self.epsilon, self.c1, self.policy, self.ref_model = epsilon, c1, policy, ref_model
+        self.updates_per_iter, self.optimizer, self.gamma, self.lam = updates_per_iter, optimizer, gamma, lam
+        self.entropy, self.batch_size, self.kl_coeff, self.monte_carlo = entropy, batch_size, kl_coeff, monte_carlo
+        if not hasattr(policy, "critic"):
+            raise L.EngineError("PPO needs a GaussianActorCritic_NeuralNetwork policy")
+        self.old_policy = copy.deepcopy(self.policy)                 # ppo.py:62
+        self._flat_opt = _FlatOptimizer(optimizer, policy)
+        self.last_stats = None
+
+    def learn(self, buffer) -> None:
+        if self.batch_size is not None:
+            raise L.EngineError("minibatched PPO (batch_size != None) is not built yet: the fused update is "
+                                "full-batch, as quadpole2d_pipeline_ppo.py configures it")
+        if _dist_world() > 1:
+            raise L.EngineError("multi-GPU PPO needs a global-statistics allreduce that is not built yet")
+        r = _rollout_of(buffer)
+        pol = self.policy
+        flat = pol.flat_parameters()
+        na = pol.actor.n_params()
+        a_flat, c_flat = flat[:na], flat[na:]
+        a_dims, c_dims, act_name, cov = pol.actor.dims, pol.critic.dims, pol.actor.activation_name, pol.cov_diag
+        # ppo.py:93-94: critic values over the rollout
+        values, _ = engine.policy_forward_traj(c_dims, act_name, c_flat, r.obs, None, None, r.len, want_mu=True,
+                                               want_logp=False)
+        values = values.view(r.T, r.N)
+        mode = L.ADV_PPO_MC if self.monte_carlo else L.ADV_PPO_GAE
+        adv, rtg = engine.advantage(mode, r.G, r.E, r.T, self.gamma, self.lam, r.rew, r.len, values)   # :100-139
+        # ppo.py:142-143: old log-prob from self.policy at the start of learn()
+        _, old_logp = engine.policy_forward_traj(a_dims, act_name, a_flat, r.obs, cov, r.act, r.len)
+        n_valid = int(r.len.sum().item())
+        grad = torch.empty_like(flat)
+        for _ in range(self.updates_per_iter):                      # ppo.py:147 (full batch; the order of a
+            # permutation does not change a mean)
+            _, stats = engine.policy_grad(a_dims, act_name, a_flat, cov, r.obs, r.act, adv, old_logp, r.len,
+                                          self.epsilon, -1.0 / n_valid, self.kl_coeff / n_valid,
+                                          out_grad=grad[:na])        # :160-166, 175-176
+            engine.value_grad(c_dims, act_name, c_flat, r.obs, rtg, r.len, self.c1 / n_valid, out_grad=grad[na:])
+            self._flat_opt.step(flat, grad)                         # :181-183 (entropy term has zero gradient)
+            pol.bump_param_epoch()
+            self.last_stats = stats
+        self.old_policy.load_state_dict(self.policy.state_dict())   # ppo.py:186
+
+    def metadata(self) -> dict:
+        return {"algorithm": "PPO", "epsilon": self.epsilon, "c1": self.c1, "kl_coeff": self.kl_coeff,
+                "gamma": self.gamma, "lam": self.lam, "entropy": self.entropy, "batch_size": self.batch_size,
+                "updates_per_iter": self.updates_per_iter}
+
+    def save(self, path: str) -> None:
+        torch.save(self.optimizer.state_dict(), os.path.join(path, "optimizer.pt"))
+
+    def load(self, path: str) -> None:
+        self.optimizer.load_state_dict(torch.load(os.path.join(path, "optimizer.pt"), weights_only=True))

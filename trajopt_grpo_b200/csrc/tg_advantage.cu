@@ -37,12 +37,18 @@ adv_grpo_kernel(int64_t G, int E, int T, int GC, float gamma, const float *__res
     for (int i = threadIdx.x; i < envs; i += ADV_THREADS) {
         const int64_t n = n0 + i;
         const int L = len[n];
+        // shift K = first scanned value of the group's first env: the one-pass variance of
+        // (y - K) is exactly 0 for a constant group (std 0 -> NaN/inf like torch)
+        // and well conditioned otherwise
+        const int64_t e0 = n0 + (int64_t)(i / E) * E;
+        const int L0 = len[e0];
+        const double K = L0 > 0 ? (double)__fadd_rn(rew[(int64_t)(L0 - 1) * N + e0], 1e-8f) : 0.0;
         float rtg = 0.0f;
         double ax = 0.0, ay = 0.0, ayy = 0.0;
 #pragma unroll 4
         for (int t = L - 1; t >= 0; --t) {
             rtg = rtg_step(rew[(int64_t)t * N + n], gamma, rtg);
-            const double y = (double)__fadd_rn(rtg, 1e-8f);
+            const double y = (double)__fadd_rn(rtg, 1e-8f) - K;
             ax += (double)rtg;
             ay += y;
             ayy += y * y;

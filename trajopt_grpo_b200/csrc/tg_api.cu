@@ -85,6 +85,52 @@ extern "C" int64_t tg_mlp_param_count(const tg_mlp_cfg *mlp) {
     return n;
 }
 
+// FP32 FMA-pipe microbenchmark: MEASURED_PEAKS.json holds no FP32 peak, and the
+// register-tiled MLP GEMMs are bounded by exactly this pipe.  16 independent FFMA
+// chains per thread, 8 warps x 4 CTAs per SM.
+__global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float *sink) {
+    float a[16];
+    const float x = 1.0f + 1e-7f * threadIdx.x, y = 1e-3f * blockIdx.x;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (float)i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], x, y);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 123.456f) sink[0] = s;
+}
+
+extern "C" int tg_fp32_peak(tg_ctx *ctx, double *out_tflops) {
+    TG_REQUIRE(ctx && out_tflops, TG_ERR_ARG, "tg_fp32_peak: null argument");
+    TG_CUDA(cudaSetDevice(ctx->device));
+    float *sink = nullptr;
+    TG_CUDA(cudaMalloc(&sink, 64));
+    cudaEvent_t e0, e1;
+    TG_CUDA(cudaEventCreate(&e0));
+    TG_CUDA(cudaEventCreate(&e1));
+    const int iters = 20000, grid = ctx->sm_count * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        TG_CUDA(cudaEventRecord(e0));
+        fma_peak_kernel<<<grid, 256>>>(iters, sink);
+        TG_CUDA(cudaEventRecord(e1));
+        TG_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.0f;
+        TG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 16.0 * iters * 256.0 * grid;
+        const double tf = fl / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *out_tflops = best;
+    return TG_OK;
+}
+
 int tg_build_layout(const tg_mlp_cfg *mlp, bool with_backward, tg_mlp_layout *out) {
     TG_REQUIRE(mlp != nullptr, TG_ERR_ARG, "mlp cfg is null");
     TG_REQUIRE(mlp->n_layers >= 1 && mlp->n_layers <= TG_MAX_LAYERS, TG_ERR_SHAPE, "n_layers %d not in [1,%d]",

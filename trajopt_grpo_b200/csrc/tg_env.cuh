@@ -34,6 +34,9 @@ template <> struct Mth<double> {
 
 TG_D float clip1(float a) { return fminf(fmaxf(a, -1.0f), 1.0f); }
 template <typename R> TG_D R clipr(R a, R lo, R hi) { return a < lo ? lo : (a > hi ? hi : a); }
+// hover + hover*clip(a) as numpy evaluates it in float32: a rounded product, then a
+// rounded sum (no FMA contraction) -- quadrotor_env.py:409-413, 928
+TG_D float wrap_hover(float hov, float a) { return __fadd_rn(hov, __fmul_rn(hov, clip1(a))); }
 
 #define TG_G 9.80665
 
@@ -114,8 +117,8 @@ template <> struct Env<TG_ENV_QUADPOLE2D> {
     template <typename R>
     static TG_D bool step(R *s, const float *a, const EnvParams &p, int steps_done, int &bal, R &reward) {
         const float hov = (float)((1.5 + 0.5) * TG_G / 2);       // :895
-        const float u1 = hov + hov * clip1(a[0]);                // :928 (float32)
-        const float u2 = hov + hov * clip1(a[1]);
+        const float u1 = wrap_hover(hov, a[0]);                  // :928 (float32 mul then add, unfused)
+        const float u2 = wrap_hover(hov, a[1]);
         R x = s[0], z = s[1], vx = s[2], vz = s[3], sth = s[4], cth = s[5], thd = s[6];
         R sph = s[7], cph = s[8], phd = s[9];
         const R mq = (R)1.5, mp = (R)0.5, Lp = (R)0.75, g = (R)TG_G, dt = (R)p.dt;
@@ -171,8 +174,8 @@ template <> struct Env<TG_ENV_QUADPOLE> {
     template <typename R>
     static TG_D bool step(R *s, const float *a, const EnvParams &p, int steps_done, int &bal, R &reward) {
         const float hov = (float)((1.5 + 0.5) * TG_G / 4);       // :376
-        const float u1 = hov + hov * clip1(a[0]), u2 = hov + hov * clip1(a[1]);   // :409-413
-        const float u3 = hov + hov * clip1(a[2]), u4 = hov + hov * clip1(a[3]);
+        const float u1 = wrap_hover(hov, a[0]), u2 = wrap_hover(hov, a[1]);   // :409-413
+        const float u3 = wrap_hover(hov, a[2]), u4 = wrap_hover(hov, a[3]);
         const R ut = (R)(((u1 + u2) + u3) + u4);                 // :442 float32 adds
         const R m0 = (R)1.5, mp = (R)0.5, L = (R)0.5, arm = (R)0.5;
         const R Ixx = (R)0.4, Iyy = (R)0.4, Izz = (R)0.25, g = (R)TG_G, dt = (R)p.dt;

@@ -444,6 +444,36 @@ extern "C" int tg_policy_forward(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t M, 
     return dispatch_update(ctx, a, grid, st);
 }
 
+extern "C" int tg_policy_forward_traj(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, const float *obs,
+                                      const float *act, const int32_t *len, const float *params,
+                                      const float *cov_diag, float *out_mu, float *out_logp, void *stream) {
+    TG_REQUIRE(ctx && mlp && obs && params, TG_ERR_ARG, "tg_policy_forward_traj: null argument");
+    TG_REQUIRE(out_mu || out_logp, TG_ERR_ARG, "tg_policy_forward_traj: no output requested");
+    TG_REQUIRE(!out_logp || (act && cov_diag), TG_ERR_ARG, "log-prob needs act and cov_diag");
+    TG_REQUIRE(N > 0 && T > 0, TG_ERR_SHAPE, "N and T must be positive");
+    UpdArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = tg_build_layout(mlp, false, &a.lay);
+    if (rc) return rc;
+    if (cov_diag) {
+        rc = fill_gauss(a, cov_diag, a.lay.A);
+        if (rc) return rc;
+    } else {
+        for (int j = 0; j < TG_MAX_ACT; ++j) a.inv_sd[j] = a.inv_var[j] = 1.0f;
+    }
+    a.N = N; a.T = T; a.head = HEAD_FORWARD;
+    a.obs = obs; a.act = act; a.len = len; a.out_mu = out_mu; a.out_logp = out_logp;
+    cudaStream_t st = (cudaStream_t)stream;
+    TG_CUDA(cudaSetDevice(ctx->device));
+    rc = tg_pack_weights(ctx, a.lay, params, st);
+    if (rc) return rc;
+    a.packed = ctx->packed;
+    int grid = update_grid(ctx, a.lay);
+    const int64_t ntiles = ((N + a.lay.B - 1) / a.lay.B) * T;
+    if (grid > ntiles) grid = (int)ntiles;
+    return dispatch_update(ctx, a, grid, st);
+}
+
 // ---------------------------------------------------------------------------
 // Adam (torch.optim.Adam defaults, single-tensor formula)
 // ---------------------------------------------------------------------------

@@ -18,6 +18,21 @@ ACT_DIM = {L.ENV_CARTPOLE: 1, L.ENV_PENDULUM: 1, L.ENV_QUADPOLE2D: 2, L.ENV_QUAD
 
 _ws_cache: dict = {}
 
+# kernels of THIS library launched through the wrappers (bench.py reports it as gpu_launches)
+COUNTERS = {"launches": 0}
+
+
+def _count(n: int):
+    COUNTERS["launches"] += n
+
+
+def fp32_peak_tflops(device=None) -> float:
+    """Measured FP32 FMA-pipe throughput (tg_fp32_peak)."""
+    lib = L.load()
+    out = C.c_double()
+    L.check(lib.tg_fp32_peak(L.ctx(device), C.byref(out)), "tg_fp32_peak")
+    return float(out.value)
+
 
 def _need(t: torch.Tensor, dtype, name: str, shape=None):
     if not (isinstance(t, torch.Tensor) and t.is_cuda):
@@ -76,6 +91,7 @@ def rollout(kind, max_steps, dt, dims, activation, params, cov_diag, init_state,
                             L.ptr(out["act"]), L.ptr(out["rew"]), L.ptr(out.get("logp")), L.ptr(out["len"]),
                             L.ptr(out.get("ret")), L.stream_ptr())
     L.check(rc, "tg_rollout")
+    _count(2)
     return out
 
 
@@ -87,6 +103,7 @@ def noise_fill(seed, N, T, A, device=None, env_offset=0):
         L.check(lib.tg_noise_fill(L.ctx(dev), int(seed) & (2 ** 64 - 1), int(env_offset), N, T, A, L.ptr(out),
                                   L.stream_ptr()),
                 "tg_noise_fill")
+    _count(1)
     return out
 
 
@@ -112,6 +129,7 @@ def env_step(kind, max_steps, dt, state, raw_action, steps_done=None, bal_count=
         rc = lib.tg_env_step(L.ctx(dev), C.byref(ecfg), prec, N, L.ptr(state), L.ptr(raw_action), L.ptr(steps_done),
                              L.ptr(bal_count), L.ptr(nxt), L.ptr(rew), L.ptr(done), L.ptr(bal), L.stream_ptr())
     L.check(rc, "tg_env_step")
+    _count(1)
     return nxt, rew, done, bal
 
 
@@ -124,6 +142,7 @@ def quadrotor12_dynamics(state, control, dt=0.05):
     with torch.cuda.device(state.device):
         L.check(lib.tg_quadrotor12_dynamics(L.ctx(state.device), prec, state.shape[1], float(dt), L.ptr(state),
                                             L.ptr(control), L.ptr(out), L.stream_ptr()), "tg_quadrotor12_dynamics")
+    _count(1)
     return out
 
 
@@ -145,6 +164,33 @@ def policy_forward(dims, activation, params, x, cov_diag=None, act=None, want_mu
         rc = lib.tg_policy_forward(L.ctx(dev), C.byref(mcfg), M, L.ptr(x), L.ptr(params), cov, L.ptr(act), L.ptr(mu),
                                    L.ptr(logp), L.stream_ptr())
     L.check(rc, "tg_policy_forward")
+    _count(2)
+    return mu, logp
+
+
+def policy_forward_traj(dims, activation, params, obs, cov_diag=None, act=None, length=None, want_mu=False,
+                        want_logp=True):
+    """tg_policy_forward_traj.  obs [T,O,N] (+ act [T,A,N]) -> (mu [T,A,N] | None, logp [T,N] | None);
+    rows past `length` are left unwritten."""
+    lib = L.load()
+    _need(obs, torch.float32, "obs")
+    T, O, N = obs.shape
+    A = int(dims[-1])
+    dev = obs.device
+    _need(params, torch.float32, "params")
+    if act is not None:
+        _need(act, torch.float32, "act", (T, A, N))
+    if length is not None:
+        _need(length, torch.int32, "len", (N,))
+    mu = torch.zeros((T, A, N), dtype=torch.float32, device=dev) if want_mu else None
+    logp = torch.zeros((T, N), dtype=torch.float32, device=dev) if want_logp else None
+    mcfg = L.mlp_cfg(dims, activation)
+    cov = L.cov_array(cov_diag) if cov_diag is not None else None
+    with torch.cuda.device(dev):
+        rc = lib.tg_policy_forward_traj(L.ctx(dev), C.byref(mcfg), N, T, L.ptr(obs), L.ptr(act), L.ptr(length),
+                                        L.ptr(params), cov, L.ptr(mu), L.ptr(logp), L.stream_ptr())
+    L.check(rc, "tg_policy_forward_traj")
+    _count(2)
     return mu, logp
 
 
@@ -165,6 +211,7 @@ def advantage(mode, G, E, T, gamma, lam, rew, length, values=None, want_rtg=Fals
         rc = lib.tg_advantage(L.ctx(dev), mode, G, E, T, float(gamma), float(lam), L.ptr(rew), L.ptr(length),
                               L.ptr(values), L.ptr(adv), L.ptr(rtg), L.ptr(ws), L.stream_ptr())
     L.check(rc, "tg_advantage")
+    _count(1 if mode == L.ADV_GRPO else 3)
     return adv, rtg
 
 
@@ -190,6 +237,7 @@ def policy_grad(dims, activation, params, cov_diag, obs, act, adv, old_logp, len
                                 L.ptr(length), L.ptr(params), L.cov_array(cov_diag), float(eps_clip), float(scale),
                                 float(kl_scale), L.ptr(grad), L.ptr(stats), L.ptr(ws), L.stream_ptr())
     L.check(rc, "tg_policy_grad")
+    _count(3)
     return grad, stats
 
 
@@ -210,6 +258,7 @@ def value_grad(dims, activation, params, obs, target, length, scale, out_grad=No
         rc = lib.tg_value_grad(L.ctx(dev), C.byref(mcfg), N, T, L.ptr(obs), L.ptr(target), L.ptr(length),
                                L.ptr(params), float(scale), L.ptr(grad), L.ptr(stats), L.ptr(ws), L.stream_ptr())
     L.check(rc, "tg_value_grad")
+    _count(3)
     return grad, stats
 
 
@@ -222,3 +271,4 @@ def adam_step(params, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.99
                               L.ptr(exp_avg_sq), int(step), float(lr), float(beta1), float(beta2), float(eps),
                               L.stream_ptr())
     L.check(rc, "tg_adam_step")
+    _count(1)
