@@ -131,7 +131,15 @@ extern "C" int tg_fp32_peak(tg_ctx *ctx, double *out_tflops) {
     return TG_OK;
 }
 
-int tg_build_layout(const tg_mlp_cfg *mlp, bool with_backward, tg_mlp_layout *out) {
+size_t tg_update_smem_bytes(const tg_mlp_layout &lay, bool with_weights) {
+    const int B = lay.B, NT = lay.NT, LDX = B + 4;
+    size_t fl = (size_t)tg_round_up(lay.O, 8) * LDX + (size_t)(lay.n_layers - 1) * lay.NP * LDX + 8 * LDX +
+                (size_t)(NT / B) * TG_MAX_ACT * B;
+    if (with_weights) fl += (size_t)lay.total;
+    return fl * sizeof(float);
+}
+
+int tg_build_layout(const tg_mlp_cfg *mlp, bool with_backward, tg_mlp_layout *out, int smem_limit) {
     TG_REQUIRE(mlp != nullptr, TG_ERR_ARG, "mlp cfg is null");
     TG_REQUIRE(mlp->n_layers >= 1 && mlp->n_layers <= TG_MAX_LAYERS, TG_ERR_SHAPE, "n_layers %d not in [1,%d]",
                mlp->n_layers, TG_MAX_LAYERS);
@@ -151,11 +159,19 @@ int tg_build_layout(const tg_mlp_cfg *mlp, bool with_backward, tg_mlp_layout *ou
     out->n_layers = nl;
     out->act = mlp->activation;
     out->cfg = maxh <= 64 ? 0 : (maxh <= 128 ? 1 : 2);
-    out->B = out->cfg == 2 ? 64 : 128;
-    out->NT = out->cfg == 0 ? 128 : 256;
-    out->NP = out->cfg == 0 ? 64 : (out->cfg == 1 ? 128 : 256);
     out->O = mlp->dims[0];
     out->A = mlp->dims[nl];
+    for (;;) {
+        static const int Bs[4] = {128, 128, 64, 64}, NTs[4] = {128, 256, 256, 128}, NPs[4] = {64, 128, 256, 128};
+        out->B = Bs[out->cfg];
+        out->NT = NTs[out->cfg];
+        out->NP = NPs[out->cfg];
+        if (smem_limit <= 0 || out->cfg != 1) break;
+        // deep width-128 nets (e.g. the reference's CartPole 128^4): the B=128 activation tiles of
+        // the update kernel do not fit -> halve the sample tile
+        if (tg_update_smem_bytes(*out, false) <= (size_t)smem_limit) break;
+        out->cfg = 3;
+    }
     // hidden outputs are stored for NP (padded) neurons, so the buffers need NP rows
     out->kmax = nl > 1 ? (out->NP > kmax ? out->NP : kmax) : kmax;
     int64_t off = 0, flat = 0;

@@ -48,6 +48,8 @@ template <int CFG> struct TileCfg;
 template <> struct TileCfg<0> { static constexpr int B = 128, NT = 128, NP = 64; };
 template <> struct TileCfg<1> { static constexpr int B = 128, NT = 256, NP = 128; };
 template <> struct TileCfg<2> { static constexpr int B = 64, NT = 256, NP = 256; };
+//   cfg 3: B= 64 NT=128 NP=128   width <= 128, update kernels of deep nets (activation tiles of cfg 1 too large)
+template <> struct TileCfg<3> { static constexpr int B = 64, NT = 128, NP = 128; };
 
 // Staged weight layout (built on the device by tg_pack_kernel from the flat
 // torch-order vector).  For every hidden Linear l (input K_l, output N_l<=NP):
@@ -69,7 +71,9 @@ struct tg_mlp_layout {
     int64_t total;   // floats in the staged buffer
     int64_t n_params;
 };
-int tg_build_layout(const tg_mlp_cfg *mlp, bool with_backward, tg_mlp_layout *out);
+// smem_limit > 0 (update kernels): pick the tile configuration whose activation tiles fit
+int tg_build_layout(const tg_mlp_cfg *mlp, bool with_backward, tg_mlp_layout *out, int smem_limit = 0);
+size_t tg_update_smem_bytes(const tg_mlp_layout &lay, bool with_weights);
 int tg_pack_weights(tg_ctx *ctx, const tg_mlp_layout &lay, const float *params, cudaStream_t st);
 
 TG_HD int tg_round_up(int x, int m) { return (x + m - 1) / m * m; }

@@ -283,11 +283,7 @@ __global__ void grad_reduce_kernel(int grid, int64_t n_params, const float *__re
 }
 
 static size_t update_smem_bytes(const tg_mlp_layout &lay, bool with_weights) {
-    const int B = lay.B, NT = lay.NT, LDX = B + 4;
-    size_t fl = (size_t)tg_round_up(lay.O, 8) * LDX + (size_t)(lay.n_layers - 1) * lay.NP * LDX + 8 * LDX +
-                (size_t)(NT / B) * TG_MAX_ACT * B;
-    if (with_weights) fl += (size_t)lay.total;
-    return fl * sizeof(float);
+    return tg_update_smem_bytes(lay, with_weights);
 }
 
 static int update_grid(const tg_ctx *ctx, const tg_mlp_layout &lay) {
@@ -325,6 +321,7 @@ static int dispatch_update_cfg(const tg_ctx *ctx, const UpdArgs &a, int grid, cu
     switch (a.lay.cfg) {
         case 0: return launch_update<0, A>(ctx, a, grid, st);
         case 1: return launch_update<1, A>(ctx, a, grid, st);
+        case 3: return launch_update<3, A>(ctx, a, grid, st);
         default: return launch_update<2, A>(ctx, a, grid, st);
     }
 }
@@ -333,15 +330,17 @@ static int dispatch_update(const tg_ctx *ctx, const UpdArgs &a, int grid, cudaSt
     switch (a.lay.A) {
         case 1: return dispatch_update_cfg<1>(ctx, a, grid, st);
         case 2: return dispatch_update_cfg<2>(ctx, a, grid, st);
-        case 3: return dispatch_update_cfg<3>(ctx, a, grid, st);
-        default: return dispatch_update_cfg<4>(ctx, a, grid, st);
+        case 4: return dispatch_update_cfg<4>(ctx, a, grid, st);
+        default:
+            tg_set_error("output dim %d has no update kernel instance (1, 2 and 4 are built)", a.lay.A);
+            return TG_ERR_UNSUPPORTED;
     }
 }
 
 extern "C" int64_t tg_policy_grad_workspace_bytes(const tg_ctx *ctx, const tg_mlp_cfg *mlp) {
     if (!ctx || !mlp) return -1;
     tg_mlp_layout lay;
-    if (tg_build_layout(mlp, true, &lay)) return -1;
+    if (tg_build_layout(mlp, true, &lay, ctx->smem_optin)) return -1;
     const int64_t grid = update_grid(ctx, lay);
     return grid * lay.n_params * (int64_t)sizeof(float) + grid * 4 * (int64_t)sizeof(double) + 256;
 }
@@ -388,7 +387,7 @@ extern "C" int tg_policy_grad(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int
     TG_REQUIRE(N > 0 && T > 0, TG_ERR_SHAPE, "tg_policy_grad: N and T must be positive");
     UpdArgs a;
     memset(&a, 0, sizeof(a));
-    int rc = tg_build_layout(mlp, true, &a.lay);
+    int rc = tg_build_layout(mlp, true, &a.lay, ctx->smem_optin);
     if (rc) return rc;
     rc = fill_gauss(a, cov_diag, a.lay.A);
     if (rc) return rc;
@@ -407,7 +406,7 @@ extern "C" int tg_value_grad(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int 
     TG_REQUIRE(mlp->dims[mlp->n_layers] == 1, TG_ERR_SHAPE, "critic output dim must be 1");
     UpdArgs a;
     memset(&a, 0, sizeof(a));
-    int rc = tg_build_layout(mlp, true, &a.lay);
+    int rc = tg_build_layout(mlp, true, &a.lay, ctx->smem_optin);
     if (rc) return rc;
     a.N = N; a.T = T; a.head = HEAD_VALUE;
     a.obs = obs; a.target = target; a.len = len; a.scale = scale;
@@ -423,7 +422,7 @@ extern "C" int tg_policy_forward(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t M, 
     TG_REQUIRE(M > 0, TG_ERR_SHAPE, "M must be positive");
     UpdArgs a;
     memset(&a, 0, sizeof(a));
-    int rc = tg_build_layout(mlp, false, &a.lay);
+    int rc = tg_build_layout(mlp, false, &a.lay, ctx->smem_optin);
     if (rc) return rc;
     if (cov_diag) {
         rc = fill_gauss(a, cov_diag, a.lay.A);
@@ -453,7 +452,7 @@ extern "C" int tg_policy_forward_traj(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_
     TG_REQUIRE(N > 0 && T > 0, TG_ERR_SHAPE, "N and T must be positive");
     UpdArgs a;
     memset(&a, 0, sizeof(a));
-    int rc = tg_build_layout(mlp, false, &a.lay);
+    int rc = tg_build_layout(mlp, false, &a.lay, ctx->smem_optin);
     if (rc) return rc;
     if (cov_diag) {
         rc = fill_gauss(a, cov_diag, a.lay.A);
