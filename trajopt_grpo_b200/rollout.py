@@ -103,6 +103,30 @@ def _device_rollout(env, policy, G, E, restart, rng, seed, precision="f32", init
                          int(env.max_steps), tag)
 
 
+def plan_shard(num_workers: int, group_size: int, rank: int, world_size: int):
+    """Whole GRPO groups per GPU: rank r owns the contiguous block of
+    `num_workers / world_size` groups; returns (local groups, first global env index)."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise L.EngineError(f"bad rank/world_size {rank}/{world_size}")
+    if num_workers % world_size != 0:
+        raise L.EngineError(f"num_workers={num_workers} must be divisible by world_size={world_size} "
+                            "(whole GRPO groups per GPU)")
+    g_local = num_workers // world_size
+    return g_local, rank * g_local * group_size
+
+
+def shard_initial_states(env, num_workers: int, group_size: int, restart: bool, rng, rank: int, world_size: int):
+    """Every rank draws the SAME global initial states from the same generator state and
+    keeps its block, so a sharded rollout equals the matching slice of the single-GPU one.
+    Returns [local envs, S] float64."""
+    g_local, first = plan_shard(num_workers, group_size, rank, world_size)
+    if restart:
+        s0 = np.repeat(env.sample_initial_states(num_workers, rng), group_size, axis=0)
+    else:
+        s0 = env.sample_initial_states(num_workers * group_size, rng)
+    return s0[first:first + g_local * group_size]
+
+
 class RolloutManager:
     """rollout/rollout_manager.py:22-133."""
 
@@ -122,11 +146,8 @@ class RolloutManager:
         self.episodes_completed = [0 for _ in range(num_workers)]
         self.precision = precision
         # multi-GPU: this rank owns a contiguous block of whole groups
-        if num_workers % world_size != 0:
-            raise L.EngineError(f"num_workers={num_workers} must be divisible by world_size={world_size} "
-                                "(whole GRPO groups per GPU)")
         self.rank, self.world_size = rank, world_size
-        self.local_workers = num_workers // world_size
+        self.local_workers, self.env_offset = plan_shard(num_workers, num_episodes_per_worker, rank, world_size)
         self._seed = int(np.random.SeedSequence(seed).generate_state(1, np.uint64)[0]) if seed is not None \
             else int(np.random.SeedSequence().generate_state(1, np.uint64)[0])
         self._rng = np.random.default_rng(self._seed)
@@ -141,16 +162,14 @@ class RolloutManager:
         the struct-of-arrays result without materialising masks."""
         G, E = self.local_workers, self.num_episodes_per_worker
         if init_state is None and self.world_size > 1:
-            # every rank draws the same global initial states and keeps its block
-            s0 = self.env.sample_initial_states(self.num_workers if self.restart else self.num_workers * E, self._rng)
-            s0 = np.repeat(s0, E, axis=0) if self.restart else s0
-            blk = s0[self.rank * G * E:(self.rank + 1) * G * E]
+            blk = shard_initial_states(self.env, self.num_workers, E, self.restart, self._rng, self.rank,
+                                       self.world_size)
             dtype = torch.float64 if self.precision == "f64" else torch.float32
             init_state = torch.from_numpy(np.ascontiguousarray(blk.T)).to(dtype).pin_memory().cuda(non_blocking=True)
         seed = (self._seed + 0x9E3779B97F4A7C15 * (self._epoch + 1)) & (2 ** 64 - 1)
         self._epoch += 1
         self.last = _device_rollout(self.env, self.policy, G, E, self.restart, self._rng, seed, self.precision,
-                                    init_state=init_state, noise=noise, env_offset=self.rank * G * E)
+                                    init_state=init_state, noise=noise, env_offset=self.env_offset)
         for i in range(self.num_workers):
             self.episodes_completed[i] = 0
         return self.last
