@@ -98,9 +98,26 @@ int tg_ctx_create(int device, tg_ctx **out);
 void tg_ctx_destroy(tg_ctx *ctx);
 int tg_ctx_sm_count(const tg_ctx *ctx);
 
+/* Arithmetic of the hidden->hidden MLP GEMMs inside tg_rollout / tg_policy_grad:
+ *   TG_MATH_AUTO   tensor cores (tcgen05.mma kind::tf32 with the 3xTF32 hi/lo split, fp32
+ *                  accumulation in TMEM) when the policy shape is eligible, FP32 FMA pipe otherwise
+ *   TG_MATH_FP32   always the FP32 FMA pipe (register-tiled GEMMs)
+ *   TG_MATH_3XTF32 require the tensor-core path (TG_ERR_UNSUPPORTED if the shape is not eligible)
+ * Default: TG_MATH_AUTO. */
+#define TG_MATH_AUTO 0
+#define TG_MATH_FP32 1
+#define TG_MATH_3XTF32 2
+int tg_ctx_set_math(tg_ctx *ctx, int math_mode);
+
 /* Measured FP32 FMA-pipe throughput of the device (TFLOP/s), the roofline of the
  * register-tiled MLP GEMMs; bench.py reports K1/K3 against it. */
 int tg_fp32_peak(tg_ctx *ctx, double *out_tflops);
+
+/* Tensor-core self test: D[128][N] = A[128][K] * B[N][K]^T (row-major fp32 in/out) through
+ * tcgen05.mma kind::tf32 with fp32 TMEM accumulation; passes = 1 (plain TF32) or 3 (3xTF32
+ * hi/lo split, fp32-faithful).  Exercises the UMMA descriptor / TMEM helpers of the fused kernels. */
+int tg_umma_selftest(tg_ctx *ctx, const float *A, const float *B, float *D, int K, int N, int passes,
+                     void *stream);
 
 /* dims of an env kind: returns 0 or TG_ERR_ARG */
 int tg_env_dims(int kind, int *obs_dim, int *act_dim);

@@ -1,0 +1,96 @@
+"""tcgen05 building blocks (descriptors, SWIZZLE_128B operand layout, TMEM load) pinned against a
+float64 matmul before the fused kernels rely on them."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(K, N, passes, seed=0):
+    from trajopt_grpo_b200 import _lib as L
+    lib = L.load()
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((128, K)).astype(np.float32)
+    B = rng.standard_normal((N, K)).astype(np.float32)
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    dD = torch.full((128, N), float("nan"), device="cuda")
+    rc = lib.tg_umma_selftest(L.ctx(), dA.data_ptr(), dB.data_ptr(), dD.data_ptr(), K, N, passes, L.stream_ptr())
+    L.check(rc, "tg_umma_selftest")
+    torch.cuda.synchronize()
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    return dD.cpu().numpy(), ref
+
+
+@pytest.mark.parametrize("K,N", [(32, 64), (64, 64), (128, 64), (64, 128), (32, 256), (64, 16)])
+def test_umma_tf32_single_pass(K, N):
+    got, ref = _run(K, N, 1)
+    # plain TF32: 10-bit mantissa operands -> ~1e-3 relative to the row scale
+    assert np.isfinite(got).all()
+    assert np.abs(got - ref).max() <= 4e-3 * np.sqrt(K) * 3
+
+
+@pytest.mark.parametrize("K,N", [(32, 64), (64, 64), (128, 64), (64, 128), (32, 256), (64, 16)])
+def test_umma_3xtf32_is_fp32_faithful(K, N):
+    got, ref = _run(K, N, 3, seed=1)
+    # 3xTF32 split: error of the order of fp32 rounding of the dot product
+    scale = np.sqrt(K)
+    assert np.abs(got - ref).max() <= 2e-6 * scale * 4, np.abs(got - ref).max()
+
+
+# ----------------------------------------------------------------------------
+# fused rollout on the tensor-core path vs the FP32 path and vs the oracle
+# ----------------------------------------------------------------------------
+def _policy(rng, dims):
+    Ws = [(rng.standard_normal((dims[i + 1], dims[i])) / np.sqrt(dims[i])).astype(np.float32) for i in range(len(dims) - 1)]
+    bs = [(0.1 * rng.standard_normal(dims[i + 1])).astype(np.float32) for i in range(len(dims) - 1)]
+    flat = np.concatenate([np.concatenate([w.reshape(-1), b]) for w, b in zip(Ws, bs)]).astype(np.float32)
+    return Ws, bs, torch.from_numpy(flat).cuda()
+
+
+@pytest.mark.parametrize("kind,hidden", [(1, [64, 64]), (3, [64, 64]), (2, [64, 64, 64]), (0, [64, 64])])
+def test_rollout_tensor_core_path_matches_fp32_path_and_oracle(kind, hidden):
+    import restate as R
+    from trajopt_grpo_b200 import engine as E
+    rng = np.random.default_rng(kind)
+    O, A = R.OBS_DIM[kind], R.ACT_DIM[kind]
+    dims = [O] + hidden + [A]
+    Ws, bs, params = _policy(rng, dims)
+    N, T = 300, 16
+    init = R.reset_states(kind, N, rng)
+    noise = rng.standard_normal((T, N, A)).astype(np.float32)
+    cov = np.full(A, 0.3, np.float32)
+    cfg = R.EnvCfg.make(kind, T)
+    o, a, r, lp, ln, m = R.rollout(cfg, init, Ws, bs, cov, noise, dtype=np.float64)
+    nz = torch.from_numpy(np.ascontiguousarray(noise.transpose(0, 2, 1))).cuda()
+    s0 = torch.from_numpy(init.T.copy()).cuda()
+    outs = {}
+    try:
+        for mode in ("fp32", "3xtf32"):
+            E.set_math(mode)
+            outs[mode] = E.rollout(kind, T, cfg.dt, dims, "ReLU", params, cov.tolist(), s0, noise=nz)
+            torch.cuda.synchronize()
+    finally:
+        E.set_math("auto")
+    for mode, out in outs.items():
+        assert np.array_equal(out["len"].cpu().numpy(), ln), mode
+        np.testing.assert_allclose(out["obs"].cpu().numpy().transpose(2, 0, 1), o, rtol=1e-4, atol=1e-4, err_msg=mode)
+        np.testing.assert_allclose(out["act"].cpu().numpy().transpose(2, 0, 1), a, rtol=1e-4, atol=1e-4, err_msg=mode)
+        np.testing.assert_allclose(out["logp"].cpu().numpy().T, lp, rtol=1e-4, atol=1e-4, err_msg=mode)
+    # first step (no accumulated drift): the mean action of the two paths agrees to 3xTF32 accuracy
+    a32, atc = outs["fp32"]["act"][0].cpu().numpy(), outs["3xtf32"]["act"][0].cpu().numpy()
+    assert np.abs(a32 - atc).max() <= 2e-5 * max(1.0, np.abs(a32).max())
+
+
+def test_math_mode_3xtf32_rejects_ineligible_shape():
+    from trajopt_grpo_b200 import engine as E
+    from trajopt_grpo_b200._lib import EngineError
+    params = torch.zeros(3 * 32 + 32 + 32 * 1 + 1, device="cuda")
+    try:
+        E.set_math("3xtf32")
+        with pytest.raises(EngineError, match="not eligible"):
+            E.rollout(1, 5, 0.05, [3, 32, 1], "ReLU", params, [0.5], torch.zeros(3, 8, device="cuda"))
+    finally:
+        E.set_math("auto")

@@ -38,17 +38,128 @@ extern "C" int tg_ctx_create(int device, tg_ctx **out) {
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
     c->packed = nullptr;
     c->packed_cap = 0;
+    c->packed_tc = nullptr;
+    c->packed_tc_cap = 0;
+    c->math_mode = TG_MATH_AUTO;
     *out = c;
     return TG_OK;
 }
 
 extern "C" void tg_ctx_destroy(tg_ctx *ctx) {
     if (!ctx) return;
-    if (ctx->packed) {
-        cudaSetDevice(ctx->device);
-        cudaFree(ctx->packed);
-    }
+    cudaSetDevice(ctx->device);
+    if (ctx->packed) cudaFree(ctx->packed);
+    if (ctx->packed_tc) cudaFree(ctx->packed_tc);
     delete ctx;
+}
+
+extern "C" int tg_ctx_set_math(tg_ctx *ctx, int math_mode) {
+    TG_REQUIRE(ctx != nullptr, TG_ERR_ARG, "tg_ctx_set_math: ctx is null");
+    TG_REQUIRE(math_mode >= TG_MATH_AUTO && math_mode <= TG_MATH_3XTF32, TG_ERR_ARG, "unknown math mode %d", math_mode);
+    ctx->math_mode = math_mode;
+    return TG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// tensor-core staging
+// ---------------------------------------------------------------------------
+bool tg_tc_eligible(const tg_mlp_cfg *mlp) {
+    if (!mlp || mlp->n_layers < 3 || mlp->n_layers > TG_MAX_LAYERS) return false;   // >= 2 hidden layers
+    for (int l = 1; l < mlp->n_layers; ++l)
+        if (mlp->dims[l] != TC_W) return false;
+    return mlp->dims[0] >= 1 && mlp->dims[0] <= TG_MAX_OBS && mlp->dims[mlp->n_layers] >= 1 &&
+           mlp->dims[mlp->n_layers] <= TG_MAX_ACT && mlp->activation >= 0 && mlp->activation <= 2;
+}
+
+int tg_build_tc_layout(const tg_mlp_cfg *mlp, tg_tc_layout *out) {
+    TG_REQUIRE(tg_tc_eligible(mlp), TG_ERR_UNSUPPORTED,
+               "tensor-core path needs >= 2 hidden layers, all of width %d", TC_W);
+    memset(out, 0, sizeof(*out));
+    const int nl = mlp->n_layers;
+    out->n_layers = nl;
+    out->nh = nl - 1;
+    out->act = mlp->activation;
+    out->O = mlp->dims[0];
+    out->O4 = tg_round_up(out->O + 1, 4);
+    out->A = mlp->dims[nl];
+    int64_t flat = 0;
+    for (int l = 0; l < nl; ++l) {
+        out->flat_w[l] = flat;
+        flat += (int64_t)mlp->dims[l] * mlp->dims[l + 1] + mlp->dims[l + 1];
+    }
+    out->n_params = flat;
+    int64_t off = 0;   // floats; MMA operand blocks 1024-byte (256-float) aligned
+    for (int l = 1; l < nl - 1; ++l) {
+        out->whi[l] = off; off += TC_W * TC_W;
+        out->wlo[l] = off; off += TC_W * TC_W;
+    }
+    for (int l = 1; l < nl - 1; ++l) { out->bias[l] = off; off += TC_W; }
+    out->w1 = off; off += (int64_t)TC_W * out->O4;
+    out->wo = off; off += (int64_t)out->A * TC_W;
+    out->bo = off; off += 4;
+    out->total = tg_round_up((int)off, 4);
+    return TG_OK;
+}
+
+__global__ void pack_tc_kernel(tg_tc_layout lay, const float *__restrict__ params, float *__restrict__ packed) {
+    const int nl = lay.n_layers;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < lay.total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float v = 0.0f;
+        // first Linear: rows (W1[n][:], b1[n], 0..)
+        if (i >= lay.w1 && i < lay.w1 + (int64_t)TC_W * lay.O4) {
+            const int n = (int)((i - lay.w1) / lay.O4), o = (int)((i - lay.w1) % lay.O4);
+            const float *Wf = params + lay.flat_w[0];
+            if (o < lay.O) v = Wf[(int64_t)n * lay.O + o];
+            else if (o == lay.O) v = Wf[(int64_t)TC_W * lay.O + n];
+        } else if (i >= lay.wo && i < lay.wo + (int64_t)lay.A * TC_W) {
+            v = params[lay.flat_w[nl - 1] + (i - lay.wo)];
+        } else if (i >= lay.bo && i < lay.bo + lay.A) {
+            v = params[lay.flat_w[nl - 1] + (int64_t)lay.A * TC_W + (i - lay.bo)];
+        } else {
+            for (int l = 1; l < nl - 1; ++l) {
+                const float *Wf = params + lay.flat_w[l];   // [N][K] torch layout = K-major B operand
+                if (i >= lay.bias[l] && i < lay.bias[l] + TC_W) v = Wf[(int64_t)TC_W * TC_W + (i - lay.bias[l])];
+                const bool hi = i >= lay.whi[l] && i < lay.whi[l] + TC_W * TC_W;
+                const bool lo = i >= lay.wlo[l] && i < lay.wlo[l] + TC_W * TC_W;
+                if (hi || lo) {
+                    // invert the SWIZZLE_128B K-major layout: byte offset -> (row n, k)
+                    const uint32_t b = (uint32_t)(i - (hi ? lay.whi[l] : lay.wlo[l])) * 4u;
+                    const int kb = (int)(b / (TC_W * 128u));
+                    const uint32_t r = b % (TC_W * 128u);
+                    const int n = (int)(r / 128u);
+                    const int chunk = (int)((r % 128u) >> 4) ^ (n & 7);
+                    const int k = kb * 32 + chunk * 4 + (int)((r & 15u) >> 2);
+                    const float w = Wf[(int64_t)n * TC_W + k];
+                    uint32_t hb;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));
+                    const float whi = __uint_as_float(hb & 0xffffe000u);
+                    v = hi ? whi : (w - whi);
+                }
+            }
+        }
+        packed[i] = v;
+    }
+}
+
+int tg_pack_weights_tc(tg_ctx *ctx, const tg_tc_layout &lay, const float *params, cudaStream_t st) {
+    const size_t bytes = (size_t)lay.total * sizeof(float);
+    if (bytes > ctx->packed_tc_cap) {
+        TG_CUDA(cudaSetDevice(ctx->device));
+        if (ctx->packed_tc) {
+            TG_CUDA(cudaDeviceSynchronize());
+            TG_CUDA(cudaFree(ctx->packed_tc));
+            ctx->packed_tc = nullptr;
+            ctx->packed_tc_cap = 0;
+        }
+        TG_CUDA(cudaMalloc(&ctx->packed_tc, bytes));
+        ctx->packed_tc_cap = bytes;
+    }
+    int64_t blocks = (lay.total + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    pack_tc_kernel<<<(unsigned)blocks, 256, 0, st>>>(lay, params, ctx->packed_tc);
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
 }
 
 extern "C" int tg_ctx_sm_count(const tg_ctx *ctx) { return ctx ? ctx->sm_count : 0; }

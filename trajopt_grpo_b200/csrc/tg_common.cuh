@@ -34,6 +34,9 @@ struct tg_ctx {
     int smem_optin;  // max dynamic shared memory per block (bytes)
     float *packed;   // staged (transposed / padded) policy weights, device
     size_t packed_cap;
+    float *packed_tc;  // staged tensor-core operands (hi/lo split, SWIZZLE_128B), device
+    size_t packed_tc_cap;
+    int math_mode;     // TG_MATH_*
 };
 int tg_ctx_reserve_packed(tg_ctx *ctx, size_t bytes);
 
@@ -77,3 +80,24 @@ size_t tg_update_smem_bytes(const tg_mlp_layout &lay, bool with_weights);
 int tg_pack_weights(tg_ctx *ctx, const tg_mlp_layout &lay, const float *params, cudaStream_t st);
 
 TG_HD int tg_round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---- tensor-core (tcgen05, 3xTF32) staging ----------------------------------------
+// Eligible policies: >= 2 hidden layers, every hidden width == TC_W (64).  The first
+// Linear (K = obs dim) and the output Linear (N = act dim <= 4) stay on the FP32 pipe;
+// every hidden->hidden Linear is a [128 x 64] x [64 x 64] UMMA per tile.
+// Staged buffer (floats; the kernel bulk-copies it to a 1024-byte aligned smem base):
+//   w1   [TC_W][O4]            row n = (W1[n][0..O), b1[n], 0...)   O4 = roundup(O+1, 4)
+//   per hidden->hidden layer l (1024-byte aligned):
+//        w_hi [TC_W x TC_W] K-major SWIZZLE_128B (tg_umma.cuh), w_lo same, bias [TC_W]
+//   wo   [A][TC_W], bo [4]
+#define TC_W 64
+struct tg_tc_layout {
+    int n_layers, nh, act, O, O4, A;
+    int64_t flat_w[TG_MAX_LAYERS];     // offsets of each Linear in the flat torch vector
+    int64_t w1, whi[TG_MAX_LAYERS], wlo[TG_MAX_LAYERS], bias[TG_MAX_LAYERS], wo, bo;
+    int64_t total;                     // floats
+    int64_t n_params;
+};
+bool tg_tc_eligible(const tg_mlp_cfg *mlp);
+int tg_build_tc_layout(const tg_mlp_cfg *mlp, tg_tc_layout *out);
+int tg_pack_weights_tc(tg_ctx *ctx, const tg_tc_layout &lay, const float *params, cudaStream_t st);

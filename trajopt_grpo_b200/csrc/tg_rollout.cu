@@ -18,6 +18,7 @@
 
 #include "tg_env.cuh"
 #include "tg_mlp.cuh"
+#include "tg_umma.cuh"
 
 struct RolloutArgs {
     EnvParams env;
@@ -174,6 +175,226 @@ static int dispatch_prec(int precision, const RolloutArgs &a, size_t smem, bool 
                                     : dispatch_cfg<KIND, float>(a, smem, wg, st);
 }
 
+// ---------------------------------------------------------------------------
+// Tensor-core variant (TG_MATH_AUTO / TG_MATH_3XTF32, eligible policies: tg_tc_eligible).
+// 128 threads, thread i = env i of the tile = TMEM lane i.  Per step each thread evaluates
+// the first Linear for its own env on the FP32 pipe, writes its activation row (hi/lo
+// split) straight into the K-major SWIZZLE_128B A operand in shared memory, one elected
+// thread issues the 3xTF32 tcgen05.mma sequence for the [128 x 64] x [64 x 64] hidden
+// GEMM (weights hi/lo resident in shared memory, staged once by TMA), the accumulator
+// comes back from TMEM with tcgen05.ld -- each thread receives exactly its env's row --
+// and bias/activation/output layer/sampling/dynamics continue in registers.
+// ---------------------------------------------------------------------------
+struct RolloutTcArgs {
+    EnvParams env;
+    tg_tc_layout lay;
+    int64_t N;
+    const void *init_state;
+    const float *packed;
+    const float *noise;
+    uint64_t seed;
+    int64_t env_offset;
+    float sd[TG_MAX_ACT], log_norm;
+    float *obs, *act, *rew, *logp, *ret;
+    int32_t *len;
+};
+
+// RELU: the activation is known at compile time (no per-element branch); otherwise a.lay.act
+template <int KIND, typename R, bool RELU>
+__global__ void __launch_bounds__(128) rollout_tc_kernel(const __grid_constant__ RolloutTcArgs a) {
+    using E = Env<KIND>;
+    constexpr int S = E::S, A = E::A, W = TC_W, O4 = (S + 1 + 3) / 4 * 4;
+    // 1024-byte alignment comes from the declaration (no integer pointer arithmetic, so the
+    // compiler keeps every access below in the shared address space: LDS/STS, not generic LD)
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t wbar, mbar;
+    __shared__ uint32_t tmem_slot;
+    unsigned char *base = smem_raw;
+    if ((smem_u32(base) & 1023u) != 0u) __trap();
+    float *Wsm = reinterpret_cast<float *>(base);
+    unsigned char *a_hi = base + ((size_t)a.lay.total * 4 + 1023) / 1024 * 1024;
+    unsigned char *a_lo = a_hi + 128 * W * 4;
+    stage_weights_tma(Wsm, a.packed, a.lay.total, &wbar);
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar, 1);
+        mbar_fence_init();
+    }
+    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = umma_idesc_tf32(128, W);
+    const uint32_t a_hi_u = smem_u32(a_hi), a_lo_u = smem_u32(a_lo), w_u = smem_u32(Wsm);
+    const int warp = threadIdx.x >> 5;
+    const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t row_off = (uint32_t)threadIdx.x * 128u;
+    const int rsw = threadIdx.x & 7;
+
+    const int T = a.env.max_steps;
+    const int64_t N = a.N;
+    const int64_t n = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const bool real_env = n < N;
+    bool alive = real_env;
+    R s[S];
+    int steps = 0, bal = 0;
+    float ret = 0.0f;
+    if (real_env) {
+        const R *init = reinterpret_cast<const R *>(a.init_state);
+#pragma unroll
+        for (int i = 0; i < S; ++i) s[i] = init[(int64_t)i * N + n];
+    } else {
+#pragma unroll
+        for (int i = 0; i < S; ++i) s[i] = (R)0;
+    }
+    const int nh = a.lay.nh, act_kind = RELU ? TG_ACT_RELU : a.lay.act;
+    const float *w1 = Wsm + a.lay.w1;
+    uint32_t phase = 0;
+    int t = 0;
+    for (; t < T; ++t) {
+        float x[S];
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            x[i] = alive ? (float)s[i] : 0.0f;
+            if (real_env) a.obs[((int64_t)t * S + i) * N + n] = x[i];
+        }
+        // first Linear on the FP32 pipe (K = obs dim is tiny): h = act(W1 x + b1)
+        float h[W];
+#pragma unroll
+        for (int nn = 0; nn < W; ++nn) {
+            float wrow[O4];
+#pragma unroll
+            for (int q = 0; q < O4; q += 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(w1 + nn * O4 + q);
+                wrow[q] = v.x; wrow[q + 1] = v.y; wrow[q + 2] = v.z; wrow[q + 3] = v.w;
+            }
+            float acc = wrow[S];
+#pragma unroll
+            for (int i = 0; i < S; ++i) acc = fmaf(wrow[i], x[i], acc);
+            h[nn] = act_fwd(acc, act_kind);
+        }
+        // hidden -> hidden Linears on the tensor cores
+        for (int l = 1; l < nh; ++l) {
+#pragma unroll
+            for (int c = 0; c < W / 4; ++c) {
+                float4 hi, lo;
+                hi.x = tf32_hi(h[4 * c]); hi.y = tf32_hi(h[4 * c + 1]);
+                hi.z = tf32_hi(h[4 * c + 2]); hi.w = tf32_hi(h[4 * c + 3]);
+                lo.x = h[4 * c] - hi.x; lo.y = h[4 * c + 1] - hi.y;
+                lo.z = h[4 * c + 2] - hi.z; lo.w = h[4 * c + 3] - hi.w;
+                const uint32_t off = (uint32_t)(c >> 3) * (128u * 128u) + row_off + (uint32_t)(((c & 7) ^ rsw) << 4);
+                *reinterpret_cast<float4 *>(a_hi + off) = hi;
+                *reinterpret_cast<float4 *>(a_lo + off) = lo;
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                tc_fence_after();
+                umma_gemm_3xtf32(tmem, a_hi_u, a_lo_u, 128, w_u + (uint32_t)a.lay.whi[l] * 4u,
+                                 w_u + (uint32_t)a.lay.wlo[l] * 4u, W, W, idesc, false, 3);
+                umma_commit(&mbar);
+            }
+            mbar_wait(&mbar, phase);
+            phase ^= 1u;
+            tc_fence_after();
+            const float *bl = Wsm + a.lay.bias[l];
+#pragma unroll
+            for (int c0 = 0; c0 < W; c0 += 32) {
+                float z[32];
+                tmem_ld32(my_tmem + (uint32_t)c0, z);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4 *>(bl + c0 + j);
+                    h[c0 + j] = act_fwd(z[j] + b4.x, act_kind);
+                    h[c0 + j + 1] = act_fwd(z[j + 1] + b4.y, act_kind);
+                    h[c0 + j + 2] = act_fwd(z[j + 2] + b4.z, act_kind);
+                    h[c0 + j + 3] = act_fwd(z[j + 3] + b4.w, act_kind);
+                }
+            }
+        }
+        // output Linear (A <= 4 neurons) on the FP32 pipe
+        float mu[A];
+        {
+            const float *wo = Wsm + a.lay.wo, *bo = Wsm + a.lay.bo;
+#pragma unroll
+            for (int j = 0; j < A; ++j) {
+                float acc = bo[j];
+#pragma unroll
+                for (int q = 0; q < W; q += 4) {
+                    const float4 v = *reinterpret_cast<const float4 *>(wo + j * W + q);
+                    acc = fmaf(h[q], v.x, acc); acc = fmaf(h[q + 1], v.y, acc);
+                    acc = fmaf(h[q + 2], v.z, acc); acc = fmaf(h[q + 3], v.w, acc);
+                }
+                mu[j] = acc;
+            }
+        }
+        float act[A], lp = 0.0f, rw = 0.0f;
+        if (alive) {
+            float eps[4];
+            if (a.noise != nullptr) {
+#pragma unroll
+                for (int j = 0; j < A; ++j) eps[j] = a.noise[((int64_t)t * A + j) * N + n];
+            } else {
+                philox_normal4(a.seed, (uint64_t)(a.env_offset + n), (uint32_t)t, eps);
+            }
+            float m2 = 0.0f;
+#pragma unroll
+            for (int j = 0; j < A; ++j) {
+                act[j] = mu[j] + a.sd[j] * eps[j];
+                const float z = (act[j] - mu[j]) / a.sd[j];
+                m2 += z * z;
+            }
+            lp = -0.5f * m2 - a.log_norm;
+            R r;
+            const bool done = E::template step<R>(s, act, a.env, steps, bal, r);
+            rw = (float)r;
+            ret += rw;
+            steps += 1;
+            alive = !done;
+        } else {
+#pragma unroll
+            for (int j = 0; j < A; ++j) act[j] = 0.0f;
+        }
+        if (real_env) {
+#pragma unroll
+            for (int j = 0; j < A; ++j) a.act[((int64_t)t * A + j) * N + n] = act[j];
+            a.rew[(int64_t)t * N + n] = rw;
+            if (a.logp) a.logp[(int64_t)t * N + n] = lp;
+        }
+        if (!__syncthreads_or(alive ? 1 : 0)) { ++t; break; }
+    }
+    if (real_env) {
+        for (; t < T; ++t) {
+#pragma unroll
+            for (int i = 0; i < S; ++i) a.obs[((int64_t)t * S + i) * N + n] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < A; ++j) a.act[((int64_t)t * A + j) * N + n] = 0.0f;
+            a.rew[(int64_t)t * N + n] = 0.0f;
+            if (a.logp) a.logp[(int64_t)t * N + n] = 0.0f;
+        }
+        a.len[n] = steps;
+        if (a.ret) a.ret[n] = ret;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem, 64);
+}
+
+template <int KIND>
+static int launch_rollout_tc(int precision, const RolloutTcArgs &a, cudaStream_t st) {
+    const size_t smem = 1024 + ((size_t)a.lay.total * 4 + 1023) / 1024 * 1024 + 2 * 128 * TC_W * 4;
+    const unsigned grid = (unsigned)((a.N + 127) / 128);
+    void (*kern)(const RolloutTcArgs);
+    const bool relu = a.lay.act == TG_ACT_RELU;
+    if (precision == TG_PREC_F64) kern = relu ? rollout_tc_kernel<KIND, double, true> : rollout_tc_kernel<KIND, double, false>;
+    else kern = relu ? rollout_tc_kernel<KIND, float, true> : rollout_tc_kernel<KIND, float, false>;
+    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 128, smem, st>>>(a);
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}
+
 static int fill_env_params(const tg_env_cfg *env, EnvParams *p) {
     TG_REQUIRE(env != nullptr, TG_ERR_ARG, "env cfg is null");
     TG_REQUIRE(env->kind >= 0 && env->kind <= 3, TG_ERR_ARG, "unknown env kind %d", env->kind);
@@ -202,10 +423,39 @@ extern "C" int tg_rollout(tg_ctx *ctx, const tg_env_cfg *env, const tg_mlp_cfg *
     TG_REQUIRE(mlp->n_layers >= 1 && mlp->dims[0] == O && mlp->dims[mlp->n_layers] == A, TG_ERR_SHAPE,
                "policy dims (%d -> %d) do not match env obs/act dims (%d/%d)", mlp->dims[0],
                mlp->dims[mlp->n_layers > 0 ? mlp->n_layers : 0], O, A);
-    rc = tg_build_layout(mlp, false, &a.lay);
-    if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     TG_CUDA(cudaSetDevice(ctx->device));
+    // ---- tensor-core path (3xTF32 tcgen05) for eligible policies
+    const bool tc_ok = tg_tc_eligible(mlp);
+    TG_REQUIRE(ctx->math_mode != TG_MATH_3XTF32 || tc_ok, TG_ERR_UNSUPPORTED,
+               "TG_MATH_3XTF32 requested but the policy shape is not eligible (>= 2 hidden layers of width %d)", TC_W);
+    if (tc_ok && ctx->math_mode != TG_MATH_FP32) {
+        RolloutTcArgs b;
+        memset(&b, 0, sizeof(b));
+        b.env = a.env;
+        rc = tg_build_tc_layout(mlp, &b.lay);
+        if (rc) return rc;
+        rc = tg_pack_weights_tc(ctx, b.lay, params, st);
+        if (rc) return rc;
+        b.N = N; b.init_state = init_state; b.packed = ctx->packed_tc; b.noise = noise; b.seed = seed;
+        b.env_offset = env_offset;
+        double lnb = 0.5 * A * log(2.0 * M_PI);
+        for (int j = 0; j < A; ++j) {
+            TG_REQUIRE(cov_diag[j] > 0.0f, TG_ERR_ARG, "cov_diag[%d] must be positive", j);
+            b.sd[j] = sqrtf(cov_diag[j]);
+            lnb += (double)logf(b.sd[j]);
+        }
+        b.log_norm = (float)lnb;
+        b.obs = out_obs; b.act = out_act; b.rew = out_rew; b.logp = out_logp; b.len = out_len; b.ret = out_ret;
+        switch (env->kind) {
+            case TG_ENV_CARTPOLE: return launch_rollout_tc<TG_ENV_CARTPOLE>(precision, b, st);
+            case TG_ENV_PENDULUM: return launch_rollout_tc<TG_ENV_PENDULUM>(precision, b, st);
+            case TG_ENV_QUADPOLE2D: return launch_rollout_tc<TG_ENV_QUADPOLE2D>(precision, b, st);
+            default: return launch_rollout_tc<TG_ENV_QUADPOLE>(precision, b, st);
+        }
+    }
+    rc = tg_build_layout(mlp, false, &a.lay);
+    if (rc) return rc;
     rc = tg_pack_weights(ctx, a.lay, params, st);
     if (rc) return rc;
     a.N = N;

@@ -26,6 +26,17 @@ def _count(n: int):
     COUNTERS["launches"] += n
 
 
+MATH_AUTO, MATH_FP32, MATH_3XTF32 = 0, 1, 2
+_MATH_NAMES = {"auto": MATH_AUTO, "fp32": MATH_FP32, "3xtf32": MATH_3XTF32}
+
+
+def set_math(mode, device=None):
+    """tg_ctx_set_math: 'auto' (tensor cores when the policy shape is eligible), 'fp32', '3xtf32'."""
+    lib = L.load()
+    m = _MATH_NAMES[mode] if isinstance(mode, str) else int(mode)
+    L.check(lib.tg_ctx_set_math(L.ctx(device), m), "tg_ctx_set_math")
+
+
 def fp32_peak_tflops(device=None) -> float:
     """Measured FP32 FMA-pipe throughput (tg_fp32_peak)."""
     lib = L.load()
