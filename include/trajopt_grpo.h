@@ -113,11 +113,14 @@ int tg_ctx_set_math(tg_ctx *ctx, int math_mode);
  * register-tiled MLP GEMMs; bench.py reports K1/K3 against it. */
 int tg_fp32_peak(tg_ctx *ctx, double *out_tflops);
 
-/* Tensor-core self test: D[128][N] = A[128][K] * B[N][K]^T (row-major fp32 in/out) through
- * tcgen05.mma kind::tf32 with fp32 TMEM accumulation; passes = 1 (plain TF32) or 3 (3xTF32
- * hi/lo split, fp32-faithful).  Exercises the UMMA descriptor / TMEM helpers of the fused kernels. */
+/* Tensor-core self test (row-major fp32 in/out) through tcgen05.mma kind::tf32 with fp32 TMEM
+ * accumulation; passes = 1 (plain TF32) or 3 (3xTF32 hi/lo split, fp32-faithful):
+ *   mode 0  D[128][N] = A[128][K] * B[N][K]^T   (forward layer: both operands K-major)
+ *   mode 1  D[128][N] = A[128][K] * B[K][N]     (backward-data: B MN-major)
+ *   mode 2  D[ 64][N] = A[K][64]^T * B[K][N]    (weight gradient: both MN-major, reduction over K rows)
+ * Exercises the UMMA descriptor / TMEM helpers of the fused kernels. */
 int tg_umma_selftest(tg_ctx *ctx, const float *A, const float *B, float *D, int K, int N, int passes,
-                     void *stream);
+                     int mode, void *stream);
 
 /* dims of an env kind: returns 0 or TG_ERR_ARG */
 int tg_env_dims(int kind, int *obs_dim, int *act_dim);

@@ -123,13 +123,12 @@ __global__ void pack_tc_kernel(tg_tc_layout lay, const float *__restrict__ param
                 const bool hi = i >= lay.whi[l] && i < lay.whi[l] + TC_W * TC_W;
                 const bool lo = i >= lay.wlo[l] && i < lay.wlo[l] + TC_W * TC_W;
                 if (hi || lo) {
-                    // invert the SWIZZLE_128B K-major layout: byte offset -> (row n, k)
+                    // invert the core-matrix layout of tg_umma.cuh: byte offset -> (row n, col k)
                     const uint32_t b = (uint32_t)(i - (hi ? lay.whi[l] : lay.wlo[l])) * 4u;
-                    const int kb = (int)(b / (TC_W * 128u));
-                    const uint32_t r = b % (TC_W * 128u);
-                    const int n = (int)(r / 128u);
-                    const int chunk = (int)((r % 128u) >> 4) ^ (n & 7);
-                    const int k = kb * 32 + chunk * 4 + (int)((r & 15u) >> 2);
+                    const uint32_t group = (TC_W / 4) * 128u;
+                    const uint32_t r = b % group;
+                    const int n = (int)(b / group) * 8 + (int)((r % 128u) >> 4);
+                    const int k = (int)(r / 128u) * 4 + (int)((r & 15u) >> 2);
                     const float w = Wf[(int64_t)n * TC_W + k];
                     uint32_t hb;
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));

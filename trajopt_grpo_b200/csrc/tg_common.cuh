@@ -88,7 +88,7 @@ TG_HD int tg_round_up(int x, int m) { return (x + m - 1) / m * m; }
 // Staged buffer (floats; the kernel bulk-copies it to a 1024-byte aligned smem base):
 //   w1   [TC_W][O4]            row n = (W1[n][0..O), b1[n], 0...)   O4 = roundup(O+1, 4)
 //   per hidden->hidden layer l (1024-byte aligned):
-//        w_hi [TC_W x TC_W] K-major SWIZZLE_128B (tg_umma.cuh), w_lo same, bias [TC_W]
+//        w_hi [TC_W x TC_W] core-matrix layout of tg_umma.cuh, w_lo same, bias [TC_W]
 //   wo   [A][TC_W], bo [4]
 #define TC_W 64
 struct tg_tc_layout {

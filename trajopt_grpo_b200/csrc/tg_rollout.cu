@@ -179,7 +179,7 @@ static int dispatch_prec(int precision, const RolloutArgs &a, size_t smem, bool 
 // Tensor-core variant (TG_MATH_AUTO / TG_MATH_3XTF32, eligible policies: tg_tc_eligible).
 // 128 threads, thread i = env i of the tile = TMEM lane i.  Per step each thread evaluates
 // the first Linear for its own env on the FP32 pipe, writes its activation row (hi/lo
-// split) straight into the K-major SWIZZLE_128B A operand in shared memory, one elected
+// split) straight into the core-matrix-layout A operand in shared memory, one elected
 // thread issues the 3xTF32 tcgen05.mma sequence for the [128 x 64] x [64 x 64] hidden
 // GEMM (weights hi/lo resident in shared memory, staged once by TMA), the accumulator
 // comes back from TMEM with tcgen05.ld -- each thread receives exactly its env's row --
@@ -228,8 +228,8 @@ __global__ void __launch_bounds__(128) rollout_tc_kernel(const __grid_constant__
     const uint32_t a_hi_u = smem_u32(a_hi), a_lo_u = smem_u32(a_lo), w_u = smem_u32(Wsm);
     const int warp = threadIdx.x >> 5;
     const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
-    const uint32_t row_off = (uint32_t)threadIdx.x * 128u;
-    const int rsw = threadIdx.x & 7;
+    // this thread's row of the [128][W] activation operand in the core-matrix layout
+    const uint32_t row_off = (uint32_t)(threadIdx.x >> 3) * (uint32_t)(W / 4) * 128u + (uint32_t)(threadIdx.x & 7) * 16u;
 
     const int T = a.env.max_steps;
     const int64_t N = a.N;
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(128) rollout_tc_kernel(const __grid_constant__
                 hi.z = tf32_hi(h[4 * c + 2]); hi.w = tf32_hi(h[4 * c + 3]);
                 lo.x = h[4 * c] - hi.x; lo.y = h[4 * c + 1] - hi.y;
                 lo.z = h[4 * c + 2] - hi.z; lo.w = h[4 * c + 3] - hi.w;
-                const uint32_t off = (uint32_t)(c >> 3) * (128u * 128u) + row_off + (uint32_t)(((c & 7) ^ rsw) << 4);
+                const uint32_t off = row_off + (uint32_t)c * 128u;      // core_offset(W, row, 4c)
                 *reinterpret_cast<float4 *>(a_hi + off) = hi;
                 *reinterpret_cast<float4 *>(a_lo + off) = lo;
             }
@@ -291,8 +291,8 @@ __global__ void __launch_bounds__(128) rollout_tc_kernel(const __grid_constant__
             __syncthreads();
             if (threadIdx.x == 0) {
                 tc_fence_after();
-                umma_gemm_3xtf32(tmem, a_hi_u, a_lo_u, 128, w_u + (uint32_t)a.lay.whi[l] * 4u,
-                                 w_u + (uint32_t)a.lay.wlo[l] * 4u, W, W, idesc, false, 3);
+                umma_gemm_3xtf32(tmem, a_hi_u, a_lo_u, W, false, w_u + (uint32_t)a.lay.whi[l] * 4u,
+                                 w_u + (uint32_t)a.lay.wlo[l] * 4u, W, false, W, idesc, false, 3);
                 umma_commit(&mbar);
             }
             mbar_wait(&mbar, phase);

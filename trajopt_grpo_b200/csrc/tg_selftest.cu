@@ -1,32 +1,39 @@
-// tg_umma_selftest: D[128 x N] = A[128 x K] * B[N x K]^T on the tcgen05 tensor cores
-// (kind::tf32, fp32 accumulation in TMEM) with 1 (plain TF32) or 3 (3xTF32) passes.
-// Exercises exactly the descriptor / layout / TMEM helpers the fused kernels use, so the
-// GPU test suite can pin them against a float64 matmul before they are trusted inside K1/K3.
+// tg_umma_selftest: small GEMMs on the tcgen05 tensor cores (kind::tf32, fp32 accumulation in
+// TMEM) with 1 (plain TF32) or 3 (3xTF32) passes, in the three operand arrangements the fused
+// kernels use.  It exercises exactly the descriptor / layout / TMEM helpers of tg_umma.cuh so
+// the GPU test suite can pin them against a float64 matmul.
+//   mode 0  D[128 x N] = A[128 x K] * B[N x K]^T      A K-major, B K-major   (forward layer)
+//   mode 1  D[128 x N] = A[128 x K] * Bm[K x N]        A K-major, B MN-major  (backward-data)
+//   mode 2  D[ 64 x N] = Am[K x 64]^T * Bm[K x N]      A MN-major, B MN-major (weight gradient,
+//                                                       reduction over the K samples)
+// All inputs/outputs are row-major fp32 in global memory.
 #include "tg_umma.cuh"
 
 __global__ void __launch_bounds__(128) umma_selftest_kernel(const float *__restrict__ A, const float *__restrict__ B,
-                                                            float *__restrict__ D, int K, int N, int passes) {
+                                                            float *__restrict__ D, int K, int N, int passes, int mode) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_base;
-    // 1024-byte aligned operand buffers
-    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int KB = K / 32;
-    unsigned char *a_hi = base;
-    unsigned char *a_lo = a_hi + (size_t)KB * 128 * 128;
-    unsigned char *b_hi = a_lo + (size_t)KB * 128 * 128;
-    unsigned char *b_lo = b_hi + (size_t)KB * N * 128;
-    for (int idx = threadIdx.x; idx < 128 * K; idx += 128) {
-        const int row = idx / K, k = idx % K;
+    if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+    const int M = mode >= 2 ? 64 : 128;
+    // operand buffers: K-major in the core-matrix layout, MN-major in SW128_32B (tg_umma.cuh)
+    const bool a_mn = mode >= 2, b_mn = mode != 0;
+    const int a_rows = a_mn ? K : M, a_cols = a_mn ? M : K;       // stored matrix [rows][cols]
+    const int b_rows = b_mn ? K : N, b_cols = b_mn ? N : K;
+    const size_t a_bytes = (size_t)a_rows * a_cols * 4;
+    const size_t b_bytes = (size_t)b_rows * b_cols * 4;
+    unsigned char *a_hi = smem_raw, *a_lo = a_hi + a_bytes, *b_hi = a_lo + a_bytes, *b_lo = b_hi + b_bytes;
+    for (int idx = threadIdx.x; idx < a_rows * a_cols; idx += 128) {
+        const int row = idx / a_cols, c = idx % a_cols;
         const float v = A[idx], hi = tf32_hi(v);
-        const uint32_t off = sw128_offset(128, row, k);
+        const uint32_t off = a_mn ? mn32_offset(a_rows, row, c) : core_offset(a_cols, row, c);
         *reinterpret_cast<float *>(a_hi + off) = hi;
         *reinterpret_cast<float *>(a_lo + off) = v - hi;
     }
-    for (int idx = threadIdx.x; idx < N * K; idx += 128) {
-        const int row = idx / K, k = idx % K;
+    for (int idx = threadIdx.x; idx < b_rows * b_cols; idx += 128) {
+        const int row = idx / b_cols, c = idx % b_cols;
         const float v = B[idx], hi = tf32_hi(v);
-        const uint32_t off = sw128_offset(N, row, k);
+        const uint32_t off = b_mn ? mn32_offset(b_rows, row, c) : core_offset(b_cols, row, c);
         *reinterpret_cast<float *>(b_hi + off) = hi;
         *reinterpret_cast<float *>(b_lo + off) = v - hi;
     }
@@ -43,20 +50,30 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float *__restr
     tc_fence_after();
     const uint32_t tmem = tmem_base;
     if (threadIdx.x == 0) {
-        umma_gemm_3xtf32(tmem, smem_u32(a_hi), smem_u32(a_lo), 128, smem_u32(b_hi), smem_u32(b_lo), N, K,
-                         umma_idesc_tf32(128, N), false, passes);
+        umma_gemm_3xtf32(tmem, smem_u32(a_hi), smem_u32(a_lo), a_mn ? a_rows : a_cols, a_mn, smem_u32(b_hi),
+                         smem_u32(b_lo), b_mn ? b_rows : b_cols, b_mn, K, umma_idesc_tf32(M, N, a_mn, b_mn), false,
+                         passes);
         umma_commit(&mma_bar);
     }
     mbar_wait(&mma_bar, 0);
     tc_fence_after();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = warp * 32 + lane;
+    // M = 128: accumulator row r lives in TMEM lane r.  M = 64 (cta_group::1): row r lives in lane
+    // 32*(r/16) + r%16, i.e. 16 rows in each warp's 32-lane quadrant, so all four warps take part.
+    const int out_row = (M == 128) ? row : (lane < 16 ? warp * 16 + lane : -1);
     for (int c = 0; c < N; c += 32) {
         float v[32];
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+        if (mode == 3) {          // raw dump of all 128 lanes (layout probing)
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (c + j < N) D[(size_t)row * N + c + j] = v[j];
+            for (int j = 0; j < 32; ++j)
+                if (c + j < N) D[(size_t)row * N + c + j] = v[j];
+        } else if (out_row >= 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (c + j < N) D[(size_t)out_row * N + c + j] = v[j];
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -64,16 +81,20 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float *__restr
 }
 
 extern "C" int tg_umma_selftest(tg_ctx *ctx, const float *A, const float *B, float *D, int K, int N, int passes,
-                                void *stream) {
+                                int mode, void *stream) {
     TG_REQUIRE(ctx && A && B && D, TG_ERR_ARG, "tg_umma_selftest: null argument");
+    TG_REQUIRE(mode >= 0 && mode <= 3, TG_ERR_ARG, "mode must be 0, 1, 2 or 3 (3 = mode 2 with a raw 128-lane dump)");
     TG_REQUIRE(K >= 32 && K % 32 == 0 && K <= 256, TG_ERR_SHAPE, "K must be a multiple of 32 in [32,256]");
     TG_REQUIRE(N >= 16 && N % 16 == 0 && N <= 256, TG_ERR_SHAPE, "N must be a multiple of 16 in [16,256]");
     TG_REQUIRE(passes == 1 || passes == 3, TG_ERR_ARG, "passes must be 1 or 3");
     TG_CUDA(cudaSetDevice(ctx->device));
-    const size_t smem = 1024 + 2 * (size_t)(K / 32) * 128 * 128 + 2 * (size_t)(K / 32) * N * 128;
+    const int M = mode >= 2 ? 64 : 128;
+    const size_t a_bytes = (size_t)M * K * 4;
+    const size_t b_bytes = (size_t)N * K * 4;
+    const size_t smem = 2 * a_bytes + 2 * b_bytes;
     TG_REQUIRE(smem <= (size_t)ctx->smem_optin, TG_ERR_SHAPE, "operands need %zu B of shared memory", smem);
     TG_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, K, N, passes);
+    umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, K, N, passes, mode);
     TG_CUDA(cudaGetLastError());
     return TG_OK;
 }

@@ -1,47 +1,77 @@
 // tcgen05 (5th-gen tensor core) helpers for sm_100a: TMEM allocation, shared-memory
-// matrix descriptors (K-major, SWIZZLE_128B), kind::tf32 MMA issue, commit, TMEM loads.
+// matrix descriptors, kind::tf32 MMA issue, commit, TMEM loads.
 //
-// Operand layout used everywhere in this engine (both A and B are K-major):
-//   a matrix of R rows x K fp32/tf32 elements is stored as K/32 "k-blocks"; inside a
-//   k-block every row is one 128-byte line (32 elements), rows are 128 B apart, and the
-//   16-byte chunk index of a line is XOR-ed with (row % 8)  -- the SWIZZLE_128B canonical
-//   layout (8 rows x 128 B = one 1024-byte swizzle atom; atoms of consecutive 8-row groups
-//   are 1024 B apart = the descriptor's stride byte offset).  The buffer must be 1024-byte
-//   aligned.  One tcgen05.mma of kind::tf32 consumes K = 8 elements = 32 bytes per row, so
-//   stepping along K inside a k-block adds 32 B to the descriptor start address.
+// Operand layout used everywhere in this engine: the no-swizzle "core matrix" layout.
+//   A stored matrix X[R rows][C cols] of fp32 is cut into core matrices of 8 rows x 4 cols
+//   (8 x 16 bytes = 128 contiguous bytes, row r of the core at +16*r); cores are ordered
+//   row-group major:  offset(r, c) = (r/8)*(C/4)*128 + (c/4)*128 + (r%8)*16 + (c%4)*4.
+// The SAME buffer can be handed to the tensor core in two ways (which is why this layout is
+// used instead of a swizzled one: for 32-bit operands the swizzled K-major and MN-major
+// layouts differ, but the core matrix is common to both):
+//   K-major view  (rows = M/N index, cols = reduction index): leading byte offset = 128
+//       (next core along K), stride byte offset = (C/4)*128 (next 8-row group); one MMA of
+//       kind::tf32 consumes K = 8 elements = 2 cores, i.e. +256 B per K step.
+//   MN-major view (rows = reduction index, cols = M/N index): stride byte offset = 128
+//       (next core along M/N), leading byte offset = (C/4)*128 (next 8-row group along the
+//       reduction); one MMA consumes 8 rows = one row group, i.e. +(C/4)*128 B per K step.
+// So an activation tile H[samples][features] is the K-major A operand of the next layer's
+// forward GEMM AND the MN-major B operand of that layer's weight-gradient GEMM (reduction
+// over samples); a weight W[out][in] is the K-major B operand of the forward GEMM AND the
+// MN-major B operand of the backward-data GEMM (reduction over out).
 //
 // 3xTF32: the tensor core reads only the top 19 bits of each 32-bit operand.  To keep
-// fp32-level accuracy (the engine's 1e-5 parity tolerance) every operand x is split as
-// hi = x & 0xffffe000 (exactly a tf32 number) and lo = x - hi (exact in fp32), and
-// D = A_hi*B_hi + A_hi*B_lo + A_lo*B_hi is accumulated in the fp32 TMEM accumulator
-// (the dropped lo*lo term is 2^-22 relative).
+// fp32-level accuracy every operand x is split as hi = rna_tf32(x) and lo = x - hi (exact
+// in fp32, |lo| <= 2^-11 |x|), and D = A_hi*B_hi + A_hi*B_lo + A_lo*B_hi is accumulated in
+// the fp32 TMEM accumulator (the dropped lo*lo term is <= 2^-22 relative).  Measured error:
+// ~1e-6 of the row scale per 8 accumulation steps (the accumulator truncates), tests/test_gpu_umma.py.
 #pragma once
 #include "tg_mlp.cuh"
 
-// hi = x rounded to nearest tf32 (cvt.rna), so |lo| = |x - hi| <= 2^-11 |x| and the dropped
-// lo*lo term is <= 2^-22 relative; the tensor core's own truncation of lo costs 2^-21.
 TG_D float tf32_hi(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r & 0xffffe000u);
 }
 
-// byte offset of element (row, k) of a K-major SWIZZLE_128B operand with `rows` rows
-TG_HD uint32_t sw128_offset(int rows, int row, int k) {
-    const int kb = k >> 5, kk = k & 31;
-    return (uint32_t)kb * (uint32_t)rows * 128u + (uint32_t)row * 128u + (uint32_t)(((kk >> 2) ^ (row & 7)) << 4) +
-           (uint32_t)((kk & 3) << 2);
+// byte offset of element (r, c) of a stored [R][C] fp32 matrix in the core-matrix layout
+TG_HD uint32_t core_offset(int C, int r, int c) {
+    return (uint32_t)(r >> 3) * (uint32_t)(C >> 2) * 128u + (uint32_t)(c >> 2) * 128u + (uint32_t)(r & 7) * 16u +
+           (uint32_t)(c & 3) * 4u;
 }
 
-TG_D uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) /* LBO (unused for swizzled K-major) */ |
-           (64ull << 32) /* SBO = 1024 B >> 4 */ | (1ull << 46) /* descriptor version (Blackwell) */ |
-           (2ull << 61) /* SWIZZLE_128B */;
+TG_D uint64_t umma_desc_raw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) /* descriptor version (Blackwell) */;
+           /* layout type bits [61,64) = 0: SWIZZLE_NONE */
+}
+// MN-major operands of 32-bit types have exactly one legal shared-memory layout on sm_100
+// (CUTLASS sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the only available smem
+// layout"): a stored [R rows = reduction][C cols = M/N] matrix keeps 32 consecutive M/N elements
+// of a row in one 128-byte line, lines of consecutive rows 128 B apart, the 32-byte chunk index
+// inside a line XOR-ed with (row % 4) (Swizzle<2,5,2>), the next 32 M/N elements R*128 B further:
+TG_HD uint32_t mn32_offset(int R, int r, int c) {
+    return (uint32_t)(c >> 5) * (uint32_t)R * 128u + (uint32_t)r * 128u + (uint32_t)((((c & 31) >> 3) ^ (r & 3)) << 5) +
+           (uint32_t)(c & 7) * 4u;
+}
+// layout type 1 = SWIZZLE_128B_BASE32B; LBO = next 32-element M/N block, SBO = next 4-row group
+TG_D uint64_t umma_desc_mn32(uint32_t smem_addr, uint32_t mn_block_bytes) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((mn_block_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)(512u >> 4) << 32) | (1ull << 46) | (1ull << 61);
 }
 
-// instruction descriptor: D fp32, A/B tf32, both K-major, dense
-TG_HD uint32_t umma_idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// descriptor of K step `k` (k = reduction offset in elements, multiple of 8) of a stored matrix:
+//   K-major : [rows = M/N][C cols = reduction] in the core-matrix layout
+//   MN-major: [C rows = reduction][cols = M/N] in the SW128_32B layout (C = row count R)
+TG_D uint64_t umma_operand_desc(uint32_t base, int C, bool mn_major, int k) {
+    if (mn_major) return umma_desc_mn32(base + (uint32_t)k * 128u, (uint32_t)C * 128u);
+    const uint32_t group = (uint32_t)(C >> 2) * 128u;     // bytes of one 8-row group
+    return umma_desc_raw(base + (uint32_t)(k >> 2) * 128u, /*LBO*/ 128u, /*SBO*/ group);
+}
+
+// instruction descriptor: D fp32, A/B tf32, dense; a_mn / b_mn select MN-major operands
+TG_HD uint32_t umma_idesc_tf32(int M, int N, bool a_mn = false, bool b_mn = false) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 TG_D void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {   // one full warp; ncols = power of two >= 32
@@ -58,7 +88,7 @@ TG_D void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::
 // generic-proxy shared-memory writes -> visible to the async proxy (UMMA operand reads)
 TG_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread
+// D[tmem] (+)= A[smem] * B[smem], issued by ONE thread
 TG_D void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -90,19 +120,17 @@ TG_D void tmem_ld32(uint32_t taddr, float v[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// Issue the MMAs of one GEMM  D[M x N] (+)= A[M x K] * B[N x K]^T  with the 3xTF32 split.
-// a_hi/a_lo/b_hi/b_lo: shared-memory byte addresses (u32) of the four operand buffers in the
-// layout above (A with a_rows rows, B with b_rows rows).  One thread.
-TG_D void umma_gemm_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, int a_rows, uint32_t b_hi, uint32_t b_lo,
-                           int b_rows, int K, uint32_t idesc, bool accumulate_first, int passes) {
+// Issue the MMAs of one GEMM with the 3xTF32 split (ONE thread).  Each operand is a stored
+// [rows][C] matrix in the core-matrix layout, read K-major or MN-major; K = reduction extent.
+//   a_hi/a_lo/b_hi/b_lo: shared-memory byte addresses (u32) of the hi and lo copies.
+TG_D void umma_gemm_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, int a_C, bool a_mn, uint32_t b_hi,
+                           uint32_t b_lo, int b_C, bool b_mn, int K, uint32_t idesc, bool accumulate_first, int passes) {
     uint32_t acc = accumulate_first ? 1u : 0u;
     for (int pass = 0; pass < passes; ++pass) {
         const uint32_t a = (pass == 2) ? a_lo : a_hi;
         const uint32_t b = (pass == 1) ? b_lo : b_hi;
         for (int k = 0; k < K; k += 8) {
-            const uint32_t ka = (uint32_t)(k >> 5) * (uint32_t)a_rows * 128u + (uint32_t)(k & 31) * 4u;
-            const uint32_t kbo = (uint32_t)(k >> 5) * (uint32_t)b_rows * 128u + (uint32_t)(k & 31) * 4u;
-            umma_tf32(tmem_d, umma_desc_sw128(a + ka), umma_desc_sw128(b + kbo), idesc, acc);
+            umma_tf32(tmem_d, umma_operand_desc(a, a_C, a_mn, k), umma_operand_desc(b, b_C, b_mn, k), idesc, acc);
             acc = 1u;
         }
     }
