@@ -112,3 +112,48 @@ def test_math_mode_3xtf32_rejects_ineligible_shape():
             E.rollout(1, 5, 0.05, [3, 32, 1], "ReLU", params, [0.5], torch.zeros(3, 8, device="cuda"))
     finally:
         E.set_math("auto")
+
+
+@pytest.mark.parametrize("kind,act_name", [(1, "ReLU"), (0, "Tanh"), (2, "ReLU"), (3, "Sigmoid")])
+def test_policy_grad_tensor_core_path_matches_fp32_path_and_oracle(kind, act_name):
+    """tg_policy_grad on the tcgen05 path (O-64-64-A) vs the FP32-pipe path and torch float64 autograd,
+    ragged episode lengths, two updates' worth of ratio != 1 (old weights differ from current)."""
+    import restate as R
+    from trajopt_grpo_b200 import engine as E
+    rng = np.random.default_rng(10 + kind)
+    O, A = R.OBS_DIM[kind], R.ACT_DIM[kind]
+    dims = [O, 64, 64, A]
+    Ws, bs, params = _policy(rng, dims)
+    oldWs = [w + 0.02 * rng.standard_normal(w.shape).astype(np.float32) for w in Ws]
+    G, Eps, T = 5, 52, 9                       # 260 envs: three tiles per step, the last one partial
+    N = G * Eps
+    obs = rng.standard_normal((G, Eps, T, O)).astype(np.float32)
+    actn = rng.standard_normal((G, Eps, T, A)).astype(np.float32)
+    adv = rng.standard_normal((G, Eps, T)).astype(np.float32)
+    ln = rng.integers(1, T + 1, (G, Eps)).astype(np.int32)
+    mask = (np.arange(T)[None, None, :] < ln[:, :, None]).astype(np.float32)
+    cov = np.full(A, 0.4, np.float32)
+    J, dW, db, lp, old_lp = R.grpo_objective_and_grad(obs, actn, adv * mask, mask, Ws, bs, oldWs, bs, cov, 0.2,
+                                                       act=R.ACT_IDS[act_name], dtype="float64")
+    ref = np.concatenate([np.concatenate([w.reshape(-1), b]) for w, b in zip(dW, db)])
+    dobs = torch.from_numpy(np.ascontiguousarray(obs.reshape(N, T, O).transpose(1, 2, 0))).cuda()
+    dact = torch.from_numpy(np.ascontiguousarray(actn.reshape(N, T, A).transpose(1, 2, 0))).cuda()
+    dadv = torch.from_numpy(np.ascontiguousarray((adv * mask).reshape(N, T).T)).cuda()
+    dlen = torch.from_numpy(ln.reshape(-1)).cuda()
+    old_flat = torch.from_numpy(np.concatenate([np.concatenate([w.reshape(-1), b]) for w, b in zip(oldWs, bs)]).astype(np.float32)).cuda()
+    out = {}
+    try:
+        for mode in ("fp32", "3xtf32"):
+            E.set_math(mode)
+            _, olp = E.policy_forward_traj(dims, act_name, old_flat, dobs, cov.tolist(), dact, dlen)
+            g, st = E.policy_grad(dims, act_name, params, cov.tolist(), dobs, dact, dadv, olp, dlen, 0.2, 1.0 / G)
+            torch.cuda.synchronize()
+            out[mode] = (g.cpu().numpy(), st.cpu().numpy())
+    finally:
+        E.set_math("auto")
+    scale = np.abs(ref).max()
+    for mode, (g, st) in out.items():
+        assert np.abs(g - ref).max() <= 2e-4 * scale, (mode, np.abs(g - ref).max(), scale)
+        assert int(st[1]) == int(mask.sum()), mode
+        assert abs(st[0] - J) <= 2e-4 * max(1.0, abs(J)), (mode, st[0], J)
+    assert np.abs(out["fp32"][0] - out["3xtf32"][0]).max() <= 5e-5 * scale

@@ -71,7 +71,7 @@ bool tg_tc_eligible(const tg_mlp_cfg *mlp) {
            mlp->dims[mlp->n_layers] <= TG_MAX_ACT && mlp->activation >= 0 && mlp->activation <= 2;
 }
 
-int tg_build_tc_layout(const tg_mlp_cfg *mlp, tg_tc_layout *out) {
+int tg_build_tc_layout(const tg_mlp_cfg *mlp, tg_tc_layout *out, bool with_backward) {
     TG_REQUIRE(tg_tc_eligible(mlp), TG_ERR_UNSUPPORTED,
                "tensor-core path needs >= 2 hidden layers, all of width %d", TC_W);
     memset(out, 0, sizeof(*out));
@@ -92,6 +92,11 @@ int tg_build_tc_layout(const tg_mlp_cfg *mlp, tg_tc_layout *out) {
     for (int l = 1; l < nl - 1; ++l) {
         out->whi[l] = off; off += TC_W * TC_W;
         out->wlo[l] = off; off += TC_W * TC_W;
+        out->wbhi[l] = out->wblo[l] = -1;
+        if (with_backward) {
+            out->wbhi[l] = off; off += TC_W * TC_W;
+            out->wblo[l] = off; off += TC_W * TC_W;
+        }
     }
     for (int l = 1; l < nl - 1; ++l) { out->bias[l] = off; off += TC_W; }
     out->w1 = off; off += (int64_t)TC_W * out->O4;
@@ -134,6 +139,21 @@ __global__ void pack_tc_kernel(tg_tc_layout lay, const float *__restrict__ param
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));
                     const float whi = __uint_as_float(hb & 0xffffe000u);
                     v = hi ? whi : (w - whi);
+                }
+                const bool bhi = lay.wbhi[l] >= 0 && i >= lay.wbhi[l] && i < lay.wbhi[l] + TC_W * TC_W;
+                const bool blo = lay.wblo[l] >= 0 && i >= lay.wblo[l] && i < lay.wblo[l] + TC_W * TC_W;
+                if (bhi || blo) {
+                    // invert mn32_offset (tg_umma.cuh) of the stored [R = TC_W rows n][cols k] matrix
+                    const uint32_t b = (uint32_t)(i - (bhi ? lay.wbhi[l] : lay.wblo[l])) * 4u;
+                    const uint32_t blk = b / (TC_W * 128u), r = b % (TC_W * 128u);
+                    const int n = (int)(r / 128u);
+                    const int chunk = (int)((r % 128u) >> 5) ^ (n & 3);
+                    const int k = (int)blk * 32 + chunk * 8 + (int)((r & 31u) >> 2);
+                    const float w = Wf[(int64_t)n * TC_W + k];
+                    uint32_t hb;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));
+                    const float whi = __uint_as_float(hb & 0xffffe000u);
+                    v = bhi ? whi : (w - whi);
                 }
             }
         }

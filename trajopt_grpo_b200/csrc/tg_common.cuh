@@ -95,9 +95,19 @@ struct tg_tc_layout {
     int n_layers, nh, act, O, O4, A;
     int64_t flat_w[TG_MAX_LAYERS];     // offsets of each Linear in the flat torch vector
     int64_t w1, whi[TG_MAX_LAYERS], wlo[TG_MAX_LAYERS], bias[TG_MAX_LAYERS], wo, bo;
+    // update kernels only: W[out][in] again in the MN-major (SW128_32B) layout, the B operand of
+    // the backward-data GEMM dH = dZ * W (reduction over `out`); -1 when absent
+    int64_t wbhi[TG_MAX_LAYERS], wblo[TG_MAX_LAYERS];
     int64_t total;                     // floats
     int64_t n_params;
 };
 bool tg_tc_eligible(const tg_mlp_cfg *mlp);
-int tg_build_tc_layout(const tg_mlp_cfg *mlp, tg_tc_layout *out);
+int tg_build_tc_layout(const tg_mlp_cfg *mlp, tg_tc_layout *out, bool with_backward = false);
 int tg_pack_weights_tc(tg_ctx *ctx, const tg_tc_layout &lay, const float *params, cudaStream_t st);
+// tensor-core update kernel (tg_update_tc.cu)
+bool tg_update_tc_eligible(const tg_mlp_cfg *mlp);
+int tg_update_tc_grid(const tg_ctx *ctx);
+int tg_policy_grad_tc(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, const float *obs, const float *act,
+                      const float *adv, const float *old_logp, const int32_t *len, const float *params,
+                      const float *inv_sd, const float *inv_var, float log_norm, float eps_clip, float scale,
+                      float kl_scale, float *gpart, double *spart, int grid, cudaStream_t st);
