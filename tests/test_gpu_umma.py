@@ -13,7 +13,7 @@ def _run(K, N, passes, seed=0, mode=0):
     from trajopt_grpo_b200 import _lib as L
     lib = L.load()
     rng = np.random.default_rng(seed)
-    if mode == 0:      # D[128,N] = A[128,K] @ B[N,K]^T
+    if mode in (0, 4):  # D[128,N] = A[128,K] @ B[N,K]^T   (mode 4: A operand through tensor memory)
         A = rng.standard_normal((128, K)).astype(np.float32)
         B = rng.standard_normal((N, K)).astype(np.float32)
         ref = A.astype(np.float64) @ B.astype(np.float64).T
@@ -50,7 +50,8 @@ def test_umma_3xtf32_is_fp32_faithful(K, N):
     assert np.abs(got - ref).max() <= 1e-6 * K, np.abs(got - ref).max()
 
 
-@pytest.mark.parametrize("mode,K,N", [(1, 64, 64), (1, 128, 64), (2, 128, 64), (2, 64, 64), (2, 128, 32)])
+@pytest.mark.parametrize("mode,K,N", [(1, 64, 64), (1, 128, 64), (2, 128, 64), (2, 64, 64), (2, 128, 32),
+                                      (4, 64, 64), (4, 32, 128)])
 def test_umma_mn_major_operands(mode, K, N):
     """backward-data (B MN-major) and weight-gradient (A and B MN-major, M = 64) arrangements"""
     got, ref = _run(K, N, 3, seed=2, mode=mode)

@@ -15,9 +15,9 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float *__restr
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_base;
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
-    const int M = mode >= 2 ? 64 : 128;
+    const int M = (mode == 2 || mode == 3) ? 64 : 128;
     // operand buffers: K-major in the core-matrix layout, MN-major in SW128_32B (tg_umma.cuh)
-    const bool a_mn = mode >= 2, b_mn = mode != 0;
+    const bool a_mn = (mode == 2 || mode == 3), b_mn = (mode >= 1 && mode <= 3);
     const int a_rows = a_mn ? K : M, a_cols = a_mn ? M : K;       // stored matrix [rows][cols]
     const int b_rows = b_mn ? K : N, b_cols = b_mn ? N : K;
     const size_t a_bytes = (size_t)a_rows * a_cols * 4;
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float *__restr
         *reinterpret_cast<float *>(b_lo + off) = v - hi;
     }
     uint32_t ncols = 32;
-    while ((int)ncols < N) ncols <<= 1;
+    while ((int)ncols < N + (mode == 4 ? 2 * K : 0)) ncols <<= 1;
     if (threadIdx.x == 0) {
         mbar_init(&mma_bar, 1);
         mbar_fence_init();
@@ -49,7 +49,38 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float *__restr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base;
-    if (threadIdx.x == 0) {
+    if (mode == 4) {
+        // A operand through tensor memory: thread i writes row i (hi at column N.., lo at N+K..)
+        const uint32_t my = tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16);
+        for (int c0 = 0; c0 < K; c0 += 32) {
+            float hi[32], lo[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float v = A[(size_t)threadIdx.x * K + c0 + j];
+                hi[j] = tf32_hi(v);
+                lo[j] = v - hi[j];
+            }
+            tmem_st32(my + (uint32_t)(N + c0), hi);
+            tmem_st32(my + (uint32_t)(N + K + c0), lo);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (threadIdx.x == 0) {
+            const uint32_t idesc = umma_idesc_tf32(128, N, false, false);
+            uint32_t acc = 0;
+            for (int pass = 0; pass < passes; ++pass) {
+                const uint32_t acol = tmem + (uint32_t)N + (pass == 2 ? (uint32_t)K : 0u);
+                const uint32_t b = smem_u32(pass == 1 ? b_lo : b_hi);
+                for (int k = 0; k < K; k += 8) {
+                    umma_tf32_ts(tmem, acol + (uint32_t)k, umma_operand_desc(b, b_cols, false, k), idesc, acc);
+                    acc = 1u;
+                }
+            }
+            umma_commit(&mma_bar);
+        }
+    } else if (threadIdx.x == 0) {
         umma_gemm_3xtf32(tmem, smem_u32(a_hi), smem_u32(a_lo), a_mn ? a_rows : a_cols, a_mn, smem_u32(b_hi),
                          smem_u32(b_lo), b_mn ? b_rows : b_cols, b_mn, K, umma_idesc_tf32(M, N, a_mn, b_mn), false,
                          passes);
@@ -83,12 +114,13 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float *__restr
 extern "C" int tg_umma_selftest(tg_ctx *ctx, const float *A, const float *B, float *D, int K, int N, int passes,
                                 int mode, void *stream) {
     TG_REQUIRE(ctx && A && B && D, TG_ERR_ARG, "tg_umma_selftest: null argument");
-    TG_REQUIRE(mode >= 0 && mode <= 3, TG_ERR_ARG, "mode must be 0, 1, 2 or 3 (3 = mode 2 with a raw 128-lane dump)");
+    TG_REQUIRE(mode >= 0 && mode <= 4, TG_ERR_ARG,
+               "mode must be 0..4 (3 = mode 2 with a raw 128-lane dump, 4 = mode 0 with A in tensor memory)");
     TG_REQUIRE(K >= 32 && K % 32 == 0 && K <= 256, TG_ERR_SHAPE, "K must be a multiple of 32 in [32,256]");
     TG_REQUIRE(N >= 16 && N % 16 == 0 && N <= 256, TG_ERR_SHAPE, "N must be a multiple of 16 in [16,256]");
     TG_REQUIRE(passes == 1 || passes == 3, TG_ERR_ARG, "passes must be 1 or 3");
     TG_CUDA(cudaSetDevice(ctx->device));
-    const int M = mode >= 2 ? 64 : 128;
+    const int M = (mode == 2 || mode == 3) ? 64 : 128;
     const size_t a_bytes = (size_t)M * K * 4;
     const size_t b_bytes = (size_t)N * K * 4;
     const size_t smem = 2 * a_bytes + 2 * b_bytes;

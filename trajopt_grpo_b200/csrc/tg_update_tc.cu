@@ -1,24 +1,29 @@
 // K3 on the tensor cores: fused clipped-surrogate objective + MLP backward for policies
 // O -> 64 -> 64 -> A (two hidden layers of width TC_W; tg_policy_grad routes here under
-// TG_MATH_AUTO / TG_MATH_3XTF32).  128 threads per CTA, thread i = sample i of the tile =
-// TMEM lane i; persistent CTAs walk tiles of 128 samples (one step t x 128 consecutive envs).
+// TG_MATH_AUTO / TG_MATH_3XTF32).  Persistent CTAs (one per SM) walk tiles of 128 samples
+// (one step t x 128 consecutive envs).  256 threads: sample s = TMEM lane s is served by TWO
+// threads (warps q and q+4 of lane quadrant q), each owning one 32-column half of every
+// 64-wide activation row -- this halves the per-thread register/ALU load of the epilogues
+// and gives the scheduler 8 warps to overlap with the tensor-core round trips.
 //
-// Per tile (all GEMMs are 3xTF32 tcgen05.mma with fp32 accumulation in TMEM):
-//   P1  FP32 pipe: H1 = act(W0 x + b0) for the thread's own sample; the row is written twice,
-//       hi/lo split: K-major (bufA, A operand of the forward GEMM) and MN-major (bufB, B operand
-//       of the weight-gradient GEMM, reduction over samples)
-//   MMA D_f[128x64] = H1 . W1^T
-//   P3  tcgen05.ld -> H2 = act(D_f + b1); output Linear, log-prob, ratio, clipped surrogate,
-//       d/dmu; dZ2 = (Wo^T dmu) * act'(H2) written K-major into bufA (forward GEMM is done)
-//   MMA D_b[128x64] = dZ2 . W1            (B = W1 MN-major: reduction over its rows)
-//       meanwhile: warp-shuffle column sums for dWo, db1
-//   P4  dZ2 written MN-major into bufA (backward GEMM is done)
-//   MMA D_w[64x64]  = dZ2^T . H1          (A, B MN-major, reduction over the 128 samples)
-//       meanwhile: tcgen05.ld D_b -> dZ1 = D_b * act'(H1); column sums for db0, dW0
-//   P5  tcgen05.ld D_w (M = 64: row r in lane 32*(r/16) + r%16) added to register accumulators
-// Column sums over samples use a register butterfly (62 shuffles per 64-column matrix): after it
-// lane l of a warp holds the warp's sums of columns 2l and 2l+1; per-warp partials live in
-// registers for the whole kernel and are combined once at the end.
+// Per tile (all GEMMs are 3xTF32 tcgen05.mma, fp32 accumulation in TMEM):
+//   P1  FP32 pipe: H1 = act(W0 x + b0); each thread writes its half row, hi/lo split, into
+//       tensor memory (A operand of the forward GEMM, tcgen05.st) and MN-major into bufB
+//       (B operand of the weight-gradient GEMM, reduction over samples)
+//   MMA D_f[128x64] = H1 . W1^T                         (A from TMEM, B = W1 K-major in smem)
+//   P3  tcgen05.ld -> H2 = act(D_f + b1); output Linear (half dot products exchanged through
+//       shared memory), log-prob, ratio, clipped surrogate, d/dmu;
+//       dZ2 = (Wo^T dmu) * act'(H2) -> tensor memory (A operand) and MN-major into bufC
+//   MMA D_b[128x64] = dZ2 . W1                          (A from TMEM, B = W1 MN-major)
+//   MMA D_w[64x64]  = dZ2^T . H1                        (A = bufC, B = bufB, both MN-major,
+//       reduction over the 128 samples) -- issued back to back with D_b, separate barriers
+//       meanwhile: butterfly column sums for dWo and db1, prefetch of the next tile's inputs
+//   P5a tcgen05.ld D_b -> dZ1 = D_b * act'(H1); butterfly column sums for db0, dW0
+//   P5b tcgen05.ld D_w (M = 64: row r in lane 32*(r/16) + r%16) added to the shared-memory
+//       accumulator of dW1
+// Column sums over samples use a register butterfly (31 shuffles per 32-column half): lane l
+// of a warp ends with the warp's sum of its column l; per-warp partials live in registers for
+// the whole kernel and are combined once, in a fixed order, at the end.
 // Every CTA writes its partial gradient into its private copy (gpart); grad_reduce_kernel
 // (tg_update.cu) sums the copies in a fixed order -> deterministic result in flat torch layout.
 #include <math.h>
@@ -38,8 +43,7 @@ struct UpdTcArgs {
     double *spart;  // [grid][4]
 };
 
-// butterfly column sums: v[0..64) per lane -> (v[0], v[1]) = sums over the warp's 32 lanes of
-// columns 2*lane and 2*lane+1.  Destroys v.
+// butterfly column sums: v[0..32) per lane -> v[0] = sum over the warp's 32 lanes of column `lane`
 template <int HALF, int OFF> TG_D void colsum_step(float *v, int lane) {
     const bool up = (lane & OFF) != 0;
 #pragma unroll
@@ -49,166 +53,213 @@ template <int HALF, int OFF> TG_D void colsum_step(float *v, int lane) {
         v[j] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
     }
 }
-TG_D void colsum64(float *v, int lane) {
-    colsum_step<32, 16>(v, lane);
-    colsum_step<16, 8>(v, lane);
-    colsum_step<8, 4>(v, lane);
-    colsum_step<4, 2>(v, lane);
-    colsum_step<2, 1>(v, lane);
+TG_D float colsum32(float *v, int lane) {
+    colsum_step<16, 16>(v, lane);
+    colsum_step<8, 8>(v, lane);
+    colsum_step<4, 4>(v, lane);
+    colsum_step<2, 2>(v, lane);
+    colsum_step<1, 1>(v, lane);
+    return v[0];
 }
 
+TG_D void split4(const float *v, float4 &hi, float4 &lo) {
+    hi.x = tf32_hi(v[0]); hi.y = tf32_hi(v[1]); hi.z = tf32_hi(v[2]); hi.w = tf32_hi(v[3]);
+    lo.x = v[0] - hi.x; lo.y = v[1] - hi.y; lo.z = v[2] - hi.z; lo.w = v[3] - hi.w;
+}
+
+// TMEM column map (512 columns allocated)
+#define TM_DF 0u
+#define TM_DB 64u
+#define TM_DW 128u
+#define TM_AHI 192u
+#define TM_ALO 256u
+
 template <int O, int A, bool RELU>
-__global__ void __launch_bounds__(128) update_tc_kernel(const __grid_constant__ UpdTcArgs a) {
-    constexpr int W = TC_W, O4 = (O + 1 + 3) / 4 * 4;
+__global__ void __launch_bounds__(256) update_tc_kernel(const __grid_constant__ UpdTcArgs a) {
+    constexpr int W = TC_W, HW = TC_W / 2, O4 = (O + 1 + 3) / 4 * 4;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t wbar, mbar;
+    __shared__ __align__(8) uint64_t wbar, bar_a, bar_w;
     __shared__ uint32_t tmem_slot;
-    __shared__ double sred[4][4];
+    __shared__ double sred[4][8];
+    __shared__ float muS[2][A][128];
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
     float *Wsm = reinterpret_cast<float *>(smem_raw);
-    unsigned char *bufA_hi = smem_raw + ((size_t)a.lay.total * 4 + 1023) / 1024 * 1024;
-    unsigned char *bufA_lo = bufA_hi + 128 * W * 4;
-    unsigned char *bufB_hi = bufA_lo + 128 * W * 4;
+    unsigned char *bufB_hi = smem_raw + ((size_t)a.lay.total * 4 + 1023) / 1024 * 1024;   // H1, MN-major
     unsigned char *bufB_lo = bufB_hi + 128 * W * 4;
+    unsigned char *bufC_hi = bufB_lo + 128 * W * 4;                                        // dZ2, MN-major
+    unsigned char *bufC_lo = bufC_hi + 128 * W * 4;
+    // dW1 accumulator [W][W], column-major (accS[k*W + r]): the 16 lanes owning consecutive rows r hit
+    // consecutive banks
+    float *accS = reinterpret_cast<float *>(bufC_lo + 128 * W * 4);
     stage_weights_tma(Wsm, a.packed, a.lay.total, &wbar);
     if (threadIdx.x == 0) {
-        mbar_init(&mbar, 1);
+        mbar_init(&bar_a, 1);
+        mbar_init(&bar_w, 1);
         mbar_fence_init();
     }
-    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, 256);
+    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, 512);
+    for (int i = threadIdx.x; i < W * W; i += 256) accS[i] = 0.0f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const uint32_t tm_f = tmem, tm_b = tmem + 64, tm_w = tmem + 128;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int q = warp & 3, hf = warp >> 2;        // lane quadrant, column half
+    const int s = q * 32 + lane;                    // sample row of this thread
+    const int c0 = hf * HW;                         // first column of this thread's half
+    const uint32_t my_tm = tmem + ((uint32_t)(q * 32) << 16);
     const uint32_t idesc_f = umma_idesc_tf32(128, W, false, false);
     const uint32_t idesc_b = umma_idesc_tf32(128, W, false, true);
     const uint32_t idesc_w = umma_idesc_tf32(64, W, true, true);
     const uint32_t w_u = smem_u32(Wsm);
     const uint32_t wf_hi = w_u + (uint32_t)a.lay.whi[1] * 4u, wf_lo = w_u + (uint32_t)a.lay.wlo[1] * 4u;
     const uint32_t wb_hi = w_u + (uint32_t)a.lay.wbhi[1] * 4u, wb_lo = w_u + (uint32_t)a.lay.wblo[1] * 4u;
-    const uint32_t A_hi = smem_u32(bufA_hi), A_lo = smem_u32(bufA_lo), B_hi = smem_u32(bufB_hi), B_lo = smem_u32(bufB_lo);
-    // this thread's row in the K-major core-matrix layout and in the MN-major SW128_32B layout
-    const uint32_t core_row = (uint32_t)(threadIdx.x >> 3) * (uint32_t)(W / 4) * 128u + (uint32_t)(threadIdx.x & 7) * 16u;
-    const uint32_t mn_row = (uint32_t)threadIdx.x * 128u;
-    const int rs = threadIdx.x & 3;
+    const uint32_t B_hi = smem_u32(bufB_hi), B_lo = smem_u32(bufB_lo), C_hi = smem_u32(bufC_hi), C_lo = smem_u32(bufC_lo);
+    // this thread's half row in the MN-major SW128_32B layout: mn32_offset(128, s, c0 + 4*i)
+    const uint32_t mn_row = (uint32_t)hf * (128u * 128u) + (uint32_t)s * 128u;
+    const int rs = s & 3;
     const float *w1 = Wsm + a.lay.w1, *b1 = Wsm + a.lay.bias[1], *wo = Wsm + a.lay.wo, *bo = Wsm + a.lay.bo;
     const int act_kind = RELU ? TG_ACT_RELU : a.lay.act;
 
-    // persistent per-thread gradient partials
-    // dW1 accumulator [W][W] in shared memory, stored column-major (accS[k*W + r]) so that the 16
-    // lanes that own consecutive rows r hit consecutive banks
-    float *accS = reinterpret_cast<float *>(bufB_lo + 128 * W * 4);
-    for (int i = threadIdx.x; i < W * W; i += 128) accS[i] = 0.0f;
-    float c_wo[A][2], c_b1[2] = {0.f, 0.f}, c_b0[2] = {0.f, 0.f}, c_w0[O][2], c_bo[A];
+    // persistent per-thread gradient partials: this warp's sum over its 32 samples of column c0 + lane
+    float c_wo[A], c_b1 = 0.f, c_b0 = 0.f, c_w0[O], c_bo[A];
 #pragma unroll
-    for (int j = 0; j < A; ++j) { c_wo[j][0] = c_wo[j][1] = 0.0f; c_bo[j] = 0.0f; }
+    for (int j = 0; j < A; ++j) c_wo[j] = c_bo[j] = 0.0f;
 #pragma unroll
-    for (int o = 0; o < O; ++o) c_w0[o][0] = c_w0[o][1] = 0.0f;
+    for (int o = 0; o < O; ++o) c_w0[o] = 0.0f;
     double s_obj = 0.0, s_cnt = 0.0, s_ratio = 0.0, s_clip = 0.0;
 
     const int64_t N = a.N;
     const int64_t NB = (N + 127) / 128;
     const int64_t ntiles = NB * a.T;
-    uint32_t phase = 0;
+    // software prefetch of a tile's per-sample inputs
+    float xn[O], an[A], advn = 0.f, olpn = 0.f;
+    bool vn = false;
+    auto prefetch = [&](int64_t tile) {
+        vn = false;
+        if (tile < ntiles) {
+            const int t = (int)(tile / NB);
+            const int64_t n = (tile % NB) * 128 + s;
+            vn = n < N && t < a.len[n];
+            if (vn) {
+#pragma unroll
+                for (int o = 0; o < O; ++o) xn[o] = a.obs[((int64_t)t * O + o) * N + n];
+#pragma unroll
+                for (int j = 0; j < A; ++j) an[j] = a.act[((int64_t)t * A + j) * N + n];
+                advn = a.adv[(int64_t)t * N + n];
+                olpn = a.oldlp[(int64_t)t * N + n];
+            }
+        }
+    };
+    prefetch(blockIdx.x);
+    uint32_t ph_a = 0, ph_w = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int t = (int)(tile / NB);
-        const int64_t n = (tile % NB) * 128 + threadIdx.x;
-        const bool valid = n < N && t < a.len[n];
-        // also orders the previous tile's TMEM loads / smem reads before this tile's writes
+        float x[O], av[A];
+        const bool valid = vn;
+        const float adv = advn, olp = olpn;
+#pragma unroll
+        for (int o = 0; o < O; ++o) x[o] = valid ? xn[o] : 0.0f;
+#pragma unroll
+        for (int j = 0; j < A; ++j) av[j] = an[j];
+        // orders the previous tile's TMEM loads / smem reads before this tile's writes
         tc_fence_before();
-        if (!__syncthreads_or(valid ? 1 : 0)) continue;
+        const int any = __syncthreads_or(valid ? 1 : 0);
         tc_fence_after();
-        // ---- P1: first Linear on the FP32 pipe
-        float x[O];
+        if (!any) { prefetch(tile + gridDim.x); continue; }
+        // ---- P1: first Linear on the FP32 pipe, this thread's 32 neurons
+        float h[HW];
 #pragma unroll
-        for (int o = 0; o < O; ++o) x[o] = valid ? a.obs[((int64_t)t * O + o) * N + n] : 0.0f;
-        float h[W];
-#pragma unroll
-        for (int nn = 0; nn < W; ++nn) {
+        for (int i = 0; i < HW; ++i) {
             float wrow[O4];
 #pragma unroll
-            for (int q = 0; q < O4; q += 4) {
-                const float4 v = *reinterpret_cast<const float4 *>(w1 + nn * O4 + q);
-                wrow[q] = v.x; wrow[q + 1] = v.y; wrow[q + 2] = v.z; wrow[q + 3] = v.w;
+            for (int k = 0; k < O4; k += 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(w1 + (c0 + i) * O4 + k);
+                wrow[k] = v.x; wrow[k + 1] = v.y; wrow[k + 2] = v.z; wrow[k + 3] = v.w;
             }
             float acc = wrow[O];
 #pragma unroll
             for (int o = 0; o < O; ++o) acc = fmaf(wrow[o], x[o], acc);
-            h[nn] = act_fwd(acc, act_kind);
+            h[i] = act_fwd(acc, act_kind);
         }
-        // act'(H1) kept as a bit mask (ReLU) or re-read from bufB later (other activations)
-        uint32_t m1lo = 0, m1hi = 0;
+        uint32_t m1 = 0;    // act'(H1) as a bit mask (ReLU); other activations re-read H1 from bufB
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            m1lo |= (h[j] > 0.0f ? 1u : 0u) << j;
-            m1hi |= (h[32 + j] > 0.0f ? 1u : 0u) << j;
-        }
+        for (int i = 0; i < HW; ++i) m1 |= (h[i] > 0.0f ? 1u : 0u) << i;
+        {
+            float hi[HW], lo[HW];
 #pragma unroll
-        for (int c = 0; c < W / 4; ++c) {
-            float4 hi, lo;
-            hi.x = tf32_hi(h[4 * c]); hi.y = tf32_hi(h[4 * c + 1]); hi.z = tf32_hi(h[4 * c + 2]); hi.w = tf32_hi(h[4 * c + 3]);
-            lo.x = h[4 * c] - hi.x; lo.y = h[4 * c + 1] - hi.y; lo.z = h[4 * c + 2] - hi.z; lo.w = h[4 * c + 3] - hi.w;
-            const uint32_t oc = core_row + (uint32_t)c * 128u;
-            *reinterpret_cast<float4 *>(bufA_hi + oc) = hi;
-            *reinterpret_cast<float4 *>(bufA_lo + oc) = lo;
-            // mn32_offset(128, row, 4c): 32-column block, 32-byte chunk XOR (row % 4), 16-byte half
-            const uint32_t om = (uint32_t)(c >> 3) * (128u * 128u) + mn_row + (uint32_t)((((c & 7) >> 1) ^ rs) << 5) +
-                                (uint32_t)(c & 1) * 16u;
-            *reinterpret_cast<float4 *>(bufB_hi + om) = hi;
-            *reinterpret_cast<float4 *>(bufB_lo + om) = lo;
+            for (int i = 0; i < HW / 4; ++i) {
+                float4 h4, l4;
+                split4(h + 4 * i, h4, l4);
+                hi[4 * i] = h4.x; hi[4 * i + 1] = h4.y; hi[4 * i + 2] = h4.z; hi[4 * i + 3] = h4.w;
+                lo[4 * i] = l4.x; lo[4 * i + 1] = l4.y; lo[4 * i + 2] = l4.z; lo[4 * i + 3] = l4.w;
+                const uint32_t om = mn_row + (uint32_t)(((i >> 1) ^ rs) << 5) + (uint32_t)(i & 1) * 16u;
+                *reinterpret_cast<float4 *>(bufB_hi + om) = h4;
+                *reinterpret_cast<float4 *>(bufB_lo + om) = l4;
+            }
+            tmem_st32(my_tm + TM_AHI + (uint32_t)c0, hi);
+            tmem_st32(my_tm + TM_ALO + (uint32_t)c0, lo);
+            tmem_st_wait();
         }
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
         if (threadIdx.x == 0) {
             tc_fence_after();
-            umma_gemm_3xtf32(tm_f, A_hi, A_lo, W, false, wf_hi, wf_lo, W, false, W, idesc_f, false, 3);
-            umma_commit(&mbar);
+            uint32_t acc = 0;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t acol = tmem + (pass == 2 ? TM_ALO : TM_AHI);
+                const uint32_t b = pass == 1 ? wf_lo : wf_hi;
+#pragma unroll
+                for (int k = 0; k < W; k += 8) {
+                    umma_tf32_ts(tmem + TM_DF, acol + (uint32_t)k, umma_operand_desc(b, W, false, k), idesc_f, acc);
+                    acc = 1u;
+                }
+            }
+            umma_commit(&bar_a);
         }
-        mbar_wait(&mbar, phase);
-        phase ^= 1u;
+        mbar_wait(&bar_a, ph_a);
+        ph_a ^= 1u;
         tc_fence_after();
-        // ---- P3: H2, output Linear, objective, dZ2
+        // ---- P3: H2 (this thread's half), output Linear, objective, dZ2
+        {
+            float z[HW];
+            tmem_ld32(my_tm + TM_DF + (uint32_t)c0, z);
 #pragma unroll
-        for (int c0 = 0; c0 < W; c0 += 32) {
-            float z[32];
-            tmem_ld32(tm_f + lane_base + (uint32_t)c0, z);
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
+            for (int j = 0; j < HW; j += 4) {
                 const float4 b4 = *reinterpret_cast<const float4 *>(b1 + c0 + j);
-                h[c0 + j] = act_fwd(z[j] + b4.x, act_kind);
-                h[c0 + j + 1] = act_fwd(z[j + 1] + b4.y, act_kind);
-                h[c0 + j + 2] = act_fwd(z[j + 2] + b4.z, act_kind);
-                h[c0 + j + 3] = act_fwd(z[j + 3] + b4.w, act_kind);
+                h[j] = act_fwd(z[j] + b4.x, act_kind);
+                h[j + 1] = act_fwd(z[j + 1] + b4.y, act_kind);
+                h[j + 2] = act_fwd(z[j + 2] + b4.z, act_kind);
+                h[j + 3] = act_fwd(z[j + 3] + b4.w, act_kind);
             }
         }
+#pragma unroll
+        for (int j = 0; j < A; ++j) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int k = 0; k < HW; k += 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(wo + j * W + c0 + k);
+                acc = fmaf(h[k], v.x, acc); acc = fmaf(h[k + 1], v.y, acc);
+                acc = fmaf(h[k + 2], v.z, acc); acc = fmaf(h[k + 3], v.w, acc);
+            }
+            muS[hf][j][s] = acc;
+        }
+        __syncthreads();
         float mu[A], dmu[A];
 #pragma unroll
         for (int j = 0; j < A; ++j) {
-            float acc = bo[j];
-#pragma unroll
-            for (int q = 0; q < W; q += 4) {
-                const float4 v = *reinterpret_cast<const float4 *>(wo + j * W + q);
-                acc = fmaf(h[q], v.x, acc); acc = fmaf(h[q + 1], v.y, acc);
-                acc = fmaf(h[q + 2], v.z, acc); acc = fmaf(h[q + 3], v.w, acc);
-            }
-            mu[j] = acc;
+            mu[j] = (bo[j] + muS[0][j][s]) + muS[1][j][s];
             dmu[j] = 0.0f;
         }
         if (valid) {
-            const int64_t row = (int64_t)t * N + n;
-            float av[A], m2 = 0.0f;
+            float m2 = 0.0f;
 #pragma unroll
             for (int j = 0; j < A; ++j) {
-                av[j] = a.act[((int64_t)t * A + j) * N + n];
                 const float z = (av[j] - mu[j]) * a.inv_sd[j];
                 m2 += z * z;
             }
             const float lp = -0.5f * m2 - a.log_norm;
-            const float adv = a.adv[row], olp = a.oldlp[row];
             const float ratio = expf(lp - olp);
             const float lo = 1.0f - a.eps_clip, hi = 1.0f + a.eps_clip;
             const float s1 = ratio * adv, s2 = fminf(fmaxf(ratio, lo), hi) * adv;
@@ -217,194 +268,167 @@ __global__ void __launch_bounds__(128) update_tc_kernel(const __grid_constant__ 
             if (s1 < s2) g = adv;
             else if (s1 > s2) g = in_range ? adv : 0.0f;
             else g = 0.5f * (adv + (in_range ? adv : 0.0f));
-            s_obj += (double)fminf(s1, s2) * a.scale;
             float dlp = a.scale * g * ratio;
+            float eo = 0.0f;
             if (a.kl_scale != 0.0f) {
-                const float eo = expf(olp);
-                s_obj += (double)a.kl_scale * eo * (olp - lp);
+                eo = expf(olp);
                 dlp -= a.kl_scale * eo;
             }
-            s_cnt += 1.0; s_ratio += ratio; s_clip += in_range ? 0.0 : 1.0;
 #pragma unroll
-            for (int j = 0; j < A; ++j) {
-                dmu[j] = dlp * (av[j] - mu[j]) * a.inv_var[j];
-                c_bo[j] += dmu[j];
+            for (int j = 0; j < A; ++j) dmu[j] = dlp * (av[j] - mu[j]) * a.inv_var[j];
+            if (hf == 0) {       // one of the two threads of a sample keeps the statistics
+                s_obj += (double)fminf(s1, s2) * a.scale + (double)a.kl_scale * eo * (olp - lp);
+                s_cnt += 1.0; s_ratio += ratio; s_clip += in_range ? 0.0 : 1.0;
+#pragma unroll
+                for (int j = 0; j < A; ++j) c_bo[j] += dmu[j];
             }
         }
-        // dZ2 = (Wo^T dmu) * act'(H2), written K-major (hi/lo) into bufA; q_j = dmu_j * H2 kept for dWo
-        float dz[W];
+        float dz[HW];
 #pragma unroll
-        for (int q = 0; q < W; q += 4) {
+        for (int k = 0; k < HW; k += 4) {
             float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int j = 0; j < A; ++j) {
-                const float4 v = *reinterpret_cast<const float4 *>(wo + j * W + q);
+                const float4 v = *reinterpret_cast<const float4 *>(wo + j * W + c0 + k);
                 s4[0] = fmaf(dmu[j], v.x, s4[0]); s4[1] = fmaf(dmu[j], v.y, s4[1]);
                 s4[2] = fmaf(dmu[j], v.z, s4[2]); s4[3] = fmaf(dmu[j], v.w, s4[3]);
             }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) dz[q + e] = s4[e] * act_bwd_from_out(h[q + e], act_kind);
-        }
-#pragma unroll
-        for (int c = 0; c < W / 4; ++c) {
-            float4 hi, lo;
-            hi.x = tf32_hi(dz[4 * c]); hi.y = tf32_hi(dz[4 * c + 1]); hi.z = tf32_hi(dz[4 * c + 2]); hi.w = tf32_hi(dz[4 * c + 3]);
-            lo.x = dz[4 * c] - hi.x; lo.y = dz[4 * c + 1] - hi.y; lo.z = dz[4 * c + 2] - hi.z; lo.w = dz[4 * c + 3] - hi.w;
-            const uint32_t oc = core_row + (uint32_t)c * 128u;
-            *reinterpret_cast<float4 *>(bufA_hi + oc) = hi;
-            *reinterpret_cast<float4 *>(bufA_lo + oc) = lo;
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            tc_fence_after();
-            umma_gemm_3xtf32(tm_b, A_hi, A_lo, W, false, wb_hi, wb_lo, W, true, W, idesc_b, false, 3);
-            umma_commit(&mbar);
-        }
-        // while the backward-data GEMM runs: column sums for dWo (q_j = dmu_j * H2) and db1 (dZ2)
-#pragma unroll
-        for (int j = 0; j < A; ++j) {
-            float q[W];
-#pragma unroll
-            for (int e = 0; e < W; ++e) q[e] = dmu[j] * h[e];
-            colsum64(q, lane);
-            c_wo[j][0] += q[0];
-            c_wo[j][1] += q[1];
+            for (int e = 0; e < 4; ++e) dz[k + e] = s4[e] * act_bwd_from_out(h[k + e], act_kind);
         }
         {
-            float q[W];
+            float hi[HW], lo[HW];
 #pragma unroll
-            for (int e = 0; e < W; ++e) q[e] = dz[e];
-            colsum64(q, lane);
-            c_b1[0] += q[0];
-            c_b1[1] += q[1];
+            for (int i = 0; i < HW / 4; ++i) {
+                float4 h4, l4;
+                split4(dz + 4 * i, h4, l4);
+                hi[4 * i] = h4.x; hi[4 * i + 1] = h4.y; hi[4 * i + 2] = h4.z; hi[4 * i + 3] = h4.w;
+                lo[4 * i] = l4.x; lo[4 * i + 1] = l4.y; lo[4 * i + 2] = l4.z; lo[4 * i + 3] = l4.w;
+                const uint32_t om = mn_row + (uint32_t)(((i >> 1) ^ rs) << 5) + (uint32_t)(i & 1) * 16u;
+                *reinterpret_cast<float4 *>(bufC_hi + om) = h4;
+                *reinterpret_cast<float4 *>(bufC_lo + om) = l4;
+            }
+            tmem_st32(my_tm + TM_AHI + (uint32_t)c0, hi);     // the forward GEMM has consumed H1
+            tmem_st32(my_tm + TM_ALO + (uint32_t)c0, lo);
+            tmem_st_wait();
         }
-        mbar_wait(&mbar, phase);
-        phase ^= 1u;
-        tc_fence_after();
-        // ---- P4: dZ2 again, MN-major (A operand of the weight-gradient GEMM), into bufA
-#pragma unroll
-        for (int c = 0; c < W / 4; ++c) {
-            float4 hi, lo;
-            hi.x = tf32_hi(dz[4 * c]); hi.y = tf32_hi(dz[4 * c + 1]); hi.z = tf32_hi(dz[4 * c + 2]); hi.w = tf32_hi(dz[4 * c + 3]);
-            lo.x = dz[4 * c] - hi.x; lo.y = dz[4 * c + 1] - hi.y; lo.z = dz[4 * c + 2] - hi.z; lo.w = dz[4 * c + 3] - hi.w;
-            const uint32_t om = (uint32_t)(c >> 3) * (128u * 128u) + mn_row + (uint32_t)((((c & 7) >> 1) ^ rs) << 5) +
-                                (uint32_t)(c & 1) * 16u;
-            *reinterpret_cast<float4 *>(bufA_hi + om) = hi;
-            *reinterpret_cast<float4 *>(bufA_lo + om) = lo;
-        }
-        // dH1 = D_b ; dZ1 = dH1 * act'(H1)
-        float d1[W];
-#pragma unroll
-        for (int c0 = 0; c0 < W; c0 += 32) tmem_ld32(tm_b + lane_base + (uint32_t)c0, d1 + c0);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
         if (threadIdx.x == 0) {
             tc_fence_after();
-            umma_gemm_3xtf32(tm_w, A_hi, A_lo, 128, true, B_hi, B_lo, 128, true, 128, idesc_w, false, 3);
-            umma_commit(&mbar);
+            uint32_t acc = 0;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t acol = tmem + (pass == 2 ? TM_ALO : TM_AHI);
+                const uint32_t b = pass == 1 ? wb_lo : wb_hi;
+#pragma unroll
+                for (int k = 0; k < W; k += 8) {
+                    umma_tf32_ts(tmem + TM_DB, acol + (uint32_t)k, umma_operand_desc(b, W, true, k), idesc_b, acc);
+                    acc = 1u;
+                }
+            }
+            umma_commit(&bar_a);
+            umma_gemm_3xtf32(tmem + TM_DW, C_hi, C_lo, 128, true, B_hi, B_lo, 128, true, 128, idesc_w, false, 3);
+            umma_commit(&bar_w);
         }
-        // while the weight-gradient GEMM runs: first-layer gradients
+        // in the shadow of the two GEMMs: next tile's inputs, column sums for dWo and db1
+        prefetch(tile + gridDim.x);
+#pragma unroll
+        for (int j = 0; j < A; ++j) {
+            float v[HW];
+#pragma unroll
+            for (int e = 0; e < HW; ++e) v[e] = dmu[j] * h[e];
+            c_wo[j] += colsum32(v, lane);
+        }
+        c_b1 += colsum32(dz, lane);
+        mbar_wait(&bar_a, ph_a);
+        ph_a ^= 1u;
+        tc_fence_after();
+        // ---- P5a: dZ1 = D_b * act'(H1); first-layer gradients
+        float d1[HW];
+        tmem_ld32(my_tm + TM_DB + (uint32_t)c0, d1);
         if (RELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                d1[j] = ((m1lo >> j) & 1u) ? d1[j] : 0.0f;
-                d1[32 + j] = ((m1hi >> j) & 1u) ? d1[32 + j] : 0.0f;
-            }
+            for (int j = 0; j < HW; ++j) d1[j] = ((m1 >> j) & 1u) ? d1[j] : 0.0f;
         } else {
-            // H1 = hi + lo from this thread's own row of bufB (MN-major copy; the GEMM only reads it)
 #pragma unroll
-            for (int c = 0; c < W / 4; ++c) {
-                const uint32_t om = (uint32_t)(c >> 3) * (128u * 128u) + mn_row +
-                                    (uint32_t)((((c & 7) >> 1) ^ rs) << 5) + (uint32_t)(c & 1) * 16u;
+            for (int i = 0; i < HW / 4; ++i) {
+                const uint32_t om = mn_row + (uint32_t)(((i >> 1) ^ rs) << 5) + (uint32_t)(i & 1) * 16u;
                 const float4 vh = *reinterpret_cast<const float4 *>(bufB_hi + om);
                 const float4 vl = *reinterpret_cast<const float4 *>(bufB_lo + om);
-                d1[4 * c] *= act_bwd_from_out(vh.x + vl.x, act_kind);
-                d1[4 * c + 1] *= act_bwd_from_out(vh.y + vl.y, act_kind);
-                d1[4 * c + 2] *= act_bwd_from_out(vh.z + vl.z, act_kind);
-                d1[4 * c + 3] *= act_bwd_from_out(vh.w + vl.w, act_kind);
+                d1[4 * i] *= act_bwd_from_out(vh.x + vl.x, act_kind);
+                d1[4 * i + 1] *= act_bwd_from_out(vh.y + vl.y, act_kind);
+                d1[4 * i + 2] *= act_bwd_from_out(vh.z + vl.z, act_kind);
+                d1[4 * i + 3] *= act_bwd_from_out(vh.w + vl.w, act_kind);
             }
         }
 #pragma unroll
         for (int o = 0; o < O; ++o) {
-            float q[W];
+            float v[HW];
 #pragma unroll
-            for (int e = 0; e < W; ++e) q[e] = d1[e] * x[o];
-            colsum64(q, lane);
-            c_w0[o][0] += q[0];
-            c_w0[o][1] += q[1];
+            for (int e = 0; e < HW; ++e) v[e] = d1[e] * x[o];
+            c_w0[o] += colsum32(v, lane);
         }
-        colsum64(d1, lane);
-        c_b0[0] += d1[0];
-        c_b0[1] += d1[1];
-        mbar_wait(&mbar, phase);
-        phase ^= 1u;
+        c_b0 += colsum32(d1, lane);
+        mbar_wait(&bar_w, ph_w);
+        ph_w ^= 1u;
         tc_fence_after();
-        // ---- P5: dW1 tile partial out of TMEM (row r of the M=64 accumulator: lane 32*(r/16) + r%16)
+        // ---- P5b: dW1 tile partial out of TMEM (row r of the M = 64 accumulator: lane 32*(r/16) + r%16)
         {
-            float z[32];
+            float z[HW];
+            tmem_ld32(my_tm + TM_DW + (uint32_t)c0, z);
+            if (lane < 16) {
 #pragma unroll
-            for (int c0 = 0; c0 < W; c0 += 32) {
-                tmem_ld32(tm_w + lane_base + (uint32_t)c0, z);
-                if (lane < 16) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) accS[(c0 + j) * W + warp * 16 + lane] += z[j];
-                }
+                for (int j = 0; j < HW; ++j) accS[(c0 + j) * W + q * 16 + lane] += z[j];
             }
         }
     }
     // ---- write this CTA's partial gradient (private copy, zero-initialised by the host)
+    __syncthreads();
     float *gp = a.gpart + (int64_t)blockIdx.x * a.lay.n_params;
     const int64_t f0 = a.lay.flat_w[0], f1 = a.lay.flat_w[1], f2 = a.lay.flat_w[2];
-    if (lane < 16) {
-        const int r = warp * 16 + lane;
-#pragma unroll
-        for (int k = 0; k < W; ++k) gp[f1 + (int64_t)r * W + k] = accS[k * W + r];
+    for (int i = threadIdx.x; i < W * W; i += 256) {
+        const int r = i / W, k = i % W;
+        gp[f1 + i] = accS[k * W + r];
     }
-    // column partials of the four warps: atomics on the CTA-private copy (sum of 4 floats starting
-    // from 0: the result does not depend on the order only up to rounding, so fix the order instead)
-    __syncthreads();
-    for (int wsel = 0; wsel < 4; ++wsel) {
-        if (warp == wsel) {
+    // column partials of the four lane quadrants, added in a fixed order
+    for (int qs = 0; qs < 4; ++qs) {
+        if (q == qs) {
+            const int col = c0 + lane;
+            gp[f1 + (int64_t)W * W + col] += c_b1;                              // b1
+            gp[f0 + (int64_t)W * O + col] += c_b0;                              // b0
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int col = 2 * lane + e;
-                gp[f1 + (int64_t)W * W + col] += c_b1[e];                       // b1
-                gp[f0 + (int64_t)W * O + col] += c_b0[e];                       // b0
+            for (int o = 0; o < O; ++o) gp[f0 + (int64_t)col * O + o] += c_w0[o];   // W0[col][o]
 #pragma unroll
-                for (int o = 0; o < O; ++o) gp[f0 + (int64_t)col * O + o] += c_w0[o][e];   // W0[col][o]
-#pragma unroll
-                for (int j = 0; j < A; ++j) gp[f2 + (int64_t)j * W + col] += c_wo[j][e];   // Wo[j][col]
-            }
+            for (int j = 0; j < A; ++j) gp[f2 + (int64_t)j * W + col] += c_wo[j];   // Wo[j][col]
         }
         __syncthreads();
     }
-    // dbo and the statistics: warp shuffle then a fixed-order sum over warps
+    // dbo and the statistics: warp shuffle, then a fixed-order sum over the warps
     {
         double v[4] = {s_obj, s_cnt, s_ratio, s_clip};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            for (int off = 16; off > 0; off >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], off);
-            if (lane == 0) sred[q][warp] = v[q];
+        for (int k = 0; k < 4; ++k) {
+            for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], off);
+            if (lane == 0) sred[k][warp] = v[k];
         }
         __syncthreads();
         if (threadIdx.x < 4 && a.spart) {
-            double s = 0.0;
-            for (int w = 0; w < 4; ++w) s += sred[threadIdx.x][w];
-            a.spart[(int64_t)blockIdx.x * 4 + threadIdx.x] = s;
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += sred[threadIdx.x][w];
+            a.spart[(int64_t)blockIdx.x * 4 + threadIdx.x] = t;
         }
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < A; ++j) {
-            float s = c_bo[j];
-            for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
-            if (lane == 0) sred[0][warp] = (double)s;
+            float t = c_bo[j];
+            for (int off = 16; off > 0; off >>= 1) t += __shfl_down_sync(0xffffffffu, t, off);
+            if (lane == 0) sred[0][warp] = (double)t;
             __syncthreads();
             if (threadIdx.x == 0) {
                 float tot = 0.0f;
-                for (int w = 0; w < 4; ++w) tot += (float)sred[0][w];
+                for (int w = 0; w < 8; ++w) tot += (float)sred[0][w];
                 gp[f2 + (int64_t)A * W + j] = tot;
             }
             __syncthreads();
@@ -412,7 +436,7 @@ __global__ void __launch_bounds__(128) update_tc_kernel(const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x < 32) tmem_dealloc(tmem, 256);
+    if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
 }
 
 template <int O, int A>
@@ -420,7 +444,7 @@ static int launch_update_tc(const UpdTcArgs &a, int grid, size_t smem, cudaStrea
     void (*kern)(const UpdTcArgs) =
         a.lay.act == TG_ACT_RELU ? update_tc_kernel<O, A, true> : update_tc_kernel<O, A, false>;
     TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 128, smem, st>>>(a);
+    kern<<<grid, 256, smem, st>>>(a);
     TG_CUDA(cudaGetLastError());
     return TG_OK;
 }
