@@ -63,50 +63,49 @@ def k1_flops_of(P, valid_steps, ms):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region, in-process through NVML
+    (a polling `nvidia-smi -lms` subprocess was measured to add ~5 ms of launch stalls per step)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            # torch's device index follows CUDA_VISIBLE_DEVICES; NVML's does not
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        self.samples.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM),
+                                             pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)))
+                    except Exception:
+                        pass
+                    time.sleep(0.05)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+            self.thread = None
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            p = [x.strip() for x in ln.split(",")]
-            if len(p) < 7:
-                continue
-            try:
-                sm.append(float(p[0])); mx.append(float(p[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, p[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        sm = [c for c, _ in self.samples]
+        reasons = set()
+        for _, mask in self.samples:
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
@@ -361,20 +360,43 @@ def run_ours(args, w):
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    roofline = {
-        "kernel": "update_kernel (tg_policy_grad: fused fwd + clipped surrogate + MLP backward)",
-        "bound": "fp32-fma", "achieved": k3_flops / (k3_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-        "frac": k3_flops / (k3_ms * 1e-3) / 1e12 / fp32_peak, "traffic": None,
-        "peak_source": "tg_fp32_peak FFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
-        "frac_of_measured_bf16_tensor_peak": k3_flops / (k3_ms * 1e-3) / 1e12 / peaks.get("bf16_tflops", 1590.0),
-        "ms_per_launch": k3_ms, "flops_per_launch": k3_flops,
-        "others": {
-            "rollout_kernel": {"bound": "fp32-fma", "ms": k1_ms, "achieved_tflops": k1_flops / (k1_ms * 1e-3) / 1e12,
-                               "frac": k1_flops / (k1_ms * 1e-3) / 1e12 / fp32_peak,
-                               "traj_write_gbs": 4.0 * (O + A + 2) * N * T / (k1_ms * 1e-3) / 1e9},
-            "adv_grpo_kernel": {"bound": "hbm", "ms": k2_ms, "achieved_gbs": 8.0 * N * T / (k2_ms * 1e-3) / 1e9,
-                                "peak_gbs": hbm_peak, "frac": 8.0 * N * T / (k2_ms * 1e-3) / 1e9 / hbm_peak},
-        },
+    bf16_peak = peaks.get("bf16_tflops", 1590.0)
+    tc = w["hidden"] == [64, 64]          # the shapes the tcgen05 kernels cover (tg_update_tc_eligible)
+    k3_tf = k3_flops / (k3_ms * 1e-3) / 1e12
+    k1_tf = k1_flops / (k1_ms * 1e-3) / 1e12
+    if tc:
+        # K3/K1 hidden GEMMs run on the tensor cores as 3xTF32: every algorithmic MAC costs 3 tf32 MMA-MACs and
+        # tf32 peaks at half the bf16 rate, so an fp32-faithful kernel tops out at bf16_peak / 6.
+        roofline = {
+            "kernel": "update_tc_kernel (tg_policy_grad: fused fwd + clipped surrogate + MLP backward, tcgen05 3xTF32)",
+            "bound": "tensor", "achieved": k3_tf, "peak": bf16_peak, "unit": "TFLOP/s", "frac": k3_tf / bf16_peak,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else
+                           "fallback of /opt/skills/guides/B200_PROFILING.md (MEASURED_PEAKS.json absent)",
+            "traffic": 320.6e6 if w is WORKLOADS["pendulum"] else None,
+            "traffic_source": "profiles/r1b_ncu_details_tensor_core_kernels.csv: dram read 315.3 MB + write 5.3 MB "
+                              "per launch (algorithmic: 315 MB of obs+act+adv+old logp)",
+            "achieved_note": "algorithmic FLOPs (6*P per valid step, SURVEY 8d) / CUDA-event time of the launch",
+            "frac_of_3xtf32_ceiling": k3_tf / (bf16_peak / 6.0),
+            "frac_of_measured_fp32_fma_peak": k3_tf / fp32_peak, "fp32_fma_peak_tflops": fp32_peak,
+            "ms_per_launch": k3_ms, "flops_per_launch": k3_flops,
+        }
+    else:
+        roofline = {
+            "kernel": "update_kernel (tg_policy_grad: fused fwd + clipped surrogate + MLP backward, FP32 pipe)",
+            "bound": "fp32-fma", "achieved": k3_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": k3_tf / fp32_peak,
+            "traffic": None,
+            "peak_source": "tg_fp32_peak FFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
+            "frac_of_measured_bf16_tensor_peak": k3_tf / bf16_peak,
+            "ms_per_launch": k3_ms, "flops_per_launch": k3_flops,
+        }
+    roofline["others"] = {
+        ("rollout_tc_kernel" if tc else "rollout_kernel"): {
+            "bound": "tensor" if tc else "fp32-fma", "ms": k1_ms, "achieved_tflops": k1_tf,
+            "frac": k1_tf / (bf16_peak if tc else fp32_peak),
+            "frac_of_measured_fp32_fma_peak": k1_tf / fp32_peak,
+            "traj_write_gbs": 4.0 * (O + A + 2) * N * T / (k1_ms * 1e-3) / 1e9},
+        "adv_grpo_kernel": {"bound": "hbm", "ms": k2_ms, "achieved_gbs": 8.0 * N * T / (k2_ms * 1e-3) / 1e9,
+                            "peak_gbs": hbm_peak, "frac": 8.0 * N * T / (k2_ms * 1e-3) / 1e9 / hbm_peak},
     }
     if rank != 0:
         if world > 1:
@@ -386,7 +408,8 @@ def run_ours(args, w):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "envs_per_gpu": N, "horizon": T, "group_size": E, "mlp": dims,
-                   "updates_per_iter": w["updates"], "precision": "fp32 state + fp32 MLP (throughput mode)",
+                   "updates_per_iter": w["updates"], "precision": "fp32 state; hidden GEMMs 3xTF32 on tcgen05 (fp32-faithful), rest fp32" if tc else
+                                "fp32 state + fp32 MLP (FP32 pipe)",
                    "l2": "per-step working set %.0f MB > 126 MB L2 (inputs larger than L2, no flush)" %
                          (4.0 * (O + A + 3) * N * T / 1e6),
                    "parallelism": f"dp{world} (whole GRPO groups per GPU, NCCL grad allreduce)"},
@@ -395,7 +418,9 @@ def run_ours(args, w):
         "gpu_launches": launches,
         "rollout_env_steps_per_s": valid_per_step_rank * world / (roll_ms * 1e-3),
         "grpo_updates_per_s": w["updates"] / (upd_ms * 1e-3),
-        "phase_ms": {"rollout": roll_ms, "learn": upd_ms},
+        "phase_ms": {"rollout": roll_ms, "learn": upd_ms,
+                     "per_step_total": [round(a.elapsed_time(d), 3) for (a, _), (_, d) in
+                                        zip(phase["rollout"], phase["update"])]},
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info,
     }
     print(json.dumps(line))

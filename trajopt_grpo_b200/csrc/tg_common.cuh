@@ -37,6 +37,8 @@ struct tg_ctx {
     float *packed_tc;  // staged tensor-core operands (hi/lo split, SWIZZLE_128B), device
     size_t packed_tc_cap;
     int math_mode;     // TG_MATH_*
+    int32_t *blkmax;   // per-128-env-block longest episode (tensor-core update kernel), device
+    size_t blkmax_cap;
 };
 int tg_ctx_reserve_packed(tg_ctx *ctx, size_t bytes);
 

@@ -1,7 +1,7 @@
 // K3 on the tensor cores: fused clipped-surrogate objective + MLP backward for policies
 // O -> 64 -> 64 -> A (two hidden layers of width TC_W; tg_policy_grad routes here under
 // TG_MATH_AUTO / TG_MATH_3XTF32).  Persistent CTAs (one per SM) walk tiles of 128 samples
-// (one step t x 128 consecutive envs).  256 threads: sample s = TMEM lane s is served by TWO
+// (one step t x 128 consecutive envs).  8 compute warps + 1 MMA-issuer warp: sample s = TMEM lane s is served by TWO
 // threads (warps q and q+4 of lane quadrant q), each owning one 32-column half of every
 // 64-wide activation row -- this halves the per-thread register/ALU load of the epilogues
 // and gives the scheduler 8 warps to overlap with the tensor-core round trips.
@@ -41,7 +41,19 @@ struct UpdTcArgs {
     float eps_clip, scale, kl_scale;
     float *gpart;   // [grid][n_params], zero-initialised
     double *spart;  // [grid][4]
+    const int32_t *blkmax;  // [ceil(N/128)] longest episode of each 128-env block
 };
+
+__global__ void __launch_bounds__(128) block_maxlen_kernel(int64_t N, const int32_t *__restrict__ len,
+                                                           int32_t *__restrict__ blkmax) {
+    __shared__ int wmax[4];
+    const int64_t n = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    int v = n < N ? len[n] : 0;
+    for (int off = 16; off > 0; off >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, off));
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) blkmax[blockIdx.x] = max(max(wmax[0], wmax[1]), max(wmax[2], wmax[3]));
+}
 
 // butterfly column sums: v[0..32) per lane -> v[0] = sum over the warp's 32 lanes of column `lane`
 template <int HALF, int OFF> TG_D void colsum_step(float *v, int lane) {
@@ -67,6 +79,12 @@ TG_D void split4(const float *v, float4 &hi, float4 &lo) {
     lo.x = v[0] - hi.x; lo.y = v[1] - hi.y; lo.z = v[2] - hi.z; lo.w = v[3] - hi.w;
 }
 
+// named barriers between the 8 compute warps (arrive, non-blocking) and the MMA issuer warp (sync)
+#define BAR_FWD 5
+#define BAR_BWD 6
+TG_D void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+TG_D void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 // TMEM column map (512 columns allocated)
 #define TM_DF 0u
 #define TM_DB 64u
@@ -75,7 +93,7 @@ TG_D void split4(const float *v, float4 &hi, float4 &lo) {
 #define TM_ALO 256u
 
 template <int O, int A, bool RELU>
-__global__ void __launch_bounds__(256) update_tc_kernel(const __grid_constant__ UpdTcArgs a) {
+__global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant__ UpdTcArgs a) {
     constexpr int W = TC_W, HW = TC_W / 2, O4 = (O + 1 + 3) / 4 * 4;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t wbar, bar_a, bar_w;
@@ -98,7 +116,7 @@ __global__ void __launch_bounds__(256) update_tc_kernel(const __grid_constant__ 
         mbar_fence_init();
     }
     if (threadIdx.x < 32) tmem_alloc(&tmem_slot, 512);
-    for (int i = threadIdx.x; i < W * W; i += 256) accS[i] = 0.0f;
+    for (int i = threadIdx.x; i < W * W; i += blockDim.x) accS[i] = 0.0f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -151,8 +169,52 @@ __global__ void __launch_bounds__(256) update_tc_kernel(const __grid_constant__ 
             }
         }
     };
-    prefetch(blockIdx.x);
     uint32_t ph_a = 0, ph_w = 0;
+    bool pending_w = false;      // a weight-gradient GEMM is in flight (CTA-uniform)
+    if (warp == 8) {
+        // ===== MMA issuer warp: one elected lane issues every tcgen05.mma of the CTA, so no compute
+        // warp is held up by the serial issue loop; it meets the compute warps on named barriers =====
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            if ((int)(tile / NB) >= a.blkmax[tile % NB]) continue;
+            named_sync(BAR_FWD, 288);
+            tc_fence_after();
+            if (lane == 0) {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t acol = tmem + (pass == 2 ? TM_ALO : TM_AHI);
+                    const uint32_t b = pass == 1 ? wf_lo : wf_hi;
+#pragma unroll
+                    for (int k = 0; k < W; k += 8) {
+                        umma_tf32_ts(tmem + TM_DF, acol + (uint32_t)k, umma_operand_desc(b, W, false, k), idesc_f, acc);
+                        acc = 1u;
+                    }
+                }
+                umma_commit(&bar_a);
+            }
+            __syncwarp();
+            named_sync(BAR_BWD, 288);
+            tc_fence_after();
+            if (lane == 0) {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t acol = tmem + (pass == 2 ? TM_ALO : TM_AHI);
+                    const uint32_t b = pass == 1 ? wb_lo : wb_hi;
+#pragma unroll
+                    for (int k = 0; k < W; k += 8) {
+                        umma_tf32_ts(tmem + TM_DB, acol + (uint32_t)k, umma_operand_desc(b, W, true, k), idesc_b, acc);
+                        acc = 1u;
+                    }
+                }
+                umma_commit(&bar_a);
+                umma_gemm_3xtf32(tmem + TM_DW, C_hi, C_lo, 128, true, B_hi, B_lo, 128, true, 128, idesc_w, false, 3);
+                umma_commit(&bar_w);
+            }
+            __syncwarp();
+        }
+    } else {
+    prefetch(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         float x[O], av[A];
         const bool valid = vn;
@@ -161,11 +223,9 @@ __global__ void __launch_bounds__(256) update_tc_kernel(const __grid_constant__ 
         for (int o = 0; o < O; ++o) x[o] = valid ? xn[o] : 0.0f;
 #pragma unroll
         for (int j = 0; j < A; ++j) av[j] = an[j];
-        // orders the previous tile's TMEM loads / smem reads before this tile's writes
-        tc_fence_before();
-        const int any = __syncthreads_or(valid ? 1 : 0);
-        tc_fence_after();
-        if (!any) { prefetch(tile + gridDim.x); continue; }
+        // whole tile is padding (step index past the longest episode of its 128 envs): CTA-uniform
+        // decision from the precomputed per-block maximum length, no barrier needed
+        if ((int)(tile / NB) >= a.blkmax[tile % NB]) { prefetch(tile + gridDim.x); continue; }
         // ---- P1: first Linear on the FP32 pipe, this thread's 32 neurons
         float h[HW];
 #pragma unroll
@@ -192,31 +252,32 @@ __global__ void __launch_bounds__(256) update_tc_kernel(const __grid_constant__ 
                 split4(h + 4 * i, h4, l4);
                 hi[4 * i] = h4.x; hi[4 * i + 1] = h4.y; hi[4 * i + 2] = h4.z; hi[4 * i + 3] = h4.w;
                 lo[4 * i] = l4.x; lo[4 * i + 1] = l4.y; lo[4 * i + 2] = l4.z; lo[4 * i + 3] = l4.w;
-                const uint32_t om = mn_row + (uint32_t)(((i >> 1) ^ rs) << 5) + (uint32_t)(i & 1) * 16u;
-                *reinterpret_cast<float4 *>(bufB_hi + om) = h4;
-                *reinterpret_cast<float4 *>(bufB_lo + om) = l4;
             }
             tmem_st32(my_tm + TM_AHI + (uint32_t)c0, hi);
             tmem_st32(my_tm + TM_ALO + (uint32_t)c0, lo);
             tmem_st_wait();
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            tc_fence_after();
-            uint32_t acc = 0;
+            tc_fence_before();
+            named_arrive(BAR_FWD, 288);          // -> issuer warp: forward-GEMM operands are in place
+            // in the shadow of the forward GEMM: retire the PREVIOUS tile's weight-gradient GEMM (its
+            // operands bufB/bufC and its accumulator D_w are then free), then publish H1 MN-major
+            if (pending_w) {
+                mbar_wait(&bar_w, ph_w);
+                ph_w ^= 1u;
+                tc_fence_after();
+                float z[HW];
+                tmem_ld32(my_tm + TM_DW + (uint32_t)c0, z);
+                if (lane < 16) {
 #pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-                const uint32_t acol = tmem + (pass == 2 ? TM_ALO : TM_AHI);
-                const uint32_t b = pass == 1 ? wf_lo : wf_hi;
-#pragma unroll
-                for (int k = 0; k < W; k += 8) {
-                    umma_tf32_ts(tmem + TM_DF, acol + (uint32_t)k, umma_operand_desc(b, W, false, k), idesc_f, acc);
-                    acc = 1u;
+                    for (int j = 0; j < HW; ++j) accS[(c0 + j) * W + q * 16 + lane] += z[j];
                 }
+                pending_w = false;
             }
-            umma_commit(&bar_a);
+#pragma unroll
+            for (int i = 0; i < HW / 4; ++i) {
+                const uint32_t om = mn_row + (uint32_t)(((i >> 1) ^ rs) << 5) + (uint32_t)(i & 1) * 16u;
+                *reinterpret_cast<float4 *>(bufB_hi + om) = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                *reinterpret_cast<float4 *>(bufB_lo + om) = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            }
         }
         mbar_wait(&bar_a, ph_a);
         ph_a ^= 1u;
@@ -245,7 +306,8 @@ __global__ void __launch_bounds__(256) update_tc_kernel(const __grid_constant__ 
             }
             muS[hf][j][s] = acc;
         }
-        __syncthreads();
+        // only the two warps that share this lane quadrant exchange data: named barrier, 64 threads
+        asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
         float mu[A], dmu[A];
 #pragma unroll
         for (int j = 0; j < A; ++j) {
@@ -314,24 +376,8 @@ __global__ void __launch_bounds__(256) update_tc_kernel(const __grid_constant__ 
         }
         fence_proxy_async();
         tc_fence_before();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            tc_fence_after();
-            uint32_t acc = 0;
-#pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-                const uint32_t acol = tmem + (pass == 2 ? TM_ALO : TM_AHI);
-                const uint32_t b = pass == 1 ? wb_lo : wb_hi;
-#pragma unroll
-                for (int k = 0; k < W; k += 8) {
-                    umma_tf32_ts(tmem + TM_DB, acol + (uint32_t)k, umma_operand_desc(b, W, true, k), idesc_b, acc);
-                    acc = 1u;
-                }
-            }
-            umma_commit(&bar_a);
-            umma_gemm_3xtf32(tmem + TM_DW, C_hi, C_lo, 128, true, B_hi, B_lo, 128, true, 128, idesc_w, false, 3);
-            umma_commit(&bar_w);
-        }
+        named_arrive(BAR_BWD, 288);          // -> issuer warp: dZ2 (TMEM + bufC) and H1 (bufB) are in place
+        pending_w = true;
         // in the shadow of the two GEMMs: next tile's inputs, column sums for dWo and db1
         prefetch(tile + gridDim.x);
 #pragma unroll
@@ -371,30 +417,31 @@ __global__ void __launch_bounds__(256) update_tc_kernel(const __grid_constant__ 
             c_w0[o] += colsum32(v, lane);
         }
         c_b0 += colsum32(d1, lane);
+        // P5b (D_w -> accS) is deferred into the next tile's forward-GEMM shadow
+    }
+    // ---- retire the last weight-gradient GEMM (row r of the M = 64 accumulator: lane 32*(r/16) + r%16)
+    if (pending_w) {
         mbar_wait(&bar_w, ph_w);
-        ph_w ^= 1u;
         tc_fence_after();
-        // ---- P5b: dW1 tile partial out of TMEM (row r of the M = 64 accumulator: lane 32*(r/16) + r%16)
-        {
-            float z[HW];
-            tmem_ld32(my_tm + TM_DW + (uint32_t)c0, z);
-            if (lane < 16) {
+        float z[HW];
+        tmem_ld32(my_tm + TM_DW + (uint32_t)c0, z);
+        if (lane < 16) {
 #pragma unroll
-                for (int j = 0; j < HW; ++j) accS[(c0 + j) * W + q * 16 + lane] += z[j];
-            }
+            for (int j = 0; j < HW; ++j) accS[(c0 + j) * W + q * 16 + lane] += z[j];
         }
     }
+    }   // compute warps
     // ---- write this CTA's partial gradient (private copy, zero-initialised by the host)
     __syncthreads();
     float *gp = a.gpart + (int64_t)blockIdx.x * a.lay.n_params;
     const int64_t f0 = a.lay.flat_w[0], f1 = a.lay.flat_w[1], f2 = a.lay.flat_w[2];
-    for (int i = threadIdx.x; i < W * W; i += 256) {
+    for (int i = threadIdx.x; i < W * W; i += blockDim.x) {
         const int r = i / W, k = i % W;
         gp[f1 + i] = accS[k * W + r];
     }
     // column partials of the four lane quadrants, added in a fixed order
     for (int qs = 0; qs < 4; ++qs) {
-        if (q == qs) {
+        if (warp < 8 && q == qs) {
             const int col = c0 + lane;
             gp[f1 + (int64_t)W * W + col] += c_b1;                              // b1
             gp[f0 + (int64_t)W * O + col] += c_b0;                              // b0
@@ -411,7 +458,7 @@ __global__ void __launch_bounds__(256) update_tc_kernel(const __grid_constant__ 
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], off);
-            if (lane == 0) sred[k][warp] = v[k];
+            if (lane == 0 && warp < 8) sred[k][warp] = v[k];
         }
         __syncthreads();
         if (threadIdx.x < 4 && a.spart) {
@@ -424,7 +471,7 @@ __global__ void __launch_bounds__(256) update_tc_kernel(const __grid_constant__ 
         for (int j = 0; j < A; ++j) {
             float t = c_bo[j];
             for (int off = 16; off > 0; off >>= 1) t += __shfl_down_sync(0xffffffffu, t, off);
-            if (lane == 0) sred[0][warp] = (double)t;
+            if (lane == 0 && warp < 8) sred[0][warp] = (double)t;
             __syncthreads();
             if (threadIdx.x == 0) {
                 float tot = 0.0f;
@@ -444,7 +491,7 @@ static int launch_update_tc(const UpdTcArgs &a, int grid, size_t smem, cudaStrea
     void (*kern)(const UpdTcArgs) =
         a.lay.act == TG_ACT_RELU ? update_tc_kernel<O, A, true> : update_tc_kernel<O, A, false>;
     TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 256, smem, st>>>(a);
+    kern<<<grid, 288, smem, st>>>(a);
     TG_CUDA(cudaGetLastError());
     return TG_OK;
 }
@@ -473,7 +520,23 @@ int tg_policy_grad_tc(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, cons
     for (int j = 0; j < TG_MAX_ACT; ++j) { a.inv_sd[j] = inv_sd[j]; a.inv_var[j] = inv_var[j]; }
     a.log_norm = log_norm; a.eps_clip = eps_clip; a.scale = scale; a.kl_scale = kl_scale;
     a.gpart = gpart; a.spart = spart;
-    const size_t smem = ((size_t)a.lay.total * 4 + 1023) / 1024 * 1024 + 4 * (size_t)128 * TC_W * 4 +
+    {
+        const int64_t NBk = (N + 127) / 128;
+        if ((size_t)NBk * sizeof(int32_t) > ctx->blkmax_cap) {
+            if (ctx->blkmax) {
+                TG_CUDA(cudaDeviceSynchronize());
+                TG_CUDA(cudaFree(ctx->blkmax));
+                ctx->blkmax = nullptr;
+                ctx->blkmax_cap = 0;
+            }
+            TG_CUDA(cudaMalloc(&ctx->blkmax, (size_t)NBk * sizeof(int32_t)));
+            ctx->blkmax_cap = (size_t)NBk * sizeof(int32_t);
+        }
+        block_maxlen_kernel<<<(unsigned)NBk, 128, 0, st>>>(N, len, ctx->blkmax);
+        TG_CUDA(cudaGetLastError());
+        a.blkmax = ctx->blkmax;
+    }
+    const size_t smem =((size_t)a.lay.total * 4 + 1023) / 1024 * 1024 + 4 * (size_t)128 * TC_W * 4 +
                         (size_t)TC_W * TC_W * 4;
     TG_REQUIRE(smem <= (size_t)ctx->smem_optin, TG_ERR_UNSUPPORTED, "tensor-core update needs %zu B of shared memory", smem);
     const int O = a.lay.O, A = a.lay.A;
