@@ -87,7 +87,7 @@ class ClockSampler:
                                              pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)))
                     except Exception:
                         pass
-                    time.sleep(0.05)
+                    time.sleep(0.02)
             self.thread = threading.Thread(target=loop, daemon=True)
             self.thread.start()
         except Exception as e:  # noqa: BLE001
@@ -147,6 +147,10 @@ def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is entitled to every host thread (torch reads
+    # the variable when it is first imported, which happens inside cpu_leg)
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.pop(k, None)
     vals, last = [], None
     for i in range(args.warmup + args.steps):
         last = cpu_leg(w, seed=i)
@@ -232,6 +236,7 @@ def run_ours(args, w):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     phase = {"rollout": [], "adv": [], "update": []}
     lens_sum = torch.zeros((), dtype=torch.int64, device=dev)
+    host_marks = []
 
     def one_step_device(i, timed):
         e = [ev() for _ in range(4)]
@@ -243,19 +248,25 @@ def run_ours(args, w):
         e[2].record()
         algo.learn(buf)
         e[3].record()
+        # also during warm-up: the first call of a torch op loads its CUDA module lazily, which stalls the
+        # host for tens of ms -- that must not land inside the timed region
+        lens_sum.add_(r.len.sum())
         if timed:
+            host_marks.append(time.perf_counter())
             phase["rollout"].append((e[0], e[1]))
             phase["update"].append((e[2], e[3]))
-            lens_sum.add_(r.len.sum())
 
     for i in range(args.warmup):
         one_step_device(i, False)
     barrier()
+    lens_sum.zero_()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    torch.cuda.synchronize()
     launches0 = engine.COUNTERS["launches"]
     t0, t1 = ev(), ev()
+    host_t0 = time.perf_counter()
     t0.record()
     for i in range(args.warmup, total):
         one_step_device(i, True)
@@ -306,6 +317,11 @@ def run_ours(args, w):
     clock_info = clocks.stop() if rank == 0 else None
 
     if args.device_only:                          # short run for ncu: no e2e / CPU legs
+        if rank == 0 and os.environ.get("TG_TIMELINE"):
+            print("gpu e0/e3 ms since t0:", [(round(t0.elapsed_time(a), 2), round(t0.elapsed_time(d), 2))
+                                             for (a, _), (_, d) in zip(phase["rollout"], phase["update"])],
+                  "end", round(t0.elapsed_time(t1), 2), file=sys.stderr)
+            print("host enqueue done ms since t0:", [round((m - host_t0) * 1e3, 2) for m in host_marks], file=sys.stderr)
         if rank == 0:
             print(json.dumps({"device_only": True, "value": value, "ms_per_step": ms_total / args.steps,
                               "k1_ms": k1_ms, "k2_ms": k2_ms, "k3_ms": k3_ms, "gpu_launches": launches,
