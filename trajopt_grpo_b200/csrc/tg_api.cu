@@ -41,8 +41,9 @@ extern "C" int tg_ctx_create(int device, tg_ctx **out) {
     c->packed_tc = nullptr;
     c->packed_tc_cap = 0;
     c->math_mode = TG_MATH_AUTO;
-    c->blkmax = nullptr;
-    c->blkmax_cap = 0;
+    c->order_buf = nullptr;
+    c->order_cap = 0;
+    c->perm = c->cnt = nullptr;
     *out = c;
     return TG_OK;
 }
@@ -52,7 +53,7 @@ extern "C" void tg_ctx_destroy(tg_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->packed) cudaFree(ctx->packed);
     if (ctx->packed_tc) cudaFree(ctx->packed_tc);
-    if (ctx->blkmax) cudaFree(ctx->blkmax);
+    if (ctx->order_buf) cudaFree(ctx->order_buf);
     delete ctx;
 }
 

@@ -37,9 +37,14 @@ struct tg_ctx {
     float *packed_tc;  // staged tensor-core operands (hi/lo split, SWIZZLE_128B), device
     size_t packed_tc_cap;
     int math_mode;     // TG_MATH_*
-    int32_t *blkmax;   // per-128-env-block longest episode (tensor-core update kernel), device
-    size_t blkmax_cap;
+    // length order of the rollout being updated (tg_order.cu): env indices sorted by episode length,
+    // longest first, and the number of live envs per step; device, owned by the ctx
+    void *order_buf;
+    size_t order_cap;
+    int32_t *perm, *cnt;
 };
+// fills ctx->perm [N] and ctx->cnt [T] for `len` (asynchronous on `st`)
+int tg_len_order(tg_ctx *ctx, int64_t N, int T, const int32_t *len, cudaStream_t st);
 int tg_ctx_reserve_packed(tg_ctx *ctx, size_t bytes);
 
 // ---- MLP tile configurations --------------------------------------------------

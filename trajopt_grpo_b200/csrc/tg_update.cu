@@ -27,6 +27,8 @@ struct UpdArgs {
     int head;
     const float *obs, *act, *adv, *oldlp, *target;
     const int32_t *len;
+    // length order (tg_order.cu) or null: sorted position j of step t is env perm[j], live iff j < cnt[t]
+    const int32_t *perm, *cnt;
     const float *packed;
     float inv_sd[TG_MAX_ACT], inv_var[TG_MAX_ACT], log_norm;
     float eps_clip, scale, kl_scale;
@@ -34,6 +36,11 @@ struct UpdArgs {
     double *spart;  // [grid][4]
     float *out_mu, *out_logp;
 };
+
+// Fire-and-forget accumulation into the CTA-private gradient copy (SASS RED.E.ADD.F32): every element has
+// one fixed owner thread, so the additions to an address are issued by one thread in program order and the
+// sum stays deterministic -- but unlike a load/add/store the thread never waits for the L2 round trip.
+TG_D void red_add(float *p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 
 // dW[n][k] (+)= sum_b dZ[n][b] * H[k][b] for a BIxBJ register block per thread;
 // rows are interleaved (n = nb + i*NBI, k = kb + j*KBJ) so that the 8 lanes of a
@@ -75,7 +82,7 @@ TG_D void tile_dw_blk(const float *dZ, int Nn, const float *Hin, int Kk, float *
 #pragma unroll
                 for (int j = 0; j < BJ; ++j) {
                     const int k = kb + j * KBJ;
-                    if (k < Kk) gW[(int64_t)n * Kk + k] += acc[i][j];
+                    if (k < Kk) red_add(gW + (int64_t)n * Kk + k, acc[i][j]);
                 }
             }
         }
@@ -97,7 +104,7 @@ TG_D void tile_dw(const float *dZ, int Nn, const float *Hin, int Kk, float *__re
             const float4 v = *reinterpret_cast<const float4 *>(dZ + n * LDX + b);
             s += (v.x + v.y) + (v.z + v.w);
         }
-        gB[n] += s;
+        red_add(gB + n, s);
     }
 }
 
@@ -107,6 +114,7 @@ __global__ void __launch_bounds__(TileCfg<CFG>::NT) update_kernel(const __grid_c
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t wbar;
     __shared__ double sred[4][NT / 32];
+    __shared__ int32_t tile_env[B];      // env index of each sample of the tile, -1 = padding
     const int nl = a.lay.n_layers, nh = nl - 1;
     const int O = a.lay.O, O8 = tg_round_up(O, 8);
     float *Ws = reinterpret_cast<float *>(smem_raw);
@@ -131,18 +139,27 @@ __global__ void __launch_bounds__(TileCfg<CFG>::NT) update_kernel(const __grid_c
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int t = (int)(tile / NB);
         const int64_t nb0 = (tile % NB) * B;
-        // ---- 1. load the tile's observations (coalesced rows of obs[t][o][:])
+        // ---- 1. load the tile's observations (rows of obs[t][o][:]; coalesced when the tile is a run of
+        //         consecutive envs, a gather through perm when the rollout is walked in length order)
         bool valid = false;
+        int64_t n_own = 0;
+        if (a.cnt != nullptr && nb0 >= a.cnt[t]) continue;   // whole tile is padding (CTA-uniform)
         if (owner) {
-            const int64_t n = nb0 + threadIdx.x;
-            valid = n < N && (a.len == nullptr || t < a.len[n]);
+            const int64_t j = nb0 + threadIdx.x;
+            if (a.cnt != nullptr) {
+                valid = j < a.cnt[t];
+                n_own = valid ? a.perm[j] : 0;
+            } else {
+                n_own = j;
+                valid = j < N && (a.len == nullptr || t < a.len[j]);
+            }
+            tile_env[threadIdx.x] = valid ? (int32_t)n_own : -1;
         }
         if (!__syncthreads_or(valid ? 1 : 0)) continue;   // whole tile is padding
         for (int idx = threadIdx.x; idx < O * B; idx += NT) {
             const int o = idx / B, b = idx % B;
-            const int64_t n = nb0 + b;
-            const bool v = n < N && (a.len == nullptr || t < a.len[n]);
-            X0[o * LDX + b] = v ? a.obs[((int64_t)t * O + o) * N + n] : 0.0f;
+            const int32_t n = tile_env[b];
+            X0[o * LDX + b] = n >= 0 ? a.obs[((int64_t)t * O + o) * N + n] : 0.0f;
         }
         __syncthreads();
         // ---- 2. forward, keeping H_1..H_nh
@@ -156,7 +173,7 @@ __global__ void __launch_bounds__(TileCfg<CFG>::NT) update_kernel(const __grid_c
         tile_output_layer<CFG, A, WG>(W + LO.wt, W + LO.bias, Hlast, P, LO.K, mu);
         // ---- 3. per-sample objective and d/dmu
         if (owner) {
-            const int64_t n = nb0 + threadIdx.x;
+            const int64_t n = n_own;
             float dmu[A];
 #pragma unroll
             for (int j = 0; j < A; ++j) dmu[j] = 0.0f;
@@ -364,6 +381,12 @@ static int run_grad(tg_ctx *ctx, UpdArgs &a, const float *params, float *out_gra
     int rc = tg_pack_weights(ctx, a.lay, params, st);
     if (rc) return rc;
     a.packed = ctx->packed;
+    if (a.len != nullptr) {                      // ragged episodes: walk the samples in length order
+        rc = tg_len_order(ctx, a.N, a.T, a.len, st);
+        if (rc) return rc;
+        a.perm = ctx->perm;
+        a.cnt = ctx->cnt;
+    }
     const int grid = update_grid(ctx, a.lay);
     const size_t gbytes = (size_t)grid * a.lay.n_params * sizeof(float);
     a.gpart = reinterpret_cast<float *>(workspace);
@@ -488,6 +511,12 @@ extern "C" int tg_policy_forward_traj(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_
     rc = tg_pack_weights(ctx, a.lay, params, st);
     if (rc) return rc;
     a.packed = ctx->packed;
+    if (len != nullptr) {
+        rc = tg_len_order(ctx, N, T, len, st);
+        if (rc) return rc;
+        a.perm = ctx->perm;
+        a.cnt = ctx->cnt;
+    }
     int grid = update_grid(ctx, a.lay);
     const int64_t ntiles = ((N + a.lay.B - 1) / a.lay.B) * T;
     if (grid > ntiles) grid = (int)ntiles;

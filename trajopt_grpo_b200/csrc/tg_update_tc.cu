@@ -41,19 +41,9 @@ struct UpdTcArgs {
     float eps_clip, scale, kl_scale;
     float *gpart;   // [grid][n_params], zero-initialised
     double *spart;  // [grid][4]
-    const int32_t *blkmax;  // [ceil(N/128)] longest episode of each 128-env block
+    // length order of the rollout (tg_order.cu): sorted position j of step t is env perm[j], live iff j < cnt[t]
+    const int32_t *perm, *cnt;
 };
-
-__global__ void __launch_bounds__(128) block_maxlen_kernel(int64_t N, const int32_t *__restrict__ len,
-                                                           int32_t *__restrict__ blkmax) {
-    __shared__ int wmax[4];
-    const int64_t n = (int64_t)blockIdx.x * 128 + threadIdx.x;
-    int v = n < N ? len[n] : 0;
-    for (int off = 16; off > 0; off >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, off));
-    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) blkmax[blockIdx.x] = max(max(wmax[0], wmax[1]), max(wmax[2], wmax[3]));
-}
 
 // butterfly column sums: v[0..32) per lane -> v[0] = sum over the warp's 32 lanes of column `lane`
 template <int HALF, int OFF> TG_D void colsum_step(float *v, int lane) {
@@ -157,9 +147,10 @@ __global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant
         vn = false;
         if (tile < ntiles) {
             const int t = (int)(tile / NB);
-            const int64_t n = (tile % NB) * 128 + s;
-            vn = n < N && t < a.len[n];
+            const int64_t j = (tile % NB) * 128 + s;
+            vn = j < a.cnt[t];
             if (vn) {
+                const int64_t n = a.perm[j];
 #pragma unroll
                 for (int o = 0; o < O; ++o) xn[o] = a.obs[((int64_t)t * O + o) * N + n];
 #pragma unroll
@@ -175,7 +166,7 @@ __global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant
         // ===== MMA issuer warp: one elected lane issues every tcgen05.mma of the CTA, so no compute
         // warp is held up by the serial issue loop; it meets the compute warps on named barriers =====
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            if ((int)(tile / NB) >= a.blkmax[tile % NB]) continue;
+            if ((tile % NB) * 128 >= a.cnt[tile / NB]) continue;
             named_sync(BAR_FWD, 288);
             tc_fence_after();
             if (lane == 0) {
@@ -223,9 +214,9 @@ __global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant
         for (int o = 0; o < O; ++o) x[o] = valid ? xn[o] : 0.0f;
 #pragma unroll
         for (int j = 0; j < A; ++j) av[j] = an[j];
-        // whole tile is padding (step index past the longest episode of its 128 envs): CTA-uniform
-        // decision from the precomputed per-block maximum length, no barrier needed
-        if ((int)(tile / NB) >= a.blkmax[tile % NB]) { prefetch(tile + gridDim.x); continue; }
+        // whole tile is padding (fewer live envs at this step than the tile's first sorted position):
+        // CTA-uniform decision from the per-step live count, no barrier needed
+        if ((tile % NB) * 128 >= a.cnt[tile / NB]) { prefetch(tile + gridDim.x); continue; }
         // ---- P1: first Linear on the FP32 pipe, this thread's 32 neurons
         float h[HW];
 #pragma unroll
@@ -520,22 +511,10 @@ int tg_policy_grad_tc(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, cons
     for (int j = 0; j < TG_MAX_ACT; ++j) { a.inv_sd[j] = inv_sd[j]; a.inv_var[j] = inv_var[j]; }
     a.log_norm = log_norm; a.eps_clip = eps_clip; a.scale = scale; a.kl_scale = kl_scale;
     a.gpart = gpart; a.spart = spart;
-    {
-        const int64_t NBk = (N + 127) / 128;
-        if ((size_t)NBk * sizeof(int32_t) > ctx->blkmax_cap) {
-            if (ctx->blkmax) {
-                TG_CUDA(cudaDeviceSynchronize());
-                TG_CUDA(cudaFree(ctx->blkmax));
-                ctx->blkmax = nullptr;
-                ctx->blkmax_cap = 0;
-            }
-            TG_CUDA(cudaMalloc(&ctx->blkmax, (size_t)NBk * sizeof(int32_t)));
-            ctx->blkmax_cap = (size_t)NBk * sizeof(int32_t);
-        }
-        block_maxlen_kernel<<<(unsigned)NBk, 128, 0, st>>>(N, len, ctx->blkmax);
-        TG_CUDA(cudaGetLastError());
-        a.blkmax = ctx->blkmax;
-    }
+    rc = tg_len_order(ctx, N, T, len, st);
+    if (rc) return rc;
+    a.perm = ctx->perm;
+    a.cnt = ctx->cnt;
     const size_t smem =((size_t)a.lay.total * 4 + 1023) / 1024 * 1024 + 4 * (size_t)128 * TC_W * 4 +
                         (size_t)TC_W * TC_W * 4;
     TG_REQUIRE(smem <= (size_t)ctx->smem_optin, TG_ERR_UNSUPPORTED, "tensor-core update needs %zu B of shared memory", smem);

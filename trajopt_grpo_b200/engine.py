@@ -201,7 +201,7 @@ def policy_forward_traj(dims, activation, params, obs, cov_diag=None, act=None, 
         rc = lib.tg_policy_forward_traj(L.ctx(dev), C.byref(mcfg), N, T, L.ptr(obs), L.ptr(act), L.ptr(length),
                                         L.ptr(params), cov, L.ptr(mu), L.ptr(logp), L.stream_ptr())
     L.check(rc, "tg_policy_forward_traj")
-    _count(2)
+    _count(2 + (2 if length is not None else 0))   # + order_keys / order_count (the radix sort is CUB's)
     return mu, logp
 
 
@@ -248,7 +248,7 @@ def policy_grad(dims, activation, params, cov_diag, obs, act, adv, old_logp, len
                                 L.ptr(length), L.ptr(params), L.cov_array(cov_diag), float(eps_clip), float(scale),
                                 float(kl_scale), L.ptr(grad), L.ptr(stats), L.ptr(ws), L.stream_ptr())
     L.check(rc, "tg_policy_grad")
-    _count(3)
+    _count(5)                                      # pack, order_keys, order_count, update, grad_reduce
     return grad, stats
 
 
@@ -269,7 +269,7 @@ def value_grad(dims, activation, params, obs, target, length, scale, out_grad=No
         rc = lib.tg_value_grad(L.ctx(dev), C.byref(mcfg), N, T, L.ptr(obs), L.ptr(target), L.ptr(length),
                                L.ptr(params), float(scale), L.ptr(grad), L.ptr(stats), L.ptr(ws), L.stream_ptr())
     L.check(rc, "tg_value_grad")
-    _count(3)
+    _count(5)
     return grad, stats
 
 
