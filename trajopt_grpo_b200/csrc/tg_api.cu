@@ -1,5 +1,6 @@
 // Context, error reporting, MLP staging layout and the weight pack kernel.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "tg_common.cuh"
 
@@ -41,6 +42,10 @@ extern "C" int tg_ctx_create(int device, tg_ctx **out) {
     c->packed_tc = nullptr;
     c->packed_tc_cap = 0;
     c->math_mode = TG_MATH_AUTO;
+    {
+        const char *e = getenv("TG_ROLLOUT_TC2");     // diagnostics only (A/B of the two width-64 rollout kernels)
+        c->rollout_tc2 = (e && e[0] == '1') ? 1 : 0;
+    }
     c->order_buf = nullptr;
     c->order_cap = 0;
     c->perm = c->cnt = nullptr;
@@ -69,18 +74,24 @@ extern "C" int tg_ctx_set_math(tg_ctx *ctx, int math_mode) {
 // ---------------------------------------------------------------------------
 bool tg_tc_eligible(const tg_mlp_cfg *mlp) {
     if (!mlp || mlp->n_layers < 3 || mlp->n_layers > TG_MAX_LAYERS) return false;   // >= 2 hidden layers
+    const int W = mlp->dims[1];
+    if (W != 64 && W != 128) return false;
     for (int l = 1; l < mlp->n_layers; ++l)
-        if (mlp->dims[l] != TC_W) return false;
+        if (mlp->dims[l] != W) return false;
+    // every hidden->hidden weight (hi + lo) is resident in shared memory next to the first/last layer rows
+    if ((size_t)(mlp->n_layers - 2) * 2 * W * W * 4 > (size_t)160 * 1024) return false;
     return mlp->dims[0] >= 1 && mlp->dims[0] <= TG_MAX_OBS && mlp->dims[mlp->n_layers] >= 1 &&
            mlp->dims[mlp->n_layers] <= TG_MAX_ACT && mlp->activation >= 0 && mlp->activation <= 2;
 }
 
 int tg_build_tc_layout(const tg_mlp_cfg *mlp, tg_tc_layout *out, bool with_backward) {
     TG_REQUIRE(tg_tc_eligible(mlp), TG_ERR_UNSUPPORTED,
-               "tensor-core path needs >= 2 hidden layers, all of width %d", TC_W);
+               "tensor-core path needs >= 2 hidden layers of equal width 64 or 128 whose weights fit in shared memory");
     memset(out, 0, sizeof(*out));
     const int nl = mlp->n_layers;
     out->n_layers = nl;
+    out->W = mlp->dims[1];
+    const int TCW = out->W;
     out->nh = nl - 1;
     out->act = mlp->activation;
     out->O = mlp->dims[0];
@@ -94,66 +105,66 @@ int tg_build_tc_layout(const tg_mlp_cfg *mlp, tg_tc_layout *out, bool with_backw
     out->n_params = flat;
     int64_t off = 0;   // floats; MMA operand blocks 1024-byte (256-float) aligned
     for (int l = 1; l < nl - 1; ++l) {
-        out->whi[l] = off; off += TC_W * TC_W;
-        out->wlo[l] = off; off += TC_W * TC_W;
+        out->whi[l] = off; off += TCW * TCW;
+        out->wlo[l] = off; off += TCW * TCW;
         out->wbhi[l] = out->wblo[l] = -1;
         if (with_backward) {
-            out->wbhi[l] = off; off += TC_W * TC_W;
-            out->wblo[l] = off; off += TC_W * TC_W;
+            out->wbhi[l] = off; off += TCW * TCW;
+            out->wblo[l] = off; off += TCW * TCW;
         }
     }
-    for (int l = 1; l < nl - 1; ++l) { out->bias[l] = off; off += TC_W; }
-    out->w1 = off; off += (int64_t)TC_W * out->O4;
-    out->wo = off; off += (int64_t)out->A * TC_W;
+    for (int l = 1; l < nl - 1; ++l) { out->bias[l] = off; off += TCW; }
+    out->w1 = off; off += (int64_t)TCW * out->O4;
+    out->wo = off; off += (int64_t)out->A * TCW;
     out->bo = off; off += 4;
     out->total = tg_round_up((int)off, 4);
     return TG_OK;
 }
 
 __global__ void pack_tc_kernel(tg_tc_layout lay, const float *__restrict__ params, float *__restrict__ packed) {
-    const int nl = lay.n_layers;
+    const int nl = lay.n_layers, TCW = lay.W;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < lay.total;
          i += (int64_t)gridDim.x * blockDim.x) {
         float v = 0.0f;
         // first Linear: rows (W1[n][:], b1[n], 0..)
-        if (i >= lay.w1 && i < lay.w1 + (int64_t)TC_W * lay.O4) {
+        if (i >= lay.w1 && i < lay.w1 + (int64_t)TCW * lay.O4) {
             const int n = (int)((i - lay.w1) / lay.O4), o = (int)((i - lay.w1) % lay.O4);
             const float *Wf = params + lay.flat_w[0];
             if (o < lay.O) v = Wf[(int64_t)n * lay.O + o];
-            else if (o == lay.O) v = Wf[(int64_t)TC_W * lay.O + n];
-        } else if (i >= lay.wo && i < lay.wo + (int64_t)lay.A * TC_W) {
+            else if (o == lay.O) v = Wf[(int64_t)TCW * lay.O + n];
+        } else if (i >= lay.wo && i < lay.wo + (int64_t)lay.A * TCW) {
             v = params[lay.flat_w[nl - 1] + (i - lay.wo)];
         } else if (i >= lay.bo && i < lay.bo + lay.A) {
-            v = params[lay.flat_w[nl - 1] + (int64_t)lay.A * TC_W + (i - lay.bo)];
+            v = params[lay.flat_w[nl - 1] + (int64_t)lay.A * TCW + (i - lay.bo)];
         } else {
             for (int l = 1; l < nl - 1; ++l) {
                 const float *Wf = params + lay.flat_w[l];   // [N][K] torch layout = K-major B operand
-                if (i >= lay.bias[l] && i < lay.bias[l] + TC_W) v = Wf[(int64_t)TC_W * TC_W + (i - lay.bias[l])];
-                const bool hi = i >= lay.whi[l] && i < lay.whi[l] + TC_W * TC_W;
-                const bool lo = i >= lay.wlo[l] && i < lay.wlo[l] + TC_W * TC_W;
+                if (i >= lay.bias[l] && i < lay.bias[l] + TCW) v = Wf[(int64_t)TCW * TCW + (i - lay.bias[l])];
+                const bool hi = i >= lay.whi[l] && i < lay.whi[l] + TCW * TCW;
+                const bool lo = i >= lay.wlo[l] && i < lay.wlo[l] + TCW * TCW;
                 if (hi || lo) {
                     // invert the core-matrix layout of tg_umma.cuh: byte offset -> (row n, col k)
                     const uint32_t b = (uint32_t)(i - (hi ? lay.whi[l] : lay.wlo[l])) * 4u;
-                    const uint32_t group = (TC_W / 4) * 128u;
+                    const uint32_t group = (TCW / 4) * 128u;
                     const uint32_t r = b % group;
                     const int n = (int)(b / group) * 8 + (int)((r % 128u) >> 4);
                     const int k = (int)(r / 128u) * 4 + (int)((r & 15u) >> 2);
-                    const float w = Wf[(int64_t)n * TC_W + k];
+                    const float w = Wf[(int64_t)n * TCW + k];
                     uint32_t hb;
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));
                     const float whi = __uint_as_float(hb & 0xffffe000u);
                     v = hi ? whi : (w - whi);
                 }
-                const bool bhi = lay.wbhi[l] >= 0 && i >= lay.wbhi[l] && i < lay.wbhi[l] + TC_W * TC_W;
-                const bool blo = lay.wblo[l] >= 0 && i >= lay.wblo[l] && i < lay.wblo[l] + TC_W * TC_W;
+                const bool bhi = lay.wbhi[l] >= 0 && i >= lay.wbhi[l] && i < lay.wbhi[l] + TCW * TCW;
+                const bool blo = lay.wblo[l] >= 0 && i >= lay.wblo[l] && i < lay.wblo[l] + TCW * TCW;
                 if (bhi || blo) {
-                    // invert mn32_offset (tg_umma.cuh) of the stored [R = TC_W rows n][cols k] matrix
+                    // invert mn32_offset (tg_umma.cuh) of the stored [R = TCW rows n][cols k] matrix
                     const uint32_t b = (uint32_t)(i - (bhi ? lay.wbhi[l] : lay.wblo[l])) * 4u;
-                    const uint32_t blk = b / (TC_W * 128u), r = b % (TC_W * 128u);
+                    const uint32_t blk = b / (TCW * 128u), r = b % (TCW * 128u);
                     const int n = (int)(r / 128u);
                     const int chunk = (int)((r % 128u) >> 5) ^ (n & 3);
                     const int k = (int)blk * 32 + chunk * 8 + (int)((r & 31u) >> 2);
-                    const float w = Wf[(int64_t)n * TC_W + k];
+                    const float w = Wf[(int64_t)n * TCW + k];
                     uint32_t hb;
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));
                     const float whi = __uint_as_float(hb & 0xffffe000u);

@@ -37,6 +37,7 @@ struct tg_ctx {
     float *packed_tc;  // staged tensor-core operands (hi/lo split, SWIZZLE_128B), device
     size_t packed_tc_cap;
     int math_mode;     // TG_MATH_*
+    int rollout_tc2;   // diagnostics: route width-64 rollouts to the two-threads-per-env kernel too
     // length order of the rollout being updated (tg_order.cu): env indices sorted by episode length,
     // longest first, and the number of live envs per step; device, owned by the ctx
     void *order_buf;
@@ -89,7 +90,8 @@ int tg_pack_weights(tg_ctx *ctx, const tg_mlp_layout &lay, const float *params, 
 TG_HD int tg_round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // ---- tensor-core (tcgen05, 3xTF32) staging ----------------------------------------
-// Eligible policies: >= 2 hidden layers, every hidden width == TC_W (64).  The first
+// Eligible policies: >= 2 hidden layers of equal width W = 64 or 128 (TC_W = 64 is the width the
+// update kernel and the one-thread-per-env rollout kernel are built for).  The first
 // Linear (K = obs dim) and the output Linear (N = act dim <= 4) stay on the FP32 pipe;
 // every hidden->hidden Linear is a [128 x 64] x [64 x 64] UMMA per tile.
 // Staged buffer (floats; the kernel bulk-copies it to a 1024-byte aligned smem base):
@@ -100,6 +102,7 @@ TG_HD int tg_round_up(int x, int m) { return (x + m - 1) / m * m; }
 #define TC_W 64
 struct tg_tc_layout {
     int n_layers, nh, act, O, O4, A;
+    int W;                             // hidden width: 64 or 128
     int64_t flat_w[TG_MAX_LAYERS];     // offsets of each Linear in the flat torch vector
     int64_t w1, whi[TG_MAX_LAYERS], wlo[TG_MAX_LAYERS], bias[TG_MAX_LAYERS], wo, bo;
     // update kernels only: W[out][in] again in the MN-major (SW128_32B) layout, the B operand of

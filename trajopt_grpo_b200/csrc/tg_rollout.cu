@@ -381,6 +381,229 @@ __global__ void __launch_bounds__(128) rollout_tc_kernel(const __grid_constant__
     if (threadIdx.x < 32) tmem_dealloc(tmem, 64);
 }
 
+// ---------------------------------------------------------------------------
+// Tensor-core variant with TWO threads per env (256 threads per 128-env tile) for hidden widths
+// 64 and 128: env e = TMEM lane e is served by warps q and q+4 of lane quadrant q, each owning one
+// half (HW = W/2 columns) of every activation row, so a 128-wide row costs 64 registers per thread.
+// The hidden activation goes to the tensor core as the A operand straight from registers through
+// tensor memory (tcgen05.st, hi/lo split; tcgen05.mma with A in TMEM), the [W x W] weight (hi/lo,
+// core-matrix K-major, staged once by TMA) is the B operand in shared memory, the accumulator comes
+// back with tcgen05.ld.  Both threads of an env integrate its dynamics redundantly (cheap next to
+// the MLP) so that `alive` and the state never have to be exchanged; only the two halves of the
+// output-layer dot product meet in shared memory (fixed order -> deterministic).
+// ---------------------------------------------------------------------------
+template <int KIND, typename R, bool RELU, int W>
+__global__ void __launch_bounds__(256, 1) rollout_tc2_kernel(const __grid_constant__ RolloutTcArgs a) {
+    using E = Env<KIND>;
+    constexpr int S = E::S, A = E::A, HW = W / 2, O4 = (S + 1 + 3) / 4 * 4;
+    constexpr uint32_t TM_D = 0u, TM_AHI = (uint32_t)W, TM_ALO = 2u * (uint32_t)W;
+    constexpr uint32_t TM_COLS = W == 64 ? 256u : 512u;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t wbar, mbar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float muS[2][A][128];
+    if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+    float *Wsm = reinterpret_cast<float *>(smem_raw);
+    stage_weights_tma(Wsm, a.packed, a.lay.total, &wbar);
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar, 1);
+        mbar_fence_init();
+    }
+    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, TM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = umma_idesc_tf32(128, W);
+    const uint32_t w_u = smem_u32(Wsm);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, hf = warp >> 2;       // lane quadrant, column half
+    const int e = q * 32 + lane;                  // env row of this thread = TMEM lane
+    const int c0 = hf * HW;                       // first column of this thread's half
+    const uint32_t my_tm = tmem + ((uint32_t)(q * 32) << 16);
+
+    const int T = a.env.max_steps;
+    const int64_t N = a.N;
+    const int64_t n = (int64_t)blockIdx.x * 128 + e;
+    const bool real_env = n < N;
+    const bool writer = real_env && hf == 0;
+    bool alive = real_env;
+    R s[S];
+    int steps = 0, bal = 0;
+    float ret = 0.0f;
+    if (real_env) {
+        const R *init = reinterpret_cast<const R *>(a.init_state);
+#pragma unroll
+        for (int i = 0; i < S; ++i) s[i] = init[(int64_t)i * N + n];
+    } else {
+#pragma unroll
+        for (int i = 0; i < S; ++i) s[i] = (R)0;
+    }
+    const int nh = a.lay.nh, act_kind = RELU ? TG_ACT_RELU : a.lay.act;
+    const float *w1 = Wsm + a.lay.w1 + (size_t)c0 * O4;
+    uint32_t phase = 0;
+    int t = 0;
+    for (; t < T; ++t) {
+        float x[S];
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            x[i] = alive ? (float)s[i] : 0.0f;
+            if (writer) a.obs[((int64_t)t * S + i) * N + n] = x[i];
+        }
+        // first Linear on the FP32 pipe, this thread's HW neurons: h = act(W1 x + b1)
+        float h[HW];
+#pragma unroll
+        for (int nn = 0; nn < HW; ++nn) {
+            float wrow[O4];
+#pragma unroll
+            for (int c = 0; c < O4; c += 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(w1 + nn * O4 + c);
+                wrow[c] = v.x; wrow[c + 1] = v.y; wrow[c + 2] = v.z; wrow[c + 3] = v.w;
+            }
+            float acc = wrow[S];
+#pragma unroll
+            for (int i = 0; i < S; ++i) acc = fmaf(wrow[i], x[i], acc);
+            h[nn] = act_fwd(acc, act_kind);
+        }
+        // hidden -> hidden Linears on the tensor cores
+        for (int l = 1; l < nh; ++l) {
+#pragma unroll
+            for (int cc = 0; cc < HW; cc += 32) {
+                float hi[32], lo[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    hi[j] = tf32_hi(h[cc + j]);
+                    lo[j] = h[cc + j] - hi[j];
+                }
+                tmem_st32(my_tm + TM_AHI + (uint32_t)(c0 + cc), hi);
+                tmem_st32(my_tm + TM_ALO + (uint32_t)(c0 + cc), lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                tc_fence_after();
+                const uint32_t b_hi = w_u + (uint32_t)a.lay.whi[l] * 4u, b_lo = w_u + (uint32_t)a.lay.wlo[l] * 4u;
+                uint32_t acc = 0;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t acol = tmem + (pass == 2 ? TM_ALO : TM_AHI);
+                    const uint32_t b = pass == 1 ? b_lo : b_hi;
+#pragma unroll 4
+                    for (int k = 0; k < W; k += 8) {
+                        umma_tf32_ts(tmem + TM_D, acol + (uint32_t)k, umma_operand_desc(b, W, false, k), idesc, acc);
+                        acc = 1u;
+                    }
+                }
+                umma_commit(&mbar);
+            }
+            mbar_wait(&mbar, phase);
+            phase ^= 1u;
+            tc_fence_after();
+            const float *bl = Wsm + a.lay.bias[l] + c0;
+#pragma unroll
+            for (int cc = 0; cc < HW; cc += 32) {
+                float z[32];
+                tmem_ld32(my_tm + TM_D + (uint32_t)(c0 + cc), z);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4 *>(bl + cc + j);
+                    h[cc + j] = act_fwd(z[j] + b4.x, act_kind);
+                    h[cc + j + 1] = act_fwd(z[j + 1] + b4.y, act_kind);
+                    h[cc + j + 2] = act_fwd(z[j + 2] + b4.z, act_kind);
+                    h[cc + j + 3] = act_fwd(z[j + 3] + b4.w, act_kind);
+                }
+            }
+            tc_fence_before();      // orders these TMEM reads before the next layer's / step's MMA
+        }
+        // output Linear (A <= 4 neurons): each thread sums its half, the halves meet in shared memory
+        {
+            const float *wo = Wsm + a.lay.wo + c0;
+#pragma unroll
+            for (int j = 0; j < A; ++j) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int c = 0; c < HW; c += 4) {
+                    const float4 v = *reinterpret_cast<const float4 *>(wo + j * W + c);
+                    acc = fmaf(h[c], v.x, acc); acc = fmaf(h[c + 1], v.y, acc);
+                    acc = fmaf(h[c + 2], v.z, acc); acc = fmaf(h[c + 3], v.w, acc);
+                }
+                muS[hf][j][e] = acc;
+            }
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");   // the two warps of this lane quadrant
+        float mu[A];
+        {
+            const float *bo = Wsm + a.lay.bo;
+#pragma unroll
+            for (int j = 0; j < A; ++j) mu[j] = (bo[j] + muS[0][j][e]) + muS[1][j][e];
+        }
+        float act[A], lp = 0.0f, rw = 0.0f;
+        if (alive) {
+            float eps[4];
+            if (a.noise != nullptr) {
+#pragma unroll
+                for (int j = 0; j < A; ++j) eps[j] = a.noise[((int64_t)t * A + j) * N + n];
+            } else {
+                philox_normal4(a.seed, (uint64_t)(a.env_offset + n), (uint32_t)t, eps);
+            }
+            float m2 = 0.0f;
+#pragma unroll
+            for (int j = 0; j < A; ++j) {
+                act[j] = mu[j] + a.sd[j] * eps[j];
+                const float z = (act[j] - mu[j]) / a.sd[j];
+                m2 += z * z;
+            }
+            lp = -0.5f * m2 - a.log_norm;
+            R r;
+            const bool done = E::template step<R>(s, act, a.env, steps, bal, r);
+            rw = (float)r;
+            ret += rw;
+            steps += 1;
+            alive = !done;
+        } else {
+#pragma unroll
+            for (int j = 0; j < A; ++j) act[j] = 0.0f;
+        }
+        if (writer) {
+#pragma unroll
+            for (int j = 0; j < A; ++j) a.act[((int64_t)t * A + j) * N + n] = act[j];
+            a.rew[(int64_t)t * N + n] = rw;
+            if (a.logp) a.logp[(int64_t)t * N + n] = lp;
+        }
+        if (!__syncthreads_or(alive ? 1 : 0)) { ++t; break; }
+    }
+    if (writer) {
+        for (; t < T; ++t) {
+#pragma unroll
+            for (int i = 0; i < S; ++i) a.obs[((int64_t)t * S + i) * N + n] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < A; ++j) a.act[((int64_t)t * A + j) * N + n] = 0.0f;
+            a.rew[(int64_t)t * N + n] = 0.0f;
+            if (a.logp) a.logp[(int64_t)t * N + n] = 0.0f;
+        }
+        a.len[n] = steps;
+        if (a.ret) a.ret[n] = ret;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem, TM_COLS);
+}
+
+template <int KIND, int W>
+static int launch_rollout_tc2(int precision, const RolloutTcArgs &a, cudaStream_t st) {
+    const size_t smem = ((size_t)a.lay.total * 4 + 1023) / 1024 * 1024;
+    const unsigned grid = (unsigned)((a.N + 127) / 128);
+    void (*kern)(const RolloutTcArgs);
+    const bool relu = a.lay.act == TG_ACT_RELU;
+    if (precision == TG_PREC_F64) kern = relu ? rollout_tc2_kernel<KIND, double, true, W> : rollout_tc2_kernel<KIND, double, false, W>;
+    else kern = relu ? rollout_tc2_kernel<KIND, float, true, W> : rollout_tc2_kernel<KIND, float, false, W>;
+    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 256, smem, st>>>(a);
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}
+
 template <int KIND>
 static int launch_rollout_tc(int precision, const RolloutTcArgs &a, cudaStream_t st) {
     const size_t smem = 1024 + ((size_t)a.lay.total * 4 + 1023) / 1024 * 1024 + 2 * 128 * TC_W * 4;
@@ -428,7 +651,7 @@ extern "C" int tg_rollout(tg_ctx *ctx, const tg_env_cfg *env, const tg_mlp_cfg *
     // ---- tensor-core path (3xTF32 tcgen05) for eligible policies
     const bool tc_ok = tg_tc_eligible(mlp);
     TG_REQUIRE(ctx->math_mode != TG_MATH_3XTF32 || tc_ok, TG_ERR_UNSUPPORTED,
-               "TG_MATH_3XTF32 requested but the policy shape is not eligible (>= 2 hidden layers of width %d)", TC_W);
+               "TG_MATH_3XTF32 requested but the policy shape is not eligible (>= 2 hidden layers of equal width 64 or 128)");
     if (tc_ok && ctx->math_mode != TG_MATH_FP32) {
         RolloutTcArgs b;
         memset(&b, 0, sizeof(b));
@@ -447,6 +670,24 @@ extern "C" int tg_rollout(tg_ctx *ctx, const tg_env_cfg *env, const tg_mlp_cfg *
         }
         b.log_norm = (float)lnb;
         b.obs = out_obs; b.act = out_act; b.rew = out_rew; b.logp = out_logp; b.len = out_len; b.ret = out_ret;
+        TG_REQUIRE(((size_t)b.lay.total * 4 + 1023) / 1024 * 1024 + 4096 <= (size_t)ctx->smem_optin, TG_ERR_UNSUPPORTED,
+                   "staged tensor-core weights need %zu B of shared memory", (size_t)b.lay.total * 4);
+        if (b.lay.W == 128 || ctx->rollout_tc2) {
+            if (b.lay.W == 128) {
+                switch (env->kind) {
+                    case TG_ENV_CARTPOLE: return launch_rollout_tc2<TG_ENV_CARTPOLE, 128>(precision, b, st);
+                    case TG_ENV_PENDULUM: return launch_rollout_tc2<TG_ENV_PENDULUM, 128>(precision, b, st);
+                    case TG_ENV_QUADPOLE2D: return launch_rollout_tc2<TG_ENV_QUADPOLE2D, 128>(precision, b, st);
+                    default: return launch_rollout_tc2<TG_ENV_QUADPOLE, 128>(precision, b, st);
+                }
+            }
+            switch (env->kind) {
+                case TG_ENV_CARTPOLE: return launch_rollout_tc2<TG_ENV_CARTPOLE, 64>(precision, b, st);
+                case TG_ENV_PENDULUM: return launch_rollout_tc2<TG_ENV_PENDULUM, 64>(precision, b, st);
+                case TG_ENV_QUADPOLE2D: return launch_rollout_tc2<TG_ENV_QUADPOLE2D, 64>(precision, b, st);
+                default: return launch_rollout_tc2<TG_ENV_QUADPOLE, 64>(precision, b, st);
+            }
+        }
         switch (env->kind) {
             case TG_ENV_CARTPOLE: return launch_rollout_tc<TG_ENV_CARTPOLE>(precision, b, st);
             case TG_ENV_PENDULUM: return launch_rollout_tc<TG_ENV_PENDULUM>(precision, b, st);

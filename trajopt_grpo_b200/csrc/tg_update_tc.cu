@@ -488,7 +488,7 @@ static int launch_update_tc(const UpdTcArgs &a, int grid, size_t smem, cudaStrea
 }
 
 bool tg_update_tc_eligible(const tg_mlp_cfg *mlp) {
-    if (!tg_tc_eligible(mlp) || mlp->n_layers != 3) return false;
+    if (!tg_tc_eligible(mlp) || mlp->n_layers != 3 || mlp->dims[1] != TC_W) return false;
     const int O = mlp->dims[0], A = mlp->dims[3];
     return (O == 3 && A == 1) || (O == 5 && A == 1) || (O == 10 && A == 2) || (O == 20 && A == 4);
 }
