@@ -148,6 +148,38 @@ TG_D void tmem_ld32(uint32_t taddr, float v[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 16-column variants (thread i of the warp <-> row lane base + i, 16 consecutive columns)
+TG_D void tmem_st16(uint32_t taddr, const float v[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+TG_D void tmem_ld16(uint32_t taddr, float v[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <int NC> TG_D void tmem_stN(uint32_t taddr, const float *v) {
+    if (NC == 32) tmem_st32(taddr, v);
+    else tmem_st16(taddr, v);
+}
+template <int NC> TG_D void tmem_ldN(uint32_t taddr, float *v) {
+    if (NC == 32) tmem_ld32(taddr, v);
+    else tmem_ld16(taddr, v);
+}
+
 // Issue the MMAs of one GEMM with the 3xTF32 split (ONE thread).  Each operand is a stored
 // [rows][C] matrix in the core-matrix layout, read K-major or MN-major; K = reduction extent.
 //   a_hi/a_lo/b_hi/b_lo: shared-memory byte addresses (u32) of the hi and lo copies.

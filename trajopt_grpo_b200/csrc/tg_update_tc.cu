@@ -28,6 +28,8 @@
 // (tg_update.cu) sums the copies in a fixed order -> deterministic result in flat torch layout.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "tg_umma.cuh"
 
 struct UpdTcArgs {
@@ -63,6 +65,20 @@ TG_D float colsum32(float *v, int lane) {
     colsum_step<1, 1>(v, lane);
     return v[0];
 }
+// 16 columns per lane: lanes l and l^1 both end up with the sum over the warp's 32 lanes of column l >> 1
+TG_D float colsum16(float *v, int lane) {
+    colsum_step<8, 16>(v, lane);
+    colsum_step<4, 8>(v, lane);
+    colsum_step<2, 4>(v, lane);
+    colsum_step<1, 2>(v, lane);
+    // fixed order (even lane's partial first) so that both lanes hold the bit-identical total
+    const float other = __shfl_xor_sync(0xffffffffu, v[0], 1);
+    return (lane & 1) ? other + v[0] : v[0] + other;
+}
+template <int NC> TG_D float colsumN(float *v, int lane) {
+    if (NC == 32) return colsum32(v, lane);
+    return colsum16(v, lane);
+}
 
 TG_D void split4(const float *v, float4 &hi, float4 &lo) {
     hi.x = tf32_hi(v[0]); hi.y = tf32_hi(v[1]); hi.z = tf32_hi(v[2]); hi.w = tf32_hi(v[3]);
@@ -82,14 +98,16 @@ TG_D void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(
 #define TM_AHI 192u
 #define TM_ALO 256u
 
-template <int O, int A, bool RELU>
-__global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant__ UpdTcArgs a) {
-    constexpr int W = TC_W, HW = TC_W / 2, O4 = (O + 1 + 3) / 4 * 4;
+// NPART threads serve one sample (2 or 4): NPART*4 compute warps + the issuer warp
+template <int O, int A, bool RELU, int NPART>
+__global__ void __launch_bounds__(NPART * 128 + 32, 1) update_tc_kernel(const __grid_constant__ UpdTcArgs a) {
+    constexpr int W = TC_W, HW = TC_W / NPART, O4 = (O + 1 + 3) / 4 * 4;
+    constexpr int NCW = NPART * 4, NT = NPART * 128 + 32;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t wbar, bar_a, bar_w;
     __shared__ uint32_t tmem_slot;
-    __shared__ double sred[4][8];
-    __shared__ float muS[2][A][128];
+    __shared__ double sred[4][NCW];
+    __shared__ float muS[NPART][A][128];
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
     float *Wsm = reinterpret_cast<float *>(smem_raw);
     unsigned char *bufB_hi = smem_raw + ((size_t)a.lay.total * 4 + 1023) / 1024 * 1024;   // H1, MN-major
@@ -112,7 +130,7 @@ __global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = warp & 3, hf = warp >> 2;        // lane quadrant, column half
+    const int q = warp & 3, hf = warp >> 2;        // lane quadrant, column part (0..NPART)
     const int s = q * 32 + lane;                    // sample row of this thread
     const int c0 = hf * HW;                         // first column of this thread's half
     const uint32_t my_tm = tmem + ((uint32_t)(q * 32) << 16);
@@ -124,7 +142,8 @@ __global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant
     const uint32_t wb_hi = w_u + (uint32_t)a.lay.wbhi[1] * 4u, wb_lo = w_u + (uint32_t)a.lay.wblo[1] * 4u;
     const uint32_t B_hi = smem_u32(bufB_hi), B_lo = smem_u32(bufB_lo), C_hi = smem_u32(bufC_hi), C_lo = smem_u32(bufC_lo);
     // this thread's half row in the MN-major SW128_32B layout: mn32_offset(128, s, c0 + 4*i)
-    const uint32_t mn_row = (uint32_t)hf * (128u * 128u) + (uint32_t)s * 128u;
+    const uint32_t mn_row = (uint32_t)(c0 >> 5) * (128u * 128u) + (uint32_t)s * 128u;
+    const int cb = (c0 & 31) >> 3;                  // first 32-byte chunk of this thread's columns inside the line
     const int rs = s & 3;
     const float *w1 = Wsm + a.lay.w1, *b1 = Wsm + a.lay.bias[1], *wo = Wsm + a.lay.wo, *bo = Wsm + a.lay.bo;
     const int act_kind = RELU ? TG_ACT_RELU : a.lay.act;
@@ -162,12 +181,12 @@ __global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant
     };
     uint32_t ph_a = 0, ph_w = 0;
     bool pending_w = false;      // a weight-gradient GEMM is in flight (CTA-uniform)
-    if (warp == 8) {
+    if (warp == NCW) {
         // ===== MMA issuer warp: one elected lane issues every tcgen05.mma of the CTA, so no compute
         // warp is held up by the serial issue loop; it meets the compute warps on named barriers =====
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             if ((tile % NB) * 128 >= a.cnt[tile / NB]) continue;
-            named_sync(BAR_FWD, 288);
+            named_sync(BAR_FWD, NT);
             tc_fence_after();
             if (lane == 0) {
                 uint32_t acc = 0;
@@ -184,7 +203,7 @@ __global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant
                 umma_commit(&bar_a);
             }
             __syncwarp();
-            named_sync(BAR_BWD, 288);
+            named_sync(BAR_BWD, NT);
             tc_fence_after();
             if (lane == 0) {
                 uint32_t acc = 0;
@@ -244,11 +263,11 @@ __global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant
                 hi[4 * i] = h4.x; hi[4 * i + 1] = h4.y; hi[4 * i + 2] = h4.z; hi[4 * i + 3] = h4.w;
                 lo[4 * i] = l4.x; lo[4 * i + 1] = l4.y; lo[4 * i + 2] = l4.z; lo[4 * i + 3] = l4.w;
             }
-            tmem_st32(my_tm + TM_AHI + (uint32_t)c0, hi);
-            tmem_st32(my_tm + TM_ALO + (uint32_t)c0, lo);
+            tmem_stN<HW>(my_tm + TM_AHI + (uint32_t)c0, hi);
+            tmem_stN<HW>(my_tm + TM_ALO + (uint32_t)c0, lo);
             tmem_st_wait();
             tc_fence_before();
-            named_arrive(BAR_FWD, 288);          // -> issuer warp: forward-GEMM operands are in place
+            named_arrive(BAR_FWD, NT);          // -> issuer warp: forward-GEMM operands are in place
             // in the shadow of the forward GEMM: retire the PREVIOUS tile's weight-gradient GEMM (its
             // operands bufB/bufC and its accumulator D_w are then free), then publish H1 MN-major
             if (pending_w) {
@@ -256,7 +275,7 @@ __global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant
                 ph_w ^= 1u;
                 tc_fence_after();
                 float z[HW];
-                tmem_ld32(my_tm + TM_DW + (uint32_t)c0, z);
+                tmem_ldN<HW>(my_tm + TM_DW + (uint32_t)c0, z);
                 if (lane < 16) {
 #pragma unroll
                     for (int j = 0; j < HW; ++j) accS[(c0 + j) * W + q * 16 + lane] += z[j];
@@ -265,7 +284,7 @@ __global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant
             }
 #pragma unroll
             for (int i = 0; i < HW / 4; ++i) {
-                const uint32_t om = mn_row + (uint32_t)(((i >> 1) ^ rs) << 5) + (uint32_t)(i & 1) * 16u;
+                const uint32_t om = mn_row + (uint32_t)((((i >> 1) + cb) ^ rs) << 5) + (uint32_t)(i & 1) * 16u;
                 *reinterpret_cast<float4 *>(bufB_hi + om) = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
                 *reinterpret_cast<float4 *>(bufB_lo + om) = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
             }
@@ -276,7 +295,7 @@ __global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant
         // ---- P3: H2 (this thread's half), output Linear, objective, dZ2
         {
             float z[HW];
-            tmem_ld32(my_tm + TM_DF + (uint32_t)c0, z);
+            tmem_ldN<HW>(my_tm + TM_DF + (uint32_t)c0, z);
 #pragma unroll
             for (int j = 0; j < HW; j += 4) {
                 const float4 b4 = *reinterpret_cast<const float4 *>(b1 + c0 + j);
@@ -298,11 +317,14 @@ __global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant
             muS[hf][j][s] = acc;
         }
         // only the two warps that share this lane quadrant exchange data: named barrier, 64 threads
-        asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "r"(NPART * 32) : "memory");
         float mu[A], dmu[A];
 #pragma unroll
         for (int j = 0; j < A; ++j) {
-            mu[j] = (bo[j] + muS[0][j][s]) + muS[1][j][s];
+            float m = bo[j];
+#pragma unroll
+            for (int p = 0; p < NPART; ++p) m += muS[p][j][s];
+            mu[j] = m;
             dmu[j] = 0.0f;
         }
         if (valid) {
@@ -357,17 +379,17 @@ __global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant
                 split4(dz + 4 * i, h4, l4);
                 hi[4 * i] = h4.x; hi[4 * i + 1] = h4.y; hi[4 * i + 2] = h4.z; hi[4 * i + 3] = h4.w;
                 lo[4 * i] = l4.x; lo[4 * i + 1] = l4.y; lo[4 * i + 2] = l4.z; lo[4 * i + 3] = l4.w;
-                const uint32_t om = mn_row + (uint32_t)(((i >> 1) ^ rs) << 5) + (uint32_t)(i & 1) * 16u;
+                const uint32_t om = mn_row + (uint32_t)((((i >> 1) + cb) ^ rs) << 5) + (uint32_t)(i & 1) * 16u;
                 *reinterpret_cast<float4 *>(bufC_hi + om) = h4;
                 *reinterpret_cast<float4 *>(bufC_lo + om) = l4;
             }
-            tmem_st32(my_tm + TM_AHI + (uint32_t)c0, hi);     // the forward GEMM has consumed H1
-            tmem_st32(my_tm + TM_ALO + (uint32_t)c0, lo);
+            tmem_stN<HW>(my_tm + TM_AHI + (uint32_t)c0, hi);     // the forward GEMM has consumed H1
+            tmem_stN<HW>(my_tm + TM_ALO + (uint32_t)c0, lo);
             tmem_st_wait();
         }
         fence_proxy_async();
         tc_fence_before();
-        named_arrive(BAR_BWD, 288);          // -> issuer warp: dZ2 (TMEM + bufC) and H1 (bufB) are in place
+        named_arrive(BAR_BWD, NT);          // -> issuer warp: dZ2 (TMEM + bufC) and H1 (bufB) are in place
         pending_w = true;
         // in the shadow of the two GEMMs: next tile's inputs, column sums for dWo and db1
         prefetch(tile + gridDim.x);
@@ -376,22 +398,22 @@ __global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant
             float v[HW];
 #pragma unroll
             for (int e = 0; e < HW; ++e) v[e] = dmu[j] * h[e];
-            c_wo[j] += colsum32(v, lane);
+            c_wo[j] += colsumN<HW>(v, lane);
         }
-        c_b1 += colsum32(dz, lane);
+        c_b1 += colsumN<HW>(dz, lane);
         mbar_wait(&bar_a, ph_a);
         ph_a ^= 1u;
         tc_fence_after();
         // ---- P5a: dZ1 = D_b * act'(H1); first-layer gradients
         float d1[HW];
-        tmem_ld32(my_tm + TM_DB + (uint32_t)c0, d1);
+        tmem_ldN<HW>(my_tm + TM_DB + (uint32_t)c0, d1);
         if (RELU) {
 #pragma unroll
             for (int j = 0; j < HW; ++j) d1[j] = ((m1 >> j) & 1u) ? d1[j] : 0.0f;
         } else {
 #pragma unroll
             for (int i = 0; i < HW / 4; ++i) {
-                const uint32_t om = mn_row + (uint32_t)(((i >> 1) ^ rs) << 5) + (uint32_t)(i & 1) * 16u;
+                const uint32_t om = mn_row + (uint32_t)((((i >> 1) + cb) ^ rs) << 5) + (uint32_t)(i & 1) * 16u;
                 const float4 vh = *reinterpret_cast<const float4 *>(bufB_hi + om);
                 const float4 vl = *reinterpret_cast<const float4 *>(bufB_lo + om);
                 d1[4 * i] *= act_bwd_from_out(vh.x + vl.x, act_kind);
@@ -405,9 +427,9 @@ __global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant
             float v[HW];
 #pragma unroll
             for (int e = 0; e < HW; ++e) v[e] = d1[e] * x[o];
-            c_w0[o] += colsum32(v, lane);
+            c_w0[o] += colsumN<HW>(v, lane);
         }
-        c_b0 += colsum32(d1, lane);
+        c_b0 += colsumN<HW>(d1, lane);
         // P5b (D_w -> accS) is deferred into the next tile's forward-GEMM shadow
     }
     // ---- retire the last weight-gradient GEMM (row r of the M = 64 accumulator: lane 32*(r/16) + r%16)
@@ -415,7 +437,7 @@ __global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant
         mbar_wait(&bar_w, ph_w);
         tc_fence_after();
         float z[HW];
-        tmem_ld32(my_tm + TM_DW + (uint32_t)c0, z);
+        tmem_ldN<HW>(my_tm + TM_DW + (uint32_t)c0, z);
         if (lane < 16) {
 #pragma unroll
             for (int j = 0; j < HW; ++j) accS[(c0 + j) * W + q * 16 + lane] += z[j];
@@ -432,8 +454,8 @@ __global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant
     }
     // column partials of the four lane quadrants, added in a fixed order
     for (int qs = 0; qs < 4; ++qs) {
-        if (warp < 8 && q == qs) {
-            const int col = c0 + lane;
+        if (warp < NCW && q == qs && (HW == 32 || (lane & 1) == 0)) {
+            const int col = c0 + (HW == 32 ? lane : (lane >> 1));
             gp[f1 + (int64_t)W * W + col] += c_b1;                              // b1
             gp[f0 + (int64_t)W * O + col] += c_b0;                              // b0
 #pragma unroll
@@ -449,12 +471,12 @@ __global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], off);
-            if (lane == 0 && warp < 8) sred[k][warp] = v[k];
+            if (lane == 0 && warp < NCW) sred[k][warp] = v[k];
         }
         __syncthreads();
         if (threadIdx.x < 4 && a.spart) {
             double t = 0.0;
-            for (int w = 0; w < 8; ++w) t += sred[threadIdx.x][w];
+            for (int w = 0; w < NCW; ++w) t += sred[threadIdx.x][w];
             a.spart[(int64_t)blockIdx.x * 4 + threadIdx.x] = t;
         }
         __syncthreads();
@@ -462,11 +484,11 @@ __global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant
         for (int j = 0; j < A; ++j) {
             float t = c_bo[j];
             for (int off = 16; off > 0; off >>= 1) t += __shfl_down_sync(0xffffffffu, t, off);
-            if (lane == 0 && warp < 8) sred[0][warp] = (double)t;
+            if (lane == 0 && warp < NCW) sred[0][warp] = (double)t;
             __syncthreads();
             if (threadIdx.x == 0) {
                 float tot = 0.0f;
-                for (int w = 0; w < 8; ++w) tot += (float)sred[0][w];
+                for (int w = 0; w < NCW; ++w) tot += (float)sred[0][w];
                 gp[f2 + (int64_t)A * W + j] = tot;
             }
             __syncthreads();
@@ -479,10 +501,17 @@ __global__ void __launch_bounds__(288, 1) update_tc_kernel(const __grid_constant
 
 template <int O, int A>
 static int launch_update_tc(const UpdTcArgs &a, int grid, size_t smem, cudaStream_t st) {
-    void (*kern)(const UpdTcArgs) =
-        a.lay.act == TG_ACT_RELU ? update_tc_kernel<O, A, true> : update_tc_kernel<O, A, false>;
+    static const int nparts = [] {
+        // 2 threads per sample is the default; 4 (TG_UPDATE_TC_PARTS=4) measured the same 4.35-4.39 ms on
+        // Pendulum: the kernel is bound by its instruction count and phase chain, not by warp parallelism
+        const char *e = getenv("TG_UPDATE_TC_PARTS");
+        return (e && e[0] == '4') ? 4 : 2;
+    }();
+    void (*kern)(const UpdTcArgs);
+    if (nparts == 2) kern = a.lay.act == TG_ACT_RELU ? update_tc_kernel<O, A, true, 2> : update_tc_kernel<O, A, false, 2>;
+    else kern = a.lay.act == TG_ACT_RELU ? update_tc_kernel<O, A, true, 4> : update_tc_kernel<O, A, false, 4>;
     TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 288, smem, st>>>(a);
+    kern<<<grid, nparts * 128 + 32, smem, st>>>(a);
     TG_CUDA(cudaGetLastError());
     return TG_OK;
 }
