@@ -211,6 +211,18 @@ int tg_advantage(tg_ctx *ctx, int mode, int64_t G, int E, int T, double gamma, d
                  const float *rew, const int32_t *len, const float *values,
                  float *out_adv, float *out_rtg, void *workspace, void *stream);
 
+/* The two halves of tg_advantage's PPO modes, for a rollout sharded over several GPUs (whole
+ * groups per GPU): PPO.learn z-scores advantages and returns over EVERY valid step of the rollout
+ * (algorithms/ppo.py:138-139), so a rank computes its raw values and the five additive sums
+ *   out_sums[5] (device, float64) = (sum adv, sum adv^2, sum ret, sum ret^2, n valid),
+ * the host allreduces them (SUM) and every rank normalises with the global sums.
+ * tg_advantage(mode = PPO_*) is exactly raw followed by normalize with the local sums. */
+int tg_advantage_ppo_raw(tg_ctx *ctx, int mode, int64_t G, int E, int T, double gamma, double lam,
+                         const float *rew, const int32_t *len, const float *values,
+                         float *out_adv, float *out_rtg, double *out_sums, void *workspace, void *stream);
+int tg_advantage_ppo_normalize(tg_ctx *ctx, int64_t N, int T, const int32_t *len, const double *sums,
+                               float *adv, float *rtg, void *stream);
+
 /* ---- K3: clipped-surrogate objective + flat gradient ------------------------
  * Replaces one iteration of the update loop of GRPO.learn
  * (algorithms/grpo.py:106-145: J = (1/G) sum_g sum_valid min(rho A, clamp(rho) A),

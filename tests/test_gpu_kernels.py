@@ -370,3 +370,59 @@ def test_large_rollout_properties(E):
     assert torch.equal(c["rew"], a["rew"][:, half:]) and torch.equal(c["len"], a["len"][half:])
     adv_h, _ = E.advantage(0, G // 2, Eps, T, 0.99, 0.0, c["rew"], c["len"])
     assert torch.equal(adv_h, adv[:, half:])
+
+
+# ----------------------------------------------------------------------------
+# PPO over a sharded rollout: raw advantages + additive sums per shard, "allreduce" = sum of the
+# shards' sums, normalise with the global statistics, gradients scaled by the global step count --
+# the two ranks of a world-size-2 run emulated one after the other on one GPU
+# ----------------------------------------------------------------------------
+@pytest.mark.parametrize("mode_name", ["mc", "gae"])
+def test_ppo_sharded_equals_single_rollout(E, mode_name):
+    from trajopt_grpo_b200 import _lib as L
+    rng = np.random.default_rng(11)
+    G, Eg, T, O, A = 6, 8, 20, 10, 2
+    N = G * Eg
+    a_dims, c_dims = [O, 32, 32, A], [O, 32, 32, 1]
+    mk = lambda dims: dev(_flat([(rng.standard_normal((dims[i + 1], dims[i])) / np.sqrt(dims[i])).astype(np.float32)
+                                 for i in range(3)], [(0.1 * rng.standard_normal(dims[i + 1])).astype(np.float32) for i in range(3)]))
+    a_flat, c_flat = mk(a_dims), mk(c_dims)
+    lens = rng.integers(1, T + 1, N).astype(np.int32)
+    mask = (np.arange(T)[:, None] < lens[None, :])
+    obs = (rng.standard_normal((T, O, N)) * mask[:, None, :]).astype(np.float32)
+    act = (rng.standard_normal((T, A, N)) * mask[:, None, :]).astype(np.float32)
+    rew = (rng.standard_normal((T, N)) * mask).astype(np.float32)
+    mode = L.ADV_PPO_MC if mode_name == "mc" else L.ADV_PPO_GAE
+    cov, eps, c1, kl = [0.4, 0.4], 0.2, 0.5, 0.5
+
+    def run(sl, sums_global=None, n_global=None):
+        o, a, r, ln = (dev(np.ascontiguousarray(x[..., sl])) for x in (obs, act, rew, lens))
+        g_loc = (sl.stop - sl.start) // Eg
+        vals, _ = E.policy_forward_traj(c_dims, "ReLU", c_flat, o, None, None, ln, want_mu=True, want_logp=False)
+        adv, rtg, sums = E.advantage_ppo_raw(mode, g_loc, Eg, T, 0.99, 0.95, r, ln, vals.view(T, -1))
+        if sums_global is None:
+            return sums
+        E.advantage_ppo_normalize(T, ln, sums_global, adv, rtg)
+        _, olp = E.policy_forward_traj(a_dims, "ReLU", a_flat, o, cov, a, ln)
+        ga, _ = E.policy_grad(a_dims, "ReLU", a_flat, cov, o, a, adv, olp, ln, eps, -1.0 / n_global, kl / n_global)
+        gc, _ = E.value_grad(c_dims, "ReLU", c_flat, o, rtg, ln, c1 / n_global)
+        return torch.cat([ga, gc]).double()
+
+    full = slice(0, N)
+    s_full = run(full)
+    n = int(round(float(s_full[4])))
+    assert n == int(lens.sum())
+    g_full = run(full, s_full, n)
+    shards = [slice(0, N // 2), slice(N // 2, N)]
+    s_sum = sum(run(sl) for sl in shards)
+    np.testing.assert_allclose(s_sum.cpu().numpy(), s_full.cpu().numpy(), rtol=1e-12, atol=1e-9)
+    g_sum = sum(run(sl, s_sum, n) for sl in shards)
+    err = (g_sum - g_full).abs().max().item()
+    assert err <= 2e-5 * g_full.abs().max().item() + 1e-7, err
+    # and the one-call form equals raw + normalize with the local sums
+    o, r, ln = dev(obs), dev(rew), dev(lens)
+    vals, _ = E.policy_forward_traj(c_dims, "ReLU", c_flat, o, None, None, ln, want_mu=True, want_logp=False)
+    adv1, rtg1 = E.advantage(mode, G, Eg, T, 0.99, 0.95, r, ln, vals.view(T, N))
+    adv2, rtg2, s2 = E.advantage_ppo_raw(mode, G, Eg, T, 0.99, 0.95, r, ln, vals.view(T, N))
+    E.advantage_ppo_normalize(T, ln, s2, adv2, rtg2)
+    assert torch.equal(adv1, adv2) and torch.equal(rtg1, rtg2)

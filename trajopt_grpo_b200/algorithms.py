@@ -217,8 +217,7 @@ class PPO(Algorithm):
         if self.batch_size is not None:
             raise L.EngineError("minibatched PPO (batch_size != None) is not built yet: the fused update is "
                                 "full-batch, as quadpole2d_pipeline_ppo.py configures it")
-        if _dist_world() > 1:
-            raise L.EngineError("multi-GPU PPO needs a global-statistics allreduce that is not built yet")
+        world = _dist_world()
         r = _rollout_of(buffer)
         pol = self.policy
         flat = pol.flat_parameters()
@@ -230,10 +229,17 @@ class PPO(Algorithm):
                                                want_logp=False)
         values = values.view(r.T, r.N)
         mode = L.ADV_PPO_MC if self.monte_carlo else L.ADV_PPO_GAE
-        adv, rtg = engine.advantage(mode, r.G, r.E, r.T, self.gamma, self.lam, r.rew, r.len, values)   # :100-139
+        # ppo.py:100-139.  The z-scores are over every valid step of the WHOLE rollout: a rank that holds
+        # a shard (whole groups per GPU) computes its raw values and five additive sums, the sums are
+        # allreduced (40 bytes), and every rank normalises with the global statistics.
+        adv, rtg, sums = engine.advantage_ppo_raw(mode, r.G, r.E, r.T, self.gamma, self.lam, r.rew, r.len, values)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(sums)
+        engine.advantage_ppo_normalize(r.T, r.len, sums, adv, rtg)
         # ppo.py:142-143: old log-prob from self.policy at the start of learn()
         _, old_logp = engine.policy_forward_traj(a_dims, act_name, a_flat, r.obs, cov, r.act, r.len)
-        n_valid = int(r.len.sum().item())
+        n_valid = int(round(float(sums[4].item())))                 # global valid-step count (the .mean()s)
         grad = torch.empty_like(flat)
         for _ in range(self.updates_per_iter):                      # ppo.py:147 (full batch; the order of a
             # permutation does not change a mean)
@@ -241,6 +247,9 @@ class PPO(Algorithm):
                                           self.epsilon, -1.0 / n_valid, self.kl_coeff / n_valid,
                                           out_grad=grad[:na])        # :160-166, 175-176
             engine.value_grad(c_dims, act_name, c_flat, r.obs, rtg, r.len, self.c1 / n_valid, out_grad=grad[na:])
+            if world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(grad)                                # actor + critic gradients in one message
             self._flat_opt.step(flat, grad)                         # :181-183 (entropy term has zero gradient)
             pol.bump_param_epoch()
             self.last_stats = stats

@@ -144,29 +144,31 @@ adv_ppo_scan_kernel(int64_t N, int T, int gae, float gamma, float gamlam, const 
     }
 }
 
-__global__ void adv_ppo_stats_kernel(int nblocks, const double *__restrict__ partial, float *__restrict__ stats) {
-    // single thread, fixed order: nblocks is N/128, a few thousand adds
+__global__ void adv_ppo_sums_kernel(int nblocks, const double *__restrict__ partial, double *__restrict__ sums) {
+    // single thread, fixed order: nblocks is N/128, a few thousand adds.
+    // sums = (sum adv, sum adv^2, sum ret, sum ret^2, n valid): additive over ranks, so a sharded run
+    // allreduces these five doubles before normalising
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         double s[5] = {0, 0, 0, 0, 0};
         for (int b = 0; b < nblocks; ++b)
             for (int k = 0; k < 5; ++k) s[k] += partial[(int64_t)b * 5 + k];
-        const double n = s[4];
-        const double ma = s[0] / n, mr = s[2] / n;
-        const double va = (s[1] - s[0] * ma) / (n - 1.0), vr = (s[3] - s[2] * mr) / (n - 1.0);
-        stats[0] = (float)ma;
-        stats[1] = (float)sqrt(va > 0.0 || va != va ? va : 0.0);
-        stats[2] = (float)mr;
-        stats[3] = (float)sqrt(vr > 0.0 || vr != vr ? vr : 0.0);
+        for (int k = 0; k < 5; ++k) sums[k] = s[k];
     }
 }
 
 __global__ void __launch_bounds__(ADV_THREADS)
-adv_ppo_norm_kernel(int64_t N, int T, const int32_t *__restrict__ len, const float *__restrict__ stats,
+adv_ppo_norm_kernel(int64_t N, int T, const int32_t *__restrict__ len, const double *__restrict__ sums,
                     float *__restrict__ adv, float *__restrict__ rtg) {
     const int64_t n = (int64_t)blockIdx.x * ADV_THREADS + threadIdx.x;
     if (n >= N) return;
     const int L = len[n];
-    const float ma = stats[0], sa = __fadd_rn(stats[1], 1e-8f), mr = stats[2], sr = __fadd_rn(stats[3], 1e-8f);
+    // mean / unbiased std in double from the five sums, then rounded to fp32 like torch's results
+    const double cnt = sums[4];
+    const double dma = sums[0] / cnt, dmr = sums[2] / cnt;
+    const double va = (sums[1] - sums[0] * dma) / (cnt - 1.0), vr = (sums[3] - sums[2] * dmr) / (cnt - 1.0);
+    const float ma = (float)dma, mr = (float)dmr;
+    const float sa = __fadd_rn((float)sqrt(va > 0.0 || va != va ? va : 0.0), 1e-8f);
+    const float sr = __fadd_rn((float)sqrt(vr > 0.0 || vr != vr ? vr : 0.0), 1e-8f);
     for (int t = 0; t < L; ++t) {
         const int64_t i = (int64_t)t * N + n;
         adv[i] = __fdiv_rn(__fsub_rn(adv[i], ma), sa);    // ppo.py:138
@@ -177,7 +179,7 @@ adv_ppo_norm_kernel(int64_t N, int T, const int32_t *__restrict__ len, const flo
 extern "C" int64_t tg_advantage_workspace_bytes(int64_t N, int G) {
     (void)G;
     const int64_t blocks = (N + ADV_THREADS - 1) / ADV_THREADS;
-    return blocks * 5 * (int64_t)sizeof(double) + 64;
+    return blocks * 5 * (int64_t)sizeof(double) + 5 * (int64_t)sizeof(double) + 64;
 }
 
 extern "C" int tg_advantage(tg_ctx *ctx, int mode, int64_t G, int E, int T, double gamma, double lam, const float *rew,
@@ -202,13 +204,40 @@ extern "C" int tg_advantage(tg_ctx *ctx, int mode, int64_t G, int E, int T, doub
     TG_REQUIRE(mode == TG_ADV_PPO_MC || mode == TG_ADV_PPO_GAE, TG_ERR_ARG, "unknown advantage mode %d", mode);
     TG_REQUIRE(values && out_rtg && workspace, TG_ERR_ARG, "PPO advantages need values, out_rtg and workspace");
     const unsigned grid = (unsigned)((N + ADV_THREADS - 1) / ADV_THREADS);
+    double *sums = reinterpret_cast<double *>(workspace) + (size_t)grid * 5;
+    int rc = tg_advantage_ppo_raw(ctx, mode, G, E, T, gamma, lam, rew, len, values, out_adv, out_rtg, sums, workspace,
+                                  stream);
+    if (rc) return rc;
+    return tg_advantage_ppo_normalize(ctx, N, T, len, sums, out_adv, out_rtg, stream);
+}
+
+extern "C" int tg_advantage_ppo_raw(tg_ctx *ctx, int mode, int64_t G, int E, int T, double gamma, double lam,
+                                    const float *rew, const int32_t *len, const float *values, float *out_adv,
+                                    float *out_rtg, double *out_sums, void *workspace, void *stream) {
+    TG_REQUIRE(ctx && rew && len && values && out_adv && out_rtg && out_sums && workspace, TG_ERR_ARG,
+               "tg_advantage_ppo_raw: null argument");
+    TG_REQUIRE(mode == TG_ADV_PPO_MC || mode == TG_ADV_PPO_GAE, TG_ERR_ARG, "unknown PPO advantage mode %d", mode);
+    TG_REQUIRE(G > 0 && E > 0 && T > 0, TG_ERR_SHAPE, "tg_advantage_ppo_raw: G, E, T must be positive");
+    TG_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t N = G * (int64_t)E;
+    const unsigned grid = (unsigned)((N + ADV_THREADS - 1) / ADV_THREADS);
     double *partial = reinterpret_cast<double *>(workspace);
-    float *stats = reinterpret_cast<float *>(partial + (size_t)grid * 5);
     adv_ppo_scan_kernel<<<grid, ADV_THREADS, 0, st>>>(N, T, mode == TG_ADV_PPO_GAE, (float)gamma,
                                                        (float)(gamma * lam), rew, len, values,
                                                        out_adv, out_rtg, partial);
-    adv_ppo_stats_kernel<<<1, 32, 0, st>>>((int)grid, partial, stats);
-    adv_ppo_norm_kernel<<<grid, ADV_THREADS, 0, st>>>(N, T, len, stats, out_adv, out_rtg);
+    adv_ppo_sums_kernel<<<1, 32, 0, st>>>((int)grid, partial, out_sums);
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}
+
+extern "C" int tg_advantage_ppo_normalize(tg_ctx *ctx, int64_t N, int T, const int32_t *len, const double *sums,
+                                          float *adv, float *rtg, void *stream) {
+    TG_REQUIRE(ctx && len && sums && adv && rtg, TG_ERR_ARG, "tg_advantage_ppo_normalize: null argument");
+    TG_REQUIRE(N > 0 && T > 0, TG_ERR_SHAPE, "tg_advantage_ppo_normalize: N, T must be positive");
+    TG_CUDA(cudaSetDevice(ctx->device));
+    const unsigned grid = (unsigned)((N + ADV_THREADS - 1) / ADV_THREADS);
+    adv_ppo_norm_kernel<<<grid, ADV_THREADS, 0, (cudaStream_t)stream>>>(N, T, len, sums, adv, rtg);
     TG_CUDA(cudaGetLastError());
     return TG_OK;
 }

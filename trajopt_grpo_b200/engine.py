@@ -226,6 +226,42 @@ def advantage(mode, G, E, T, gamma, lam, rew, length, values=None, want_rtg=Fals
     return adv, rtg
 
 
+def advantage_ppo_raw(mode, G, E, T, gamma, lam, rew, length, values):
+    """tg_advantage_ppo_raw -> (raw adv [T,N], raw returns [T,N], sums [5] float64 =
+    (sum adv, sum adv^2, sum ret, sum ret^2, n valid)).  The sums are additive over ranks."""
+    lib = L.load()
+    N = G * E
+    _need(rew, torch.float32, "rew", (T, N))
+    _need(length, torch.int32, "len", (N,))
+    _need(values, torch.float32, "values", (T, N))
+    dev = rew.device
+    adv, rtg = torch.empty_like(rew), torch.empty_like(rew)
+    sums = torch.empty((5,), dtype=torch.float64, device=dev)
+    ws = _workspace("adv", lib.tg_advantage_workspace_bytes(N, G), dev)
+    with torch.cuda.device(dev):
+        rc = lib.tg_advantage_ppo_raw(L.ctx(dev), mode, G, E, T, float(gamma), float(lam), L.ptr(rew), L.ptr(length),
+                                      L.ptr(values), L.ptr(adv), L.ptr(rtg), L.ptr(sums), L.ptr(ws), L.stream_ptr())
+    L.check(rc, "tg_advantage_ppo_raw")
+    _count(2)
+    return adv, rtg, sums
+
+
+def advantage_ppo_normalize(T, length, sums, adv, rtg):
+    """tg_advantage_ppo_normalize: z-score adv and rtg in place with the (global) sums."""
+    lib = L.load()
+    N = length.shape[0]
+    _need(adv, torch.float32, "adv", (T, N))
+    _need(rtg, torch.float32, "rtg", (T, N))
+    _need(sums, torch.float64, "sums", (5,))
+    dev = adv.device
+    with torch.cuda.device(dev):
+        rc = lib.tg_advantage_ppo_normalize(L.ctx(dev), N, T, L.ptr(length), L.ptr(sums), L.ptr(adv), L.ptr(rtg),
+                                            L.stream_ptr())
+    L.check(rc, "tg_advantage_ppo_normalize")
+    _count(1)
+    return adv, rtg
+
+
 def policy_grad(dims, activation, params, cov_diag, obs, act, adv, old_logp, length, eps_clip, scale, kl_scale=0.0,
                 out_grad=None):
     """tg_policy_grad -> (grad [n_params], stats [4] = objective, n_valid, sum ratio, n_clipped)."""
