@@ -223,6 +223,16 @@ int tg_advantage_ppo_raw(tg_ctx *ctx, int mode, int64_t G, int E, int T, double 
 int tg_advantage_ppo_normalize(tg_ctx *ctx, int64_t N, int T, const int32_t *len, const double *sums,
                                float *adv, float *rtg, void *stream);
 
+/* ---- trajectory export ---------------------------------------------------------
+ * Replaces the host loop of Rollout_Buffer.save_trajectory (buffers/rollout_buffer.py:72-102):
+ * compacts the valid steps of a rollout into a dense table on the device.
+ *   obs [T][O][N], act [T][A][N], len [N]; row0 [N] int64 = exclusive prefix sum of len
+ *   -> out_episode_id [n_valid] int32 (= env index n = worker*E + episode, rollout_buffer.py:88),
+ *      out_rows [n_valid][O + A] fp32 (observation_0.., action_0..), row row0[n] + t = step t of episode n */
+int tg_export_trajectory(tg_ctx *ctx, int64_t N, int T, int O, int A, const float *obs, const float *act,
+                         const int32_t *len, const int64_t *row0, int32_t *out_episode_id, float *out_rows,
+                         void *stream);
+
 /* ---- K3: clipped-surrogate objective + flat gradient ------------------------
  * Replaces one iteration of the update loop of GRPO.learn
  * (algorithms/grpo.py:106-145: J = (1/G) sum_g sum_valid min(rho A, clamp(rho) A),

@@ -13,6 +13,7 @@ import os
 import numpy as np
 import torch
 
+from . import _lib as L
 from .rollout import DeviceRollout
 
 
@@ -90,20 +91,23 @@ class Rollout_Buffer(Buffer):
         self.avg_reward.append(rew.sum(2).mean().detach().cpu().numpy())
 
     def save_trajectory(self, path: str):
-        """rollout_buffer.py:72-102: CSV of (episode_id, observation_i..., action_i...) for valid steps."""
+        """rollout_buffer.py:72-102: CSV of (episode_id, observation_i..., action_i...) for valid steps.
+        The valid rows are compacted on the device (tg_export_trajectory) and copied to the host
+        once through pinned memory; the reference's float64 table is reproduced for the CSV."""
         import pandas as pd
-        obs = self.group_observations.detach().cpu().numpy()
-        act = self.group_actions.detach().cpu().numpy()
-        ln = self.group_lengths.detach().cpu().numpy().astype(int)
-        rows_o, rows_a, ids = [], [], []
-        for i in range(ln.shape[0]):
-            for j in range(ln.shape[1]):
-                rows_o.append(obs[i, j, :ln[i, j]])
-                rows_a.append(act[i, j, :ln[i, j]])
-                ids.extend([j + i * ln.shape[1]] * ln[i, j])
-        header = ["episode_id"] + [f"observation_{i}" for i in range(obs.shape[3])] + \
-                 [f"action_{i}" for i in range(act.shape[3])]
-        data = np.hstack([np.array(ids).reshape(-1, 1), np.vstack(rows_o), np.vstack(rows_a)])
+        from . import engine
+        r = self.device_rollout
+        if r is None:
+            raise L.EngineError("buffer holds no rollout: call sample() or store(...) first")
+        ids_d, rows_d = engine.export_trajectory(r.obs, r.act, r.len)
+        ids = torch.empty(ids_d.shape, dtype=ids_d.dtype).pin_memory()
+        rows = torch.empty(rows_d.shape, dtype=rows_d.dtype).pin_memory()
+        ids.copy_(ids_d, non_blocking=True)
+        rows.copy_(rows_d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        O, A = r.obs.shape[1], r.act.shape[1]
+        header = ["episode_id"] + [f"observation_{i}" for i in range(O)] + [f"action_{i}" for i in range(A)]
+        data = np.hstack([ids.numpy().reshape(-1, 1).astype(np.float64), rows.numpy().astype(np.float64)])
         df = pd.DataFrame(data, columns=header)
         df["episode_id"] = df["episode_id"].astype(int)
         df.to_csv(os.path.join(path, "trajectory.csv"), index=False)

@@ -319,3 +319,27 @@ def adam_step(params, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.99
                               L.stream_ptr())
     L.check(rc, "tg_adam_step")
     _count(1)
+
+
+def export_trajectory(obs, act, length):
+    """tg_export_trajectory: obs [T,O,N], act [T,A,N], len [N] -> (episode_id [n_valid] i32,
+    rows [n_valid, O+A] f32) with the valid steps of episode n in rows row0[n] .. row0[n]+len[n]."""
+    lib = L.load()
+    _need(obs, torch.float32, "obs")
+    T, O, N = obs.shape
+    A = act.shape[1]
+    _need(act, torch.float32, "act", (T, A, N))
+    _need(length, torch.int32, "len", (N,))
+    dev = obs.device
+    csum = torch.cumsum(length.to(torch.int64), 0)
+    row0 = (csum - length).contiguous()
+    n_valid = int(csum[-1].item())
+    ids = torch.empty((n_valid,), dtype=torch.int32, device=dev)
+    rows = torch.empty((n_valid, O + A), dtype=torch.float32, device=dev)
+    if n_valid > 0:
+        with torch.cuda.device(dev):
+            rc = lib.tg_export_trajectory(L.ctx(dev), N, T, O, A, L.ptr(obs), L.ptr(act), L.ptr(length), L.ptr(row0),
+                                          L.ptr(ids), L.ptr(rows), L.stream_ptr())
+        L.check(rc, "tg_export_trajectory")
+        _count(1)
+    return ids, rows
