@@ -175,6 +175,12 @@ def test_rollout_manager_and_buffer_protocol(tg, tmp_path):
     i, ep = 1, 2
     n = int(buf.group_lengths[i, ep])
     assert buf.group_observations[i, ep, n - 1].shape == (3,)
+    # the render feed: only the first k episodes of the first 4 groups travel to the host
+    hs = buf.host_slice(4, 5)
+    assert hs["observations"].shape == (4, 5, 50, 3) and hs["lengths"].shape == (4, 5)
+    np.testing.assert_array_equal(hs["observations"], buf.group_observations[:4, :5].cpu().numpy())
+    np.testing.assert_array_equal(hs["actions"], buf.group_actions[:4, :5].cpu().numpy())
+    np.testing.assert_array_equal(hs["lengths"], buf.group_lengths[:4, :5].cpu().numpy().astype(int))
     # one training epoch through the reference's two calls (pipelines/pipeline.py:163-164)
     opt = torch.optim.Adam(pol.parameters(), lr=5e-4)
     algo = tg.GRPO(0.2, 0.01, 0.99, pol, opt, None, updates_per_iter=2)

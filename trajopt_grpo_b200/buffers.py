@@ -112,6 +112,22 @@ class Rollout_Buffer(Buffer):
         df["episode_id"] = df["episode_id"].astype(int)
         df.to_csv(os.path.join(path, "trajectory.csv"), index=False)
 
+    def host_slice(self, num_groups: int = 4, num_episodes: int = 5):
+        """The Dashboard / Publisher feed (visualize/visualizer.py:105-142, publish/publisher.py:38-64 draw
+        the first `max_episodes_per_render` episodes of the first 4 groups): copies ONLY that slice to the
+        host -- [g, e, T, .] numpy arrays plus integer lengths -- so rendering never moves the full trajectory."""
+        r = self.device_rollout
+        if r is None:
+            raise L.EngineError("buffer holds no rollout: call sample() or store(...) first")
+        g, e = min(num_groups, r.G), min(num_episodes, r.E)
+        idx = (torch.arange(g, device=r.obs.device)[:, None] * r.E + torch.arange(e, device=r.obs.device)[None, :]).reshape(-1)
+        obs = r.obs.index_select(2, idx).permute(2, 0, 1).reshape(g, e, r.T, -1)
+        act = r.act.index_select(2, idx).permute(2, 0, 1).reshape(g, e, r.T, -1)
+        rew = r.rew.index_select(1, idx).t().reshape(g, e, r.T)
+        ln = r.len.index_select(0, idx).reshape(g, e)
+        return {"observations": obs.cpu().numpy(), "actions": act.cpu().numpy(), "rewards": rew.cpu().numpy(),
+                "lengths": ln.cpu().numpy().astype(int)}
+
     def metadata(self):
         return {"avg_reward": float(self.avg_reward[-1]) if len(self.avg_reward) > 0 else None}
 

@@ -6,21 +6,24 @@
 // 64-wide activation row -- this halves the per-thread register/ALU load of the epilogues
 // and gives the scheduler 8 warps to overlap with the tensor-core round trips.
 //
-// Per tile (all GEMMs are 3xTF32 tcgen05.mma, fp32 accumulation in TMEM):
-//   P1  FP32 pipe: H1 = act(W0 x + b0); each thread writes its half row, hi/lo split, into
-//       tensor memory (A operand of the forward GEMM, tcgen05.st) and MN-major into bufB
-//       (B operand of the weight-gradient GEMM, reduction over samples)
+// Per tile i (all GEMMs are 3xTF32 tcgen05.mma, fp32 accumulation in TMEM), software-pipelined so that
+// the compute warps never wait for the backward GEMM at the end of a tile:
+//   P1  FP32 pipe: H1 = act(W0 x + b0); each thread writes its part of the row, hi/lo split, into
+//       tensor memory (A operand buffer i%2, tcgen05.st)
 //   MMA D_f[128x64] = H1 . W1^T                         (A from TMEM, B = W1 K-major in smem)
-//   P3  tcgen05.ld -> H2 = act(D_f + b1); output Linear (half dot products exchanged through
+//       in its shadow: finish tile i-1 -- tcgen05.ld D_b, dZ1 = D_b * act'(H1), butterfly column sums
+//       for db0 / dW0 -- then publish H1 MN-major into bufB (B operand of the weight-gradient GEMM)
+//   P3  tcgen05.ld -> H2 = act(D_f + b1); output Linear (partial dot products exchanged through
 //       shared memory), log-prob, ratio, clipped surrogate, d/dmu;
 //       dZ2 = (Wo^T dmu) * act'(H2) -> tensor memory (A operand) and MN-major into bufC
 //   MMA D_b[128x64] = dZ2 . W1                          (A from TMEM, B = W1 MN-major)
-//   MMA D_w[64x64]  = dZ2^T . H1                        (A = bufC, B = bufB, both MN-major,
-//       reduction over the 128 samples) -- issued back to back with D_b, separate barriers
+//   MMA D_w[64x64] += dZ2^T . H1                        (A = bufC, B = bufB, both MN-major, reduction
+//       over the 128 samples; the accumulator stays in tensor memory for ALL tiles of the CTA and
+//       is read once at the end: M = 64, row r in lane 32*(r/16) + r%16)
 //       meanwhile: butterfly column sums for dWo and db1, prefetch of the next tile's inputs
-//   P5a tcgen05.ld D_b -> dZ1 = D_b * act'(H1); butterfly column sums for db0, dW0
-//   P5b tcgen05.ld D_w (M = 64: row r in lane 32*(r/16) + r%16) added to the shared-memory
-//       accumulator of dW1
+// Measured and rejected (round 1): the first-layer / bias column sums as extra tcgen05 GEMMs
+// (dZ1^T.[x,1], dZ2^T.1 with N = 8): correct, but bufC becomes a serial resource between three GEMMs of
+// a tile and every tiny MMA still costs ~32 tensor clocks: 5.6 ms instead of 4.2 ms per update.
 // Column sums over samples use a register butterfly (31 shuffles per 32-column half): lane l
 // of a warp ends with the warp's sum of its column l; per-warp partials live in registers for
 // the whole kernel and are combined once, in a fixed order, at the end.
@@ -92,11 +95,10 @@ TG_D void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::
 TG_D void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 // TMEM column map (512 columns allocated)
-#define TM_DF 0u
-#define TM_DB 64u
-#define TM_DW 128u
-#define TM_AHI 192u
-#define TM_ALO 256u
+#define TM_DF 0u     // forward accumulator  [128 x 64]
+#define TM_DB 64u    // backward-data accumulator [128 x 64]
+#define TM_DW 128u   // dW1 [64 x 64], M = 64 layout, PERSISTENT across the CTA's tiles
+#define TM_A0 192u   // A operand buffer 0: hi at +0, lo at +64; buffer 1 at +128
 
 // NPART threads serve one sample (2 or 4): NPART*4 compute warps + the issuer warp
 template <int O, int A, bool RELU, int NPART>
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(NPART * 128 + 32, 1) update_tc_kernel(const __
     constexpr int W = TC_W, HW = TC_W / NPART, O4 = (O + 1 + 3) / 4 * 4;
     constexpr int NCW = NPART * 4, NT = NPART * 128 + 32;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t wbar, bar_a, bar_w;
+    __shared__ __align__(8) uint64_t wbar, bar_a, bar_b, bar_w;
     __shared__ uint32_t tmem_slot;
     __shared__ double sred[4][NCW];
     __shared__ float muS[NPART][A][128];
@@ -112,19 +114,16 @@ __global__ void __launch_bounds__(NPART * 128 + 32, 1) update_tc_kernel(const __
     float *Wsm = reinterpret_cast<float *>(smem_raw);
     unsigned char *bufB_hi = smem_raw + ((size_t)a.lay.total * 4 + 1023) / 1024 * 1024;   // H1, MN-major
     unsigned char *bufB_lo = bufB_hi + 128 * W * 4;
-    unsigned char *bufC_hi = bufB_lo + 128 * W * 4;                                        // dZ2, MN-major
+    unsigned char *bufC_hi = bufB_lo + 128 * W * 4;      // dZ2, MN-major
     unsigned char *bufC_lo = bufC_hi + 128 * W * 4;
-    // dW1 accumulator [W][W], column-major (accS[k*W + r]): the 16 lanes owning consecutive rows r hit
-    // consecutive banks
-    float *accS = reinterpret_cast<float *>(bufC_lo + 128 * W * 4);
     stage_weights_tma(Wsm, a.packed, a.lay.total, &wbar);
     if (threadIdx.x == 0) {
         mbar_init(&bar_a, 1);
+        mbar_init(&bar_b, 1);
         mbar_init(&bar_w, 1);
         mbar_fence_init();
     }
     if (threadIdx.x < 32) tmem_alloc(&tmem_slot, 512);
-    for (int i = threadIdx.x; i < W * W; i += blockDim.x) accS[i] = 0.0f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -132,7 +131,7 @@ __global__ void __launch_bounds__(NPART * 128 + 32, 1) update_tc_kernel(const __
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3, hf = warp >> 2;        // lane quadrant, column part (0..NPART)
     const int s = q * 32 + lane;                    // sample row of this thread
-    const int c0 = hf * HW;                         // first column of this thread's half
+    const int c0 = hf * HW;                         // first column of this thread's part
     const uint32_t my_tm = tmem + ((uint32_t)(q * 32) << 16);
     const uint32_t idesc_f = umma_idesc_tf32(128, W, false, false);
     const uint32_t idesc_b = umma_idesc_tf32(128, W, false, true);
@@ -141,14 +140,14 @@ __global__ void __launch_bounds__(NPART * 128 + 32, 1) update_tc_kernel(const __
     const uint32_t wf_hi = w_u + (uint32_t)a.lay.whi[1] * 4u, wf_lo = w_u + (uint32_t)a.lay.wlo[1] * 4u;
     const uint32_t wb_hi = w_u + (uint32_t)a.lay.wbhi[1] * 4u, wb_lo = w_u + (uint32_t)a.lay.wblo[1] * 4u;
     const uint32_t B_hi = smem_u32(bufB_hi), B_lo = smem_u32(bufB_lo), C_hi = smem_u32(bufC_hi), C_lo = smem_u32(bufC_lo);
-    // this thread's half row in the MN-major SW128_32B layout: mn32_offset(128, s, c0 + 4*i)
+    // this thread's part of a row in the MN-major SW128_32B layout: mn32_offset(128, s, c0 + 4*i)
     const uint32_t mn_row = (uint32_t)(c0 >> 5) * (128u * 128u) + (uint32_t)s * 128u;
     const int cb = (c0 & 31) >> 3;                  // first 32-byte chunk of this thread's columns inside the line
     const int rs = s & 3;
     const float *w1 = Wsm + a.lay.w1, *b1 = Wsm + a.lay.bias[1], *wo = Wsm + a.lay.wo, *bo = Wsm + a.lay.bo;
     const int act_kind = RELU ? TG_ACT_RELU : a.lay.act;
 
-    // persistent per-thread gradient partials: this warp's sum over its 32 samples of column c0 + lane
+    // per-thread gradient partials that stay on the register butterfly (this warp's sum over its samples)
     float c_wo[A], c_b1 = 0.f, c_b0 = 0.f, c_w0[O], c_bo[A];
 #pragma unroll
     for (int j = 0; j < A; ++j) c_wo[j] = c_bo[j] = 0.0f;
@@ -159,6 +158,58 @@ __global__ void __launch_bounds__(NPART * 128 + 32, 1) update_tc_kernel(const __
     const int64_t N = a.N;
     const int64_t NB = (N + 127) / 128;
     const int64_t ntiles = NB * a.T;
+    bool have_prev = false;      // a tile has been processed before the current one (CTA-uniform)
+    if (warp == NCW) {
+        // ===== MMA issuer warp: one elected lane issues every tcgen05.mma of the CTA; it meets the compute
+        // warps on named barriers.  Tensor-pipe order per tile i:
+        //   fwd(i) | bwd(i), wgrad1(i)
+        uint32_t buf = 0, first_w = 1u;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            if ((tile % NB) * 128 >= a.cnt[tile / NB]) continue;
+            const uint32_t acol = tmem + TM_A0 + buf * 128u;
+            named_sync(BAR_FWD, NT);
+            tc_fence_after();
+            if (lane == 0) {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t ac = acol + (pass == 2 ? 64u : 0u);
+                    const uint32_t b = pass == 1 ? wf_lo : wf_hi;
+#pragma unroll
+                    for (int k = 0; k < W; k += 8) {
+                        umma_tf32_ts(tmem + TM_DF, ac + (uint32_t)k, umma_operand_desc(b, W, false, k), idesc_f, acc);
+                        acc = 1u;
+                    }
+                }
+                umma_commit(&bar_a);
+            }
+            __syncwarp();
+            named_sync(BAR_BWD, NT);
+            tc_fence_after();
+            if (lane == 0) {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t ac = acol + (pass == 2 ? 64u : 0u);
+                    const uint32_t b = pass == 1 ? wb_lo : wb_hi;
+#pragma unroll
+                    for (int k = 0; k < W; k += 8) {
+                        umma_tf32_ts(tmem + TM_DB, ac + (uint32_t)k, umma_operand_desc(b, W, true, k), idesc_b, acc);
+                        acc = 1u;
+                    }
+                }
+                umma_commit(&bar_b);
+                // dW1 += dZ2^T . H1, accumulated in tensor memory over all of this CTA's tiles
+                umma_gemm_3xtf32(tmem + TM_DW, C_hi, C_lo, 128, true, B_hi, B_lo, 128, true, 128, idesc_w, first_w == 0u, 3);
+                first_w = 0u;
+                umma_commit(&bar_w);
+            }
+            __syncwarp();
+            have_prev = true;
+            buf ^= 1u;
+        }
+    } else {
+    // ===== compute warps =====
     // software prefetch of a tile's per-sample inputs
     float xn[O], an[A], advn = 0.f, olpn = 0.f;
     bool vn = false;
@@ -173,57 +224,51 @@ __global__ void __launch_bounds__(NPART * 128 + 32, 1) update_tc_kernel(const __
 #pragma unroll
                 for (int o = 0; o < O; ++o) xn[o] = a.obs[((int64_t)t * O + o) * N + n];
 #pragma unroll
-                for (int j = 0; j < A; ++j) an[j] = a.act[((int64_t)t * A + j) * N + n];
+                for (int j2 = 0; j2 < A; ++j2) an[j2] = a.act[((int64_t)t * A + j2) * N + n];
                 advn = a.adv[(int64_t)t * N + n];
                 olpn = a.oldlp[(int64_t)t * N + n];
             }
         }
     };
-    uint32_t ph_a = 0, ph_w = 0;
-    bool pending_w = false;      // a weight-gradient GEMM is in flight (CTA-uniform)
-    if (warp == NCW) {
-        // ===== MMA issuer warp: one elected lane issues every tcgen05.mma of the CTA, so no compute
-        // warp is held up by the serial issue loop; it meets the compute warps on named barriers =====
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            if ((tile % NB) * 128 >= a.cnt[tile / NB]) continue;
-            named_sync(BAR_FWD, NT);
-            tc_fence_after();
-            if (lane == 0) {
-                uint32_t acc = 0;
+    uint32_t ph_a = 0, ph_b = 0, ph_w = 0, buf = 0;
+    float xp[O];                 // previous tile's inputs and act'(H1) mask: its dZ1 is finished one tile later
+    uint32_t m1p = 0;
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t acol = tmem + (pass == 2 ? TM_ALO : TM_AHI);
-                    const uint32_t b = pass == 1 ? wf_lo : wf_hi;
+    for (int o = 0; o < O; ++o) xp[o] = 0.0f;
+    // finish the PREVIOUS tile's backward: dZ1 = D_b * act'(H1) -> first-layer gradients (register butterflies)
+    auto finish_prev = [&]() {
+        mbar_wait(&bar_b, ph_b);
+        ph_b ^= 1u;
+        tc_fence_after();
+        float d1[HW];
+        tmem_ldN<HW>(my_tm + TM_DB + (uint32_t)c0, d1);
+        if (RELU) {
 #pragma unroll
-                    for (int k = 0; k < W; k += 8) {
-                        umma_tf32_ts(tmem + TM_DF, acol + (uint32_t)k, umma_operand_desc(b, W, false, k), idesc_f, acc);
-                        acc = 1u;
-                    }
-                }
-                umma_commit(&bar_a);
+            for (int j = 0; j < HW; ++j) d1[j] = ((m1p >> j) & 1u) ? d1[j] : 0.0f;
+        } else {
+#pragma unroll
+            for (int i = 0; i < HW / 4; ++i) {     // bufB still holds the previous tile's H1
+                const uint32_t om = mn_row + (uint32_t)((((i >> 1) + cb) ^ rs) << 5) + (uint32_t)(i & 1) * 16u;
+                const float4 vh = *reinterpret_cast<const float4 *>(bufB_hi + om);
+                const float4 vl = *reinterpret_cast<const float4 *>(bufB_lo + om);
+                d1[4 * i] *= act_bwd_from_out(vh.x + vl.x, act_kind);
+                d1[4 * i + 1] *= act_bwd_from_out(vh.y + vl.y, act_kind);
+                d1[4 * i + 2] *= act_bwd_from_out(vh.z + vl.z, act_kind);
+                d1[4 * i + 3] *= act_bwd_from_out(vh.w + vl.w, act_kind);
             }
-            __syncwarp();
-            named_sync(BAR_BWD, NT);
-            tc_fence_after();
-            if (lane == 0) {
-                uint32_t acc = 0;
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t acol = tmem + (pass == 2 ? TM_ALO : TM_AHI);
-                    const uint32_t b = pass == 1 ? wb_lo : wb_hi;
-#pragma unroll
-                    for (int k = 0; k < W; k += 8) {
-                        umma_tf32_ts(tmem + TM_DB, acol + (uint32_t)k, umma_operand_desc(b, W, true, k), idesc_b, acc);
-                        acc = 1u;
-                    }
-                }
-                umma_commit(&bar_a);
-                umma_gemm_3xtf32(tmem + TM_DW, C_hi, C_lo, 128, true, B_hi, B_lo, 128, true, 128, idesc_w, false, 3);
-                umma_commit(&bar_w);
-            }
-            __syncwarp();
         }
-    } else {
+#pragma unroll
+        for (int o = 0; o < O; ++o) {
+            float v[HW];
+#pragma unroll
+            for (int e = 0; e < HW; ++e) v[e] = d1[e] * xp[o];
+            c_w0[o] += colsumN<HW>(v, lane);
+        }
+        c_b0 += colsumN<HW>(d1, lane);
+        // the previous tile's weight-gradient GEMM has consumed bufB / bufC
+        mbar_wait(&bar_w, ph_w);
+        ph_w ^= 1u;
+    };
     prefetch(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         float x[O], av[A];
@@ -236,7 +281,8 @@ __global__ void __launch_bounds__(NPART * 128 + 32, 1) update_tc_kernel(const __
         // whole tile is padding (fewer live envs at this step than the tile's first sorted position):
         // CTA-uniform decision from the per-step live count, no barrier needed
         if ((tile % NB) * 128 >= a.cnt[tile / NB]) { prefetch(tile + gridDim.x); continue; }
-        // ---- P1: first Linear on the FP32 pipe, this thread's 32 neurons
+        const uint32_t my_a = my_tm + TM_A0 + buf * 128u;
+        // ---- P1: first Linear on the FP32 pipe, this thread's HW neurons
         float h[HW];
 #pragma unroll
         for (int i = 0; i < HW; ++i) {
@@ -263,25 +309,13 @@ __global__ void __launch_bounds__(NPART * 128 + 32, 1) update_tc_kernel(const __
                 hi[4 * i] = h4.x; hi[4 * i + 1] = h4.y; hi[4 * i + 2] = h4.z; hi[4 * i + 3] = h4.w;
                 lo[4 * i] = l4.x; lo[4 * i + 1] = l4.y; lo[4 * i + 2] = l4.z; lo[4 * i + 3] = l4.w;
             }
-            tmem_stN<HW>(my_tm + TM_AHI + (uint32_t)c0, hi);
-            tmem_stN<HW>(my_tm + TM_ALO + (uint32_t)c0, lo);
+            tmem_stN<HW>(my_a + (uint32_t)c0, hi);
+            tmem_stN<HW>(my_a + 64u + (uint32_t)c0, lo);
             tmem_st_wait();
             tc_fence_before();
             named_arrive(BAR_FWD, NT);          // -> issuer warp: forward-GEMM operands are in place
-            // in the shadow of the forward GEMM: retire the PREVIOUS tile's weight-gradient GEMM (its
-            // operands bufB/bufC and its accumulator D_w are then free), then publish H1 MN-major
-            if (pending_w) {
-                mbar_wait(&bar_w, ph_w);
-                ph_w ^= 1u;
-                tc_fence_after();
-                float z[HW];
-                tmem_ldN<HW>(my_tm + TM_DW + (uint32_t)c0, z);
-                if (lane < 16) {
-#pragma unroll
-                    for (int j = 0; j < HW; ++j) accS[(c0 + j) * W + q * 16 + lane] += z[j];
-                }
-                pending_w = false;
-            }
+            // in the shadow of the forward GEMM: finish the previous tile's backward, then publish H1 MN-major
+            if (have_prev) finish_prev();
 #pragma unroll
             for (int i = 0; i < HW / 4; ++i) {
                 const uint32_t om = mn_row + (uint32_t)((((i >> 1) + cb) ^ rs) << 5) + (uint32_t)(i & 1) * 16u;
@@ -292,7 +326,7 @@ __global__ void __launch_bounds__(NPART * 128 + 32, 1) update_tc_kernel(const __
         mbar_wait(&bar_a, ph_a);
         ph_a ^= 1u;
         tc_fence_after();
-        // ---- P3: H2 (this thread's half), output Linear, objective, dZ2
+        // ---- P3: H2 (this thread's part), output Linear, objective, dZ2
         {
             float z[HW];
             tmem_ldN<HW>(my_tm + TM_DF + (uint32_t)c0, z);
@@ -316,7 +350,7 @@ __global__ void __launch_bounds__(NPART * 128 + 32, 1) update_tc_kernel(const __
             }
             muS[hf][j][s] = acc;
         }
-        // only the two warps that share this lane quadrant exchange data: named barrier, 64 threads
+        // only the warps that share this lane quadrant exchange data: named barrier
         asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "r"(NPART * 32) : "memory");
         float mu[A], dmu[A];
 #pragma unroll
@@ -351,7 +385,7 @@ __global__ void __launch_bounds__(NPART * 128 + 32, 1) update_tc_kernel(const __
             }
 #pragma unroll
             for (int j = 0; j < A; ++j) dmu[j] = dlp * (av[j] - mu[j]) * a.inv_var[j];
-            if (hf == 0) {       // one of the two threads of a sample keeps the statistics
+            if (hf == 0) {       // one of the threads of a sample keeps the statistics
                 s_obj += (double)fminf(s1, s2) * a.scale + (double)a.kl_scale * eo * (olp - lp);
                 s_cnt += 1.0; s_ratio += ratio; s_clip += in_range ? 0.0 : 1.0;
 #pragma unroll
@@ -383,16 +417,16 @@ __global__ void __launch_bounds__(NPART * 128 + 32, 1) update_tc_kernel(const __
                 *reinterpret_cast<float4 *>(bufC_hi + om) = h4;
                 *reinterpret_cast<float4 *>(bufC_lo + om) = l4;
             }
-            tmem_stN<HW>(my_tm + TM_AHI + (uint32_t)c0, hi);     // the forward GEMM has consumed H1
-            tmem_stN<HW>(my_tm + TM_ALO + (uint32_t)c0, lo);
+            tmem_stN<HW>(my_a + (uint32_t)c0, hi);            // the forward GEMM has consumed H1
+            tmem_stN<HW>(my_a + 64u + (uint32_t)c0, lo);
             tmem_st_wait();
         }
         fence_proxy_async();
         tc_fence_before();
         named_arrive(BAR_BWD, NT);          // -> issuer warp: dZ2 (TMEM + bufC) and H1 (bufB) are in place
-        pending_w = true;
-        // in the shadow of the two GEMMs: next tile's inputs, column sums for dWo and db1
+        // in the shadow of the GEMMs: next tile's inputs, column sums for dWo and db1
         prefetch(tile + gridDim.x);
+        c_b1 += colsumN<HW>(dz, lane);
 #pragma unroll
         for (int j = 0; j < A; ++j) {
             float v[HW];
@@ -400,59 +434,34 @@ __global__ void __launch_bounds__(NPART * 128 + 32, 1) update_tc_kernel(const __
             for (int e = 0; e < HW; ++e) v[e] = dmu[j] * h[e];
             c_wo[j] += colsumN<HW>(v, lane);
         }
-        c_b1 += colsumN<HW>(dz, lane);
-        mbar_wait(&bar_a, ph_a);
-        ph_a ^= 1u;
-        tc_fence_after();
-        // ---- P5a: dZ1 = D_b * act'(H1); first-layer gradients
-        float d1[HW];
-        tmem_ldN<HW>(my_tm + TM_DB + (uint32_t)c0, d1);
-        if (RELU) {
 #pragma unroll
-            for (int j = 0; j < HW; ++j) d1[j] = ((m1 >> j) & 1u) ? d1[j] : 0.0f;
-        } else {
-#pragma unroll
-            for (int i = 0; i < HW / 4; ++i) {
-                const uint32_t om = mn_row + (uint32_t)((((i >> 1) + cb) ^ rs) << 5) + (uint32_t)(i & 1) * 16u;
-                const float4 vh = *reinterpret_cast<const float4 *>(bufB_hi + om);
-                const float4 vl = *reinterpret_cast<const float4 *>(bufB_lo + om);
-                d1[4 * i] *= act_bwd_from_out(vh.x + vl.x, act_kind);
-                d1[4 * i + 1] *= act_bwd_from_out(vh.y + vl.y, act_kind);
-                d1[4 * i + 2] *= act_bwd_from_out(vh.z + vl.z, act_kind);
-                d1[4 * i + 3] *= act_bwd_from_out(vh.w + vl.w, act_kind);
-            }
-        }
-#pragma unroll
-        for (int o = 0; o < O; ++o) {
-            float v[HW];
-#pragma unroll
-            for (int e = 0; e < HW; ++e) v[e] = d1[e] * x[o];
-            c_w0[o] += colsumN<HW>(v, lane);
-        }
-        c_b0 += colsumN<HW>(d1, lane);
-        // P5b (D_w -> accS) is deferred into the next tile's forward-GEMM shadow
+        for (int o = 0; o < O; ++o) xp[o] = x[o];
+        m1p = m1;
+        have_prev = true;
+        buf ^= 1u;
     }
-    // ---- retire the last weight-gradient GEMM (row r of the M = 64 accumulator: lane 32*(r/16) + r%16)
-    if (pending_w) {
-        mbar_wait(&bar_w, ph_w);
-        tc_fence_after();
+    // ---- drain: the last tile's backward
+    if (have_prev) finish_prev();
+    }   // compute warps
+    // ---- write this CTA's partial gradient (private copy, zero-initialised by the host)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    float *gp = a.gpart + (int64_t)blockIdx.x * a.lay.n_params;
+    const int64_t f0 = a.lay.flat_w[0], f1 = a.lay.flat_w[1], f2 = a.lay.flat_w[2];
+    // tensor-memory accumulators (M = 64: row r lives in lane 32*(r/16) + r%16).  have_prev is false in a CTA
+    // that processed no tile: its accumulators were never written and its gradient copy stays zero.
+    if (warp < NCW && have_prev) {
+        const int r = q * 16 + lane;
         float z[HW];
         tmem_ldN<HW>(my_tm + TM_DW + (uint32_t)c0, z);
         if (lane < 16) {
 #pragma unroll
-            for (int j = 0; j < HW; ++j) accS[(c0 + j) * W + q * 16 + lane] += z[j];
+            for (int j = 0; j < HW; ++j) gp[f1 + (int64_t)r * W + c0 + j] = z[j];       // dW1[out r][in c0+j]
         }
     }
-    }   // compute warps
-    // ---- write this CTA's partial gradient (private copy, zero-initialised by the host)
     __syncthreads();
-    float *gp = a.gpart + (int64_t)blockIdx.x * a.lay.n_params;
-    const int64_t f0 = a.lay.flat_w[0], f1 = a.lay.flat_w[1], f2 = a.lay.flat_w[2];
-    for (int i = threadIdx.x; i < W * W; i += blockDim.x) {
-        const int r = i / W, k = i % W;
-        gp[f1 + i] = accS[k * W + r];
-    }
-    // column partials of the four lane quadrants, added in a fixed order
+    // butterfly partials of the four lane quadrants, added in a fixed order
     for (int qs = 0; qs < 4; ++qs) {
         if (warp < NCW && q == qs && (HW == 32 || (lane & 1) == 0)) {
             const int col = c0 + (HW == 32 ? lane : (lane >> 1));
@@ -544,8 +553,7 @@ int tg_policy_grad_tc(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, cons
     if (rc) return rc;
     a.perm = ctx->perm;
     a.cnt = ctx->cnt;
-    const size_t smem =((size_t)a.lay.total * 4 + 1023) / 1024 * 1024 + 4 * (size_t)128 * TC_W * 4 +
-                        (size_t)TC_W * TC_W * 4;
+    const size_t smem = ((size_t)a.lay.total * 4 + 1023) / 1024 * 1024 + 4 * (size_t)128 * TC_W * 4;
     TG_REQUIRE(smem <= (size_t)ctx->smem_optin, TG_ERR_UNSUPPORTED, "tensor-core update needs %zu B of shared memory", smem);
     const int O = a.lay.O, A = a.lay.A;
     if (O == 3 && A == 1) return launch_update_tc<3, 1>(a, grid, smem, st);
