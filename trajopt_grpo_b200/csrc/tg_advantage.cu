@@ -14,6 +14,7 @@
 #include "tg_common.cuh"
 
 #define ADV_THREADS 128
+#define ADV_UNROLL 16
 
 // rtg recurrence with torch's rounding (separate multiply and add, no FMA)
 TG_D float rtg_step(float r, float gamma, float next) { return __fadd_rn(r, __fmul_rn(gamma, next)); }
@@ -45,8 +46,23 @@ adv_grpo_kernel(int64_t G, int E, int T, int GC, float gamma, const float *__res
         const double K = L0 > 0 ? (double)__fadd_rn(rew[(int64_t)(L0 - 1) * N + e0], 1e-8f) : 0.0;
         float rtg = 0.0f;
         double ax = 0.0, ay = 0.0, ayy = 0.0;
-#pragma unroll 4
-        for (int t = L - 1; t >= 0; --t) {
+        // the recurrence is serial per env (bit-exact torch rounding forbids re-association), so the memory
+        // parallelism comes from loading ADV_UNROLL reward rows ahead of the dependent chain
+        int t = L - 1;
+        for (; t >= ADV_UNROLL - 1; t -= ADV_UNROLL) {
+            float r[ADV_UNROLL];
+#pragma unroll
+            for (int j = 0; j < ADV_UNROLL; ++j) r[j] = rew[(int64_t)(t - j) * N + n];
+#pragma unroll
+            for (int j = 0; j < ADV_UNROLL; ++j) {
+                rtg = rtg_step(r[j], gamma, rtg);
+                const double y = (double)__fadd_rn(rtg, 1e-8f) - K;
+                ax += (double)rtg;
+                ay += y;
+                ayy += y * y;
+            }
+        }
+        for (; t >= 0; --t) {
             rtg = rtg_step(rew[(int64_t)t * N + n], gamma, rtg);
             const double y = (double)__fadd_rn(rtg, 1e-8f) - K;
             ax += (double)rtg;
@@ -81,8 +97,19 @@ adv_grpo_kernel(int64_t G, int E, int T, int GC, float gamma, const float *__res
             if (rtg_out) rtg_out[(int64_t)t * N + n] = 0.0f;
         }
         float rtg = 0.0f;
-#pragma unroll 4
-        for (int t = L - 1; t >= 0; --t) {
+        int t = L - 1;
+        for (; t >= ADV_UNROLL - 1; t -= ADV_UNROLL) {
+            float r[ADV_UNROLL];
+#pragma unroll
+            for (int j = 0; j < ADV_UNROLL; ++j) r[j] = rew[(int64_t)(t - j) * N + n];
+#pragma unroll
+            for (int j = 0; j < ADV_UNROLL; ++j) {
+                rtg = rtg_step(r[j], gamma, rtg);
+                adv[(int64_t)(t - j) * N + n] = __fdiv_rn(__fsub_rn(rtg, mean), sd);
+                if (rtg_out) rtg_out[(int64_t)(t - j) * N + n] = rtg;
+            }
+        }
+        for (; t >= 0; --t) {
             rtg = rtg_step(rew[(int64_t)t * N + n], gamma, rtg);
             adv[(int64_t)t * N + n] = __fdiv_rn(__fsub_rn(rtg, mean), sd);
             if (rtg_out) rtg_out[(int64_t)t * N + n] = rtg;
@@ -112,9 +139,24 @@ adv_ppo_scan_kernel(int64_t N, int T, int gae, float gamma, float gamlam, const 
             rtg_out[(int64_t)t * N + n] = 0.0f;
         }
         float rtg = 0.0f, a_next = 0.0f, v_next = 0.0f;
+        constexpr int PU = 8;                 // rows loaded ahead of the serial recurrence
+        float rb[PU], vb[PU];
         for (int t = L - 1; t >= 0; --t) {
-            const float r = rew[(int64_t)t * N + n];
-            const float v = val[(int64_t)t * N + n];
+            const int slot = (L - 1 - t) % PU;
+            if (slot == 0) {
+#pragma unroll
+                for (int j = 0; j < PU; ++j) {
+                    const int tt = t - j;
+                    rb[j] = tt >= 0 ? rew[(int64_t)tt * N + n] : 0.0f;
+                    vb[j] = tt >= 0 ? val[(int64_t)tt * N + n] : 0.0f;
+                }
+            }
+            float r = rb[0], v = vb[0];
+#pragma unroll
+            for (int j = 1; j < PU; ++j) {
+                r = slot == j ? rb[j] : r;
+                v = slot == j ? vb[j] : v;
+            }
             float a, ret;
             if (!gae) {
                 rtg = rtg_step(r, gamma, rtg);            // ppo.py:103-108

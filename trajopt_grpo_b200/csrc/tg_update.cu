@@ -13,6 +13,7 @@
 // kernel sums the private copies in a fixed order: the result is deterministic
 // and has the flat torch layout the NCCL allreduce and Adam consume.
 #include <math.h>
+#include <stdlib.h>
 
 #include "tg_mlp.cuh"
 
