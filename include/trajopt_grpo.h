@@ -258,6 +258,18 @@ int tg_value_grad(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T,
                   const float *obs, const float *target, const int32_t *len, const float *params,
                   float scale, float *out_grad, float *out_stats, void *workspace, void *stream);
 
+/* Minibatch forms of tg_policy_grad / tg_value_grad (PPO with batch_size != None, algorithms/ppo.py:147-183:
+ * `permutation[start:start+batch_size]` over the valid steps).  sample_ids [n_samples] int64 (device) lists the
+ * samples of the minibatch as flat slot ids t*N + n into the [T][.][N] buffers; `scale` is the caller's
+ * 1/len(batch) (the reference's .mean() over the batch).  Same outputs and workspace as the full forms. */
+int tg_policy_grad_batch(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, const float *obs, const float *act,
+                         const float *adv, const float *old_logp, const int64_t *sample_ids, int64_t n_samples,
+                         const float *params, const float *cov_diag, float eps_clip, float scale, float kl_coef,
+                         float *out_grad, float *out_stats, void *workspace, void *stream);
+int tg_value_grad_batch(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, const float *obs, const float *target,
+                        const int64_t *sample_ids, int64_t n_samples, const float *params, float scale,
+                        float *out_grad, float *out_stats, void *workspace, void *stream);
+
 /* ---- Adam --------------------------------------------------------------------
  * torch.optim.Adam defaults as the reference constructs it
  * (pipelines/cartpole_pipeline_grpo.py:65): p -= lr/(1-b1^t) * m/(sqrt(v)/sqrt(1-b2^t)+eps).

@@ -264,7 +264,45 @@ def gen_ppo(kind, hidden, cov, G, E, T, seed, gamma, lam, eps_clip, monte_carlo)
     return out
 
 
+def gen_ppo_minibatch(kind, hidden, cov, G, E, T, seed, gamma, lam, eps_clip, batch_size, updates, torch_seed):
+    """PPO.learn with randperm minibatches (ppo.py:147-183): Adam, `updates` epochs; torch's default CPU
+    generator is seeded right before learn() so the permutations can be redrawn by the checker."""
+    import copy
+    from algorithms.ppo import PPO
+    rng = np.random.default_rng(seed)
+    import restate
+    policy = make_policy(kind, hidden, cov, seed, critic=True)
+    A = {0: 1, 1: 1, 2: 2, 3: 4}[kind]
+    init = restate.reset_states(kind, G * E, rng)
+    noise = rng.standard_normal((T, G * E, A)).astype(np.float32)
+    obs, act, rew, ln, mask = run_rollout(kind, policy, init, noise, G, E, T, False)
+    out = dict(kind=kind, hidden=np.array(hidden), cov=np.float32(cov), G=G, E=E, T=T, gamma=gamma,
+               lam=lam, eps_clip=eps_clip, monte_carlo=False, init=init, noise=noise, batch_size=batch_size,
+               updates=updates, torch_seed=torch_seed,
+               obs=obs, act=act, rew=rew, len=ln, mask=mask, **policy_arrays(policy))
+    buf = Buf()
+    buf.group_observations, buf.group_actions = torch.from_numpy(obs), torch.from_numpy(act)
+    buf.group_rewards, buf.group_masks = torch.from_numpy(rew), torch.from_numpy(mask)
+    kw = dict(c1=0.5, kl_coeff=0.5, gamma=gamma, lam=lam, entropy=0.01, batch_size=batch_size, monte_carlo=False)
+    p2 = copy.deepcopy(policy)
+    algo = PPO(eps_clip, p2, torch.optim.Adam(p2.parameters(), lr=2e-4), None, updates, **kw)
+    torch.manual_seed(torch_seed)
+    algo.learn(buf)
+    for i, a in enumerate(p2.parameters()):
+        out[f"ppo_mb_adam_p{i}"] = a.detach().numpy().copy()
+    return out
+
+
 def main():
+    if "--only-ppo-minibatch" in sys.argv:
+        if not ref_shims.available():
+            raise SystemExit("reference not mounted; fixtures can only be regenerated in the build container")
+        ref_shims.install()
+        out = gen_ppo_minibatch(kind=2, hidden=[32, 32], cov=0.5, G=3, E=4, T=120, seed=11, gamma=0.99, lam=0.95,
+                                eps_clip=0.2, batch_size=64, updates=2, torch_seed=4321)
+        np.savez_compressed(os.path.join(OUT, "ppo_minibatch_quadpole2d.npz"), **out)
+        print(f"ppo_minibatch: lens={out['len'].reshape(-1).tolist()}")
+        return
     if not ref_shims.available():
         raise SystemExit("reference not mounted; fixtures can only be regenerated in the build container")
     ref_shims.install()
@@ -302,6 +340,10 @@ def main():
                       eps_clip=0.2, monte_carlo=mc)
         np.savez_compressed(os.path.join(OUT, f"ppo_{name}_quadpole2d.npz"), **out)
         print(f"ppo_{name}: lens={out['len'].reshape(-1).tolist()}")
+    out = gen_ppo_minibatch(kind=2, hidden=[32, 32], cov=0.5, G=3, E=4, T=120, seed=11, gamma=0.99, lam=0.95,
+                            eps_clip=0.2, batch_size=64, updates=2, torch_seed=4321)
+    np.savez_compressed(os.path.join(OUT, "ppo_minibatch_quadpole2d.npz"), **out)
+    print(f"ppo_minibatch: lens={out['len'].reshape(-1).tolist()}")
 
 
 if __name__ == "__main__":

@@ -299,3 +299,29 @@ def test_pipeline_train_save_load_resume(tg, tmp_path):
     assert os.path.exists(os.path.join(pipe2.archive_path, "trajectory.csv"))
     pipe2.publish()
     assert os.path.exists(os.path.join(pipe2.publish_path, "metadata.json"))
+
+
+def test_ppo_minibatched_learn_matches_reference(tg, golden_dir):
+    """PPO.learn with batch_size=64 (the reference constructor's default, ppo.py:147-183): randperm
+    minibatches over the valid steps of a ragged rollout, one Adam step per minibatch.  The fixture was
+    produced by the unmodified reference with torch's CPU generator seeded right before learn()."""
+    g = load(golden_dir, "ppo_minibatch_quadpole2d.npz")
+    kind = int(g["kind"])
+    hidden = [int(h) for h in g["hidden"]]
+    O, A = R.OBS_DIM[kind], R.ACT_DIM[kind]
+    Ws, bs = _weights(g)
+    cWs, cbs = _weights(g, "c")
+    buf = _make_buffer(tg, g)
+    assert len(set(g["len"].reshape(-1).tolist())) > 1          # ragged
+    pol = tg.GaussianActorCritic_NeuralNetwork(O, A, hidden, "ReLU", float(g["cov"]))
+    _load_actor(pol.actor, Ws, bs)
+    _load_actor(pol.critic, cWs, cbs)
+    algo = tg.PPO(float(g["eps_clip"]), pol, torch.optim.Adam(pol.parameters(), lr=2e-4), None, int(g["updates"]),
+                  c1=0.5, kl_coeff=0.5, gamma=float(g["gamma"]), lam=float(g["lam"]), entropy=0.01,
+                  batch_size=int(g["batch_size"]), monte_carlo=False)
+    torch.manual_seed(int(g["torch_seed"]))
+    algo.learn(buf)
+    n_steps = int(g["updates"]) * -(-int(g["len"].sum()) // int(g["batch_size"]))
+    assert algo._flat_opt.step_count == n_steps                   # one optimizer step per minibatch
+    for i, p in enumerate(pol.parameters()):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), g[f"ppo_mb_adam_p{i}"], rtol=1e-3, atol=2e-5)

@@ -199,7 +199,8 @@ class GRPO(Algorithm):
 
 
 class PPO(Algorithm):
-    """algorithms/ppo.py:8-225 (full-batch updates: batch_size=None, the shipped pipelines' setting)."""
+    """algorithms/ppo.py:8-225: full-batch updates (batch_size=None, the shipped pipelines' setting; shards over
+    GPUs) and randperm minibatches (batch_size=k, single GPU)."""
 
     def __init__(self, epsilon: float, policy, optimizer, ref_model, updates_per_iter: int, c1: float = 0.5,
                  kl_coeff: float = 0.5, gamma: float = 0.99, lam: float = 0.95, entropy: float = 0.01,
@@ -214,10 +215,10 @@ class PPO(Algorithm):
         self.last_stats = None
 
     def learn(self, buffer) -> None:
-        if self.batch_size is not None:
-            raise L.EngineError("minibatched PPO (batch_size != None) is not built yet: the fused update is "
-                                "full-batch, as quadpole2d_pipeline_ppo.py configures it")
         world = _dist_world()
+        if self.batch_size is not None and world > 1:
+            # ppo.py:149 draws ONE torch.randperm over all valid steps; it has no sharded equivalent
+            raise L.EngineError("minibatched PPO (batch_size != None) runs on one GPU; use batch_size=None when sharded")
         r = _rollout_of(buffer)
         pol = self.policy
         flat = pol.flat_parameters()
@@ -241,6 +242,10 @@ class PPO(Algorithm):
         _, old_logp = engine.policy_forward_traj(a_dims, act_name, a_flat, r.obs, cov, r.act, r.len)
         n_valid = int(round(float(sums[4].item())))                 # global valid-step count (the .mean()s)
         grad = torch.empty_like(flat)
+        if self.batch_size is not None:
+            self._learn_minibatched(r, flat, grad, na, a_dims, c_dims, act_name, cov, adv, rtg, old_logp, n_valid)
+            self.old_policy.load_state_dict(self.policy.state_dict())   # ppo.py:186
+            return
         for _ in range(self.updates_per_iter):                      # ppo.py:147 (full batch; the order of a
             # permutation does not change a mean)
             _, stats = engine.policy_grad(a_dims, act_name, a_flat, cov, r.obs, r.act, adv, old_logp, r.len,
@@ -254,6 +259,31 @@ class PPO(Algorithm):
             pol.bump_param_epoch()
             self.last_stats = stats
         self.old_policy.load_state_dict(self.policy.state_dict())   # ppo.py:186
+
+    def _learn_minibatched(self, r, flat, grad, na, a_dims, c_dims, act_name, cov, adv, rtg, old_logp, n_valid):
+        """ppo.py:147-183 with batch_size != None: one `torch.randperm(data_size)` per epoch from torch's
+        default CPU generator (the reference's call, so a seeded run draws the same permutation), sliced
+        into minibatches over the valid steps in the reference's flattening order (env-major, step-minor);
+        one Adam step per minibatch.  Each minibatch is a list of flat slot ids for the *_batch kernels."""
+        a_flat, c_flat = flat[:na], flat[na:]
+        dev = flat.device
+        lens = r.len.to(torch.int64)
+        csum = torch.cumsum(lens, 0)
+        row0 = csum - lens
+        for _ in range(self.updates_per_iter):
+            permutation = torch.randperm(n_valid)                   # ppo.py:149
+            perm_d = permutation.to(dev)
+            n_of = torch.searchsorted(csum, perm_d, right=True)     # valid-step index k -> env n, step t
+            sid_all = ((perm_d - row0[n_of]) * r.N + n_of).contiguous()
+            for start in range(0, n_valid, self.batch_size):        # ppo.py:152-153
+                sid = sid_all[start:start + self.batch_size]
+                m = sid.numel()
+                _, stats = engine.policy_grad_batch(a_dims, act_name, a_flat, cov, r.obs, r.act, adv, old_logp, sid,
+                                                    self.epsilon, -1.0 / m, self.kl_coeff / m, out_grad=grad[:na])
+                engine.value_grad_batch(c_dims, act_name, c_flat, r.obs, rtg, sid, self.c1 / m, out_grad=grad[na:])
+                self._flat_opt.step(flat, grad)
+                self.policy.bump_param_epoch()
+                self.last_stats = stats
 
     def metadata(self) -> dict:
         return {"algorithm": "PPO", "epsilon": self.epsilon, "c1": self.c1, "kl_coeff": self.kl_coeff,

@@ -30,6 +30,10 @@ struct UpdArgs {
     const int32_t *len;
     // length order (tg_order.cu) or null: sorted position j of step t is env perm[j], live iff j < cnt[t]
     const int32_t *perm, *cnt;
+    // minibatch mode (PPO with batch_size, ppo.py:147-157) or null: the launch covers the n_sidx samples
+    // whose flat slot ids t*N + n are listed in sidx, in that order
+    const int64_t *sidx;
+    int64_t n_sidx;
     const float *packed;
     float inv_sd[TG_MAX_ACT], inv_var[TG_MAX_ACT], log_norm;
     float eps_clip, scale, kl_scale;
@@ -116,6 +120,7 @@ __global__ void __launch_bounds__(TileCfg<CFG>::NT) update_kernel(const __grid_c
     __shared__ __align__(8) uint64_t wbar;
     __shared__ double sred[4][NT / 32];
     __shared__ int32_t tile_env[B];      // env index of each sample of the tile, -1 = padding
+    __shared__ int32_t tile_t[B];        // its step index (tile-uniform except in minibatch mode)
     const int nl = a.lay.n_layers, nh = nl - 1;
     const int O = a.lay.O, O8 = tg_round_up(O, 8);
     float *Ws = reinterpret_cast<float *>(smem_raw);
@@ -130,8 +135,8 @@ __global__ void __launch_bounds__(TileCfg<CFG>::NT) update_kernel(const __grid_c
     __syncthreads();
 
     const int64_t N = a.N;
-    const int64_t NB = (N + B - 1) / B;
-    const int64_t ntiles = NB * a.T;
+    const int64_t NB = a.sidx ? (a.n_sidx + B - 1) / B : (N + B - 1) / B;
+    const int64_t ntiles = a.sidx ? NB : NB * a.T;
     float *gp = a.gpart ? a.gpart + (int64_t)blockIdx.x * a.lay.n_params : nullptr;
     const bool owner = threadIdx.x < B;
     double s_obj = 0.0, s_cnt = 0.0, s_ratio = 0.0, s_clip = 0.0;
@@ -144,10 +149,18 @@ __global__ void __launch_bounds__(TileCfg<CFG>::NT) update_kernel(const __grid_c
         //         consecutive envs, a gather through perm when the rollout is walked in length order)
         bool valid = false;
         int64_t n_own = 0;
-        if (a.cnt != nullptr && nb0 >= a.cnt[t]) continue;   // whole tile is padding (CTA-uniform)
+        int t_own = t;
+        if (a.sidx == nullptr && a.cnt != nullptr && nb0 >= a.cnt[t]) continue;   // whole tile is padding (CTA-uniform)
         if (owner) {
             const int64_t j = nb0 + threadIdx.x;
-            if (a.cnt != nullptr) {
+            if (a.sidx != nullptr) {
+                valid = j < a.n_sidx;
+                if (valid) {
+                    const int64_t id = a.sidx[j];
+                    t_own = (int)(id / N);
+                    n_own = id % N;
+                }
+            } else if (a.cnt != nullptr) {
                 valid = j < a.cnt[t];
                 n_own = valid ? a.perm[j] : 0;
             } else {
@@ -155,12 +168,13 @@ __global__ void __launch_bounds__(TileCfg<CFG>::NT) update_kernel(const __grid_c
                 valid = j < N && (a.len == nullptr || t < a.len[j]);
             }
             tile_env[threadIdx.x] = valid ? (int32_t)n_own : -1;
+            tile_t[threadIdx.x] = t_own;
         }
         if (!__syncthreads_or(valid ? 1 : 0)) continue;   // whole tile is padding
         for (int idx = threadIdx.x; idx < O * B; idx += NT) {
             const int o = idx / B, b = idx % B;
             const int32_t n = tile_env[b];
-            X0[o * LDX + b] = n >= 0 ? a.obs[((int64_t)t * O + o) * N + n] : 0.0f;
+            X0[o * LDX + b] = n >= 0 ? a.obs[((int64_t)tile_t[b] * O + o) * N + n] : 0.0f;
         }
         __syncthreads();
         // ---- 2. forward, keeping H_1..H_nh
@@ -179,7 +193,7 @@ __global__ void __launch_bounds__(TileCfg<CFG>::NT) update_kernel(const __grid_c
 #pragma unroll
             for (int j = 0; j < A; ++j) dmu[j] = 0.0f;
             if (valid) {
-                const int64_t row = (int64_t)t * N + n;
+                const int64_t row = (int64_t)t_own * N + n;
                 if (a.head == HEAD_VALUE) {
                     const float err = mu[0] - a.target[row];       // ppo.py:168-169 MSELoss
                     s_obj += (double)err * err;
@@ -190,7 +204,7 @@ __global__ void __launch_bounds__(TileCfg<CFG>::NT) update_kernel(const __grid_c
                     bool have_act = a.act != nullptr;
 #pragma unroll
                     for (int j = 0; j < A; ++j) {
-                        av[j] = have_act ? a.act[((int64_t)t * A + j) * N + n] : mu[j];
+                        av[j] = have_act ? a.act[((int64_t)t_own * A + j) * N + n] : mu[j];
                         const float z = (av[j] - mu[j]) * a.inv_sd[j];
                         m2 += z * z;
                     }
@@ -199,7 +213,7 @@ __global__ void __launch_bounds__(TileCfg<CFG>::NT) update_kernel(const __grid_c
                         if (a.out_logp) a.out_logp[row] = lp;
 #pragma unroll
                         for (int j = 0; j < A; ++j)
-                            if (a.out_mu) a.out_mu[((int64_t)t * A + j) * N + n] = mu[j];
+                            if (a.out_mu) a.out_mu[((int64_t)t_own * A + j) * N + n] = mu[j];
                     } else {
                         const float adv = a.adv[row], olp = a.oldlp[row];
                         const float ratio = expf(lp - olp);          // grpo.py:125 / ppo.py:160
@@ -382,7 +396,7 @@ static int run_grad(tg_ctx *ctx, UpdArgs &a, const float *params, float *out_gra
     int rc = tg_pack_weights(ctx, a.lay, params, st);
     if (rc) return rc;
     a.packed = ctx->packed;
-    if (a.len != nullptr) {                      // ragged episodes: walk the samples in length order
+    if (a.len != nullptr && a.sidx == nullptr) {  // ragged episodes: walk the samples in length order
         rc = tg_len_order(ctx, a.N, a.T, a.len, st);
         if (rc) return rc;
         a.perm = ctx->perm;
@@ -439,6 +453,47 @@ extern "C" int tg_policy_grad(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int
         TG_CUDA(cudaGetLastError());
         return TG_OK;
     }
+    return run_grad(ctx, a, params, out_grad, out_stats, workspace, (cudaStream_t)stream);
+}
+
+// Minibatch forms (PPO with batch_size != None, algorithms/ppo.py:147-183): the gradient of the same
+// objective over an explicit list of samples.  Always the FP32-pipe kernel (a minibatch is a few tiles).
+extern "C" int tg_policy_grad_batch(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, const float *obs,
+                                    const float *act, const float *adv, const float *old_logp,
+                                    const int64_t *sample_ids, int64_t n_samples, const float *params,
+                                    const float *cov_diag, float eps_clip, float scale, float kl_coef, float *out_grad,
+                                    float *out_stats, void *workspace, void *stream) {
+    TG_REQUIRE(ctx && mlp && obs && act && adv && old_logp && sample_ids && params && cov_diag && out_grad && workspace,
+               TG_ERR_ARG, "tg_policy_grad_batch: null argument");
+    TG_REQUIRE(N > 0 && T > 0 && n_samples > 0, TG_ERR_SHAPE, "tg_policy_grad_batch: N, T, n_samples must be positive");
+    UpdArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = tg_build_layout(mlp, true, &a.lay, ctx->smem_optin);
+    if (rc) return rc;
+    rc = fill_gauss(a, cov_diag, a.lay.A);
+    if (rc) return rc;
+    a.N = N; a.T = T; a.head = HEAD_POLICY;
+    a.obs = obs; a.act = act; a.adv = adv; a.oldlp = old_logp;
+    a.sidx = sample_ids; a.n_sidx = n_samples;
+    a.eps_clip = eps_clip; a.scale = scale; a.kl_scale = kl_coef;
+    return run_grad(ctx, a, params, out_grad, out_stats, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int tg_value_grad_batch(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, const float *obs,
+                                   const float *target, const int64_t *sample_ids, int64_t n_samples,
+                                   const float *params, float scale, float *out_grad, float *out_stats,
+                                   void *workspace, void *stream) {
+    TG_REQUIRE(ctx && mlp && obs && target && sample_ids && params && out_grad && workspace, TG_ERR_ARG,
+               "tg_value_grad_batch: null argument");
+    TG_REQUIRE(N > 0 && T > 0 && n_samples > 0, TG_ERR_SHAPE, "tg_value_grad_batch: N, T, n_samples must be positive");
+    TG_REQUIRE(mlp->dims[mlp->n_layers] == 1, TG_ERR_SHAPE, "critic output dim must be 1");
+    UpdArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = tg_build_layout(mlp, true, &a.lay, ctx->smem_optin);
+    if (rc) return rc;
+    a.N = N; a.T = T; a.head = HEAD_VALUE;
+    a.obs = obs; a.target = target; a.scale = scale;
+    a.sidx = sample_ids; a.n_sidx = n_samples;
     return run_grad(ctx, a, params, out_grad, out_stats, workspace, (cudaStream_t)stream);
 }
 

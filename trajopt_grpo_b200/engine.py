@@ -288,6 +288,56 @@ def policy_grad(dims, activation, params, cov_diag, obs, act, adv, old_logp, len
     return grad, stats
 
 
+def policy_grad_batch(dims, activation, params, cov_diag, obs, act, adv, old_logp, sample_ids, eps_clip, scale,
+                      kl_scale=0.0, out_grad=None):
+    """tg_policy_grad_batch: the clipped-surrogate gradient over the samples listed in `sample_ids`
+    (int64 flat slot ids t*N + n)."""
+    lib = L.load()
+    T, O, N = obs.shape
+    A = act.shape[1]
+    _need(obs, torch.float32, "obs")
+    _need(act, torch.float32, "act", (T, A, N))
+    _need(adv, torch.float32, "adv", (T, N))
+    _need(old_logp, torch.float32, "old_logp", (T, N))
+    _need(sample_ids, torch.int64, "sample_ids")
+    _need(params, torch.float32, "params")
+    dev = obs.device
+    mcfg = L.mlp_cfg(dims, activation)
+    grad = torch.empty_like(params) if out_grad is None else out_grad
+    stats = torch.empty((4,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace("grad", lib.tg_policy_grad_workspace_bytes(L.ctx(dev), C.byref(mcfg)), dev)
+        rc = lib.tg_policy_grad_batch(L.ctx(dev), C.byref(mcfg), N, T, L.ptr(obs), L.ptr(act), L.ptr(adv),
+                                      L.ptr(old_logp), L.ptr(sample_ids), sample_ids.numel(), L.ptr(params),
+                                      L.cov_array(cov_diag), float(eps_clip), float(scale), float(kl_scale),
+                                      L.ptr(grad), L.ptr(stats), L.ptr(ws), L.stream_ptr())
+    L.check(rc, "tg_policy_grad_batch")
+    _count(3)
+    return grad, stats
+
+
+def value_grad_batch(dims, activation, params, obs, target, sample_ids, scale, out_grad=None):
+    """tg_value_grad_batch: critic MSE gradient over the listed samples."""
+    lib = L.load()
+    T, O, N = obs.shape
+    _need(obs, torch.float32, "obs")
+    _need(target, torch.float32, "target", (T, N))
+    _need(sample_ids, torch.int64, "sample_ids")
+    _need(params, torch.float32, "params")
+    dev = obs.device
+    mcfg = L.mlp_cfg(dims, activation)
+    grad = torch.empty_like(params) if out_grad is None else out_grad
+    stats = torch.empty((4,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace("grad", lib.tg_policy_grad_workspace_bytes(L.ctx(dev), C.byref(mcfg)), dev)
+        rc = lib.tg_value_grad_batch(L.ctx(dev), C.byref(mcfg), N, T, L.ptr(obs), L.ptr(target), L.ptr(sample_ids),
+                                     sample_ids.numel(), L.ptr(params), float(scale), L.ptr(grad), L.ptr(stats),
+                                     L.ptr(ws), L.stream_ptr())
+    L.check(rc, "tg_value_grad_batch")
+    _count(3)
+    return grad, stats
+
+
 def value_grad(dims, activation, params, obs, target, length, scale, out_grad=None):
     """tg_value_grad -> (grad [n_params], stats[0] = sum of squared errors, stats[1] = n_valid)."""
     lib = L.load()
