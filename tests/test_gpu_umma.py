@@ -70,7 +70,8 @@ def _policy(rng, dims):
 
 
 @pytest.mark.parametrize("kind,hidden", [(1, [64, 64]), (3, [64, 64]), (2, [64, 64, 64]), (0, [64, 64]),
-                                         (2, [128, 128]), (3, [128, 128]), (1, [128, 128]), (0, [128, 128])])
+                                         (2, [128, 128]), (3, [128, 128]), (1, [128, 128]), (0, [128, 128]),
+                                         (3, [256, 256]), (2, [256, 256]), (1, [256, 256]), (0, [256, 256])])
 def test_rollout_tensor_core_path_matches_fp32_path_and_oracle(kind, hidden):
     import restate as R
     from trajopt_grpo_b200 import engine as E

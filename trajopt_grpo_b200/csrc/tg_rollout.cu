@@ -20,6 +20,13 @@
 #include "tg_mlp.cuh"
 #include "tg_umma.cuh"
 
+// tg_rollout_tc256.cu
+bool tg_tc256_eligible(const tg_mlp_cfg *mlp);
+int tg_rollout_tc256(tg_ctx *ctx, const tg_env_cfg *env, const EnvParams &ep, const tg_mlp_cfg *mlp, int precision,
+                     int64_t N, const void *init_state, const float *params, const float *cov_diag, const float *noise,
+                     uint64_t seed, int64_t env_offset, float *out_obs, float *out_act, float *out_rew, float *out_logp,
+                     int32_t *out_len, float *out_ret, cudaStream_t st);
+
 struct RolloutArgs {
     EnvParams env;
     tg_mlp_layout lay;
@@ -648,7 +655,10 @@ extern "C" int tg_rollout(tg_ctx *ctx, const tg_env_cfg *env, const tg_mlp_cfg *
                mlp->dims[mlp->n_layers > 0 ? mlp->n_layers : 0], O, A);
     cudaStream_t st = (cudaStream_t)stream;
     TG_CUDA(cudaSetDevice(ctx->device));
-    // ---- tensor-core path (3xTF32 tcgen05) for eligible policies
+    // ---- tensor-core paths (3xTF32 tcgen05) for eligible policies
+    if (tg_tc256_eligible(mlp) && ctx->math_mode != TG_MATH_FP32)      // 256-wide: weights streamed from L2
+        return tg_rollout_tc256(ctx, env, a.env, mlp, precision, N, init_state, params, cov_diag, noise, seed, env_offset,
+                                out_obs, out_act, out_rew, out_logp, out_len, out_ret, st);
     const bool tc_ok = tg_tc_eligible(mlp);
     TG_REQUIRE(ctx->math_mode != TG_MATH_3XTF32 || tc_ok, TG_ERR_UNSUPPORTED,
                "TG_MATH_3XTF32 requested but the policy shape is not eligible (>= 2 hidden layers of equal width 64 or 128)");
