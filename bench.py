@@ -316,6 +316,11 @@ def run_ours(args, w):
     k2_ms = float(np.mean(k2))
     clock_info = clocks.stop() if rank == 0 else None
 
+    # env-steps a rollout tile actually executes: a tile of 128 consecutive envs runs until its longest episode ends
+    ln_t = r.len.to(torch.int64)
+    pad_n = (-ln_t.numel()) % 128
+    tile_max = torch.nn.functional.pad(ln_t, (0, pad_n)).view(-1, 128).max(dim=1).values
+    k1_exec_steps = float(tile_max.sum().item()) * 128.0
     if args.device_only:                          # short run for ncu: no e2e / CPU legs
         if rank == 0 and os.environ.get("TG_TIMELINE"):
             print("gpu e0/e3 ms since t0:", [(round(t0.elapsed_time(a), 2), round(t0.elapsed_time(d), 2))
@@ -325,7 +330,8 @@ def run_ours(args, w):
         if rank == 0:
             print(json.dumps({"device_only": True, "value": value, "ms_per_step": ms_total / args.steps,
                               "k1_ms": k1_ms, "k2_ms": k2_ms, "k3_ms": k3_ms, "gpu_launches": launches,
-                              "valid_frac": valid_per_step_rank / (N * T),
+                              "valid_frac": valid_per_step_rank / (N * T), "k1_executed_frac": k1_exec_steps / (N * T),
+                              "k1_executed_tflops": 2.0 * P * k1_exec_steps / (k1_ms * 1e-3) / 1e12,
                               "rollout_env_steps_per_s": valid_per_step_rank / (k1_ms * 1e-3),
                               "k1_tflops": k1_flops_of(P, valid_per_step_rank, k1_ms),
                               "k3_tflops": 6.0 * P * valid_per_step_rank / (k3_ms * 1e-3) / 1e12}))
