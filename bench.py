@@ -394,8 +394,8 @@ def run_ours(args, w):
             "bound": "tensor", "achieved": k3_tf, "peak": bf16_peak, "unit": "TFLOP/s", "frac": k3_tf / bf16_peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else
                            "fallback of /opt/skills/guides/B200_PROFILING.md (MEASURED_PEAKS.json absent)",
-            "traffic": 320.6e6 if w is WORKLOADS["pendulum"] else None,
-            "traffic_source": "profiles/r1b_ncu_details_tensor_core_kernels.csv: dram read 315.3 MB + write 5.3 MB "
+            "traffic": 324.0e6 if w is WORKLOADS["pendulum"] else None,
+            "traffic_source": "profiles/r1d_ncu_details_pendulum_kernels.csv: dram read 315.5 MB + write 8.5 MB "
                               "per launch (algorithmic: 315 MB of obs+act+adv+old logp)",
             "achieved_note": "algorithmic FLOPs (6*P per valid step, SURVEY 8d) / CUDA-event time of the launch",
             "frac_of_3xtf32_ceiling": k3_tf / (bf16_peak / 6.0),
@@ -411,10 +411,15 @@ def run_ours(args, w):
             "frac_of_measured_bf16_tensor_peak": k3_tf / bf16_peak,
             "ms_per_launch": k3_ms, "flops_per_launch": k3_flops,
         }
+    hid = w["hidden"]
+    k1_tc = len(hid) >= 2 and len(set(hid)) == 1 and hid[0] in (64, 128) or hid == [256, 256]   # tg_rollout's routing
+    k1_name = {64: "rollout_tc_kernel", 128: "rollout_tc2_kernel", 256: "rollout_tc256_kernel"}.get(hid[0]) if k1_tc \
+        else "rollout_kernel"
     roofline["others"] = {
-        ("rollout_tc_kernel" if tc else "rollout_kernel"): {
-            "bound": "tensor" if tc else "fp32-fma", "ms": k1_ms, "achieved_tflops": k1_tf,
-            "frac": k1_tf / (bf16_peak if tc else fp32_peak),
+        k1_name: {
+            "bound": "tensor" if k1_tc else "fp32-fma", "ms": k1_ms, "achieved_tflops": k1_tf,
+            "executed_tflops": 2.0 * P * k1_exec_steps / (k1_ms * 1e-3) / 1e12,
+            "frac": k1_tf / (bf16_peak if k1_tc else fp32_peak),
             "frac_of_measured_fp32_fma_peak": k1_tf / fp32_peak,
             "traj_write_gbs": 4.0 * (O + A + 2) * N * T / (k1_ms * 1e-3) / 1e9},
         "adv_grpo_kernel": {"bound": "hbm", "ms": k2_ms, "achieved_gbs": 8.0 * N * T / (k2_ms * 1e-3) / 1e9,
