@@ -105,6 +105,42 @@ def test_rollout_tensor_core_path_matches_fp32_path_and_oracle(kind, hidden):
     assert np.abs(a32 - atc).max() <= 2e-5 * max(1.0, np.abs(a32).max())
 
 
+@pytest.mark.parametrize("hidden,act_name,N", [([256, 256], "Tanh", 129), ([128, 128], "Sigmoid", 1), ([256, 256], "Sigmoid", 257)])
+def test_rollout_wide_tensor_core_kernels_other_activations_and_ragged_tiles(hidden, act_name, N):
+    """The 128- and 256-wide tensor-core rollout kernels with non-ReLU activations and env counts that leave
+    a partial last tile, against the FP32-pipe kernel (first step: no accumulated drift) and bit-exact
+    determinism of repeated launches."""
+    import restate as R
+    from trajopt_grpo_b200 import engine as E
+    kind = 3
+    rng = np.random.default_rng(N)
+    O, A = R.OBS_DIM[kind], R.ACT_DIM[kind]
+    dims = [O] + hidden + [A]
+    Ws, bs, params = _policy(rng, dims)
+    T = 6
+    init = R.reset_states(kind, N, rng)
+    noise = rng.standard_normal((T, N, A)).astype(np.float32)
+    nz = torch.from_numpy(np.ascontiguousarray(noise.transpose(0, 2, 1))).cuda()
+    s0 = torch.from_numpy(init.T.copy()).cuda().float()
+    outs = {}
+    try:
+        for mode in ("fp32", "3xtf32", "3xtf32"):
+            E.set_math(mode)
+            out = E.rollout(kind, T, 0.02, dims, act_name, params, [0.3] * A, s0, noise=nz)
+            torch.cuda.synchronize()
+            outs.setdefault(mode, []).append(out)
+    finally:
+        E.set_math("auto")
+    a, b = outs["3xtf32"]
+    for k in ("obs", "act", "rew", "logp", "len", "ret"):
+        assert torch.equal(a[k], b[k]), k
+    f = outs["fp32"][0]
+    assert torch.equal(f["len"], a["len"])
+    d = (f["act"][0] - a["act"][0]).abs().max().item()
+    assert d <= 2e-5 * max(1.0, f["act"][0].abs().max().item()), d
+    np.testing.assert_allclose(a["obs"].cpu().numpy(), f["obs"].cpu().numpy(), rtol=2e-3, atol=2e-3)
+
+
 def test_math_mode_3xtf32_rejects_ineligible_shape():
     from trajopt_grpo_b200 import engine as E
     from trajopt_grpo_b200._lib import EngineError
@@ -117,15 +153,18 @@ def test_math_mode_3xtf32_rejects_ineligible_shape():
         E.set_math("auto")
 
 
-@pytest.mark.parametrize("kind,act_name", [(1, "ReLU"), (0, "Tanh"), (2, "ReLU"), (3, "Sigmoid")])
-def test_policy_grad_tensor_core_path_matches_fp32_path_and_oracle(kind, act_name):
-    """tg_policy_grad on the tcgen05 path (O-64-64-A) vs the FP32-pipe path and torch float64 autograd,
+@pytest.mark.parametrize("kind,act_name,width", [(1, "ReLU", 64), (0, "Tanh", 64), (2, "ReLU", 64), (3, "Sigmoid", 64),
+                                                 (2, "ReLU", 128), (3, "ReLU", 256), (1, "Tanh", 128), (0, "Sigmoid", 256),
+                                                 (3, "Tanh", 128), (2, "Sigmoid", 256)])
+def test_policy_grad_tensor_core_path_matches_fp32_path_and_oracle(kind, act_name, width):
+    """tg_policy_grad on the tcgen05 paths (O-64-64-A fused kernel; O-128-128-A and O-256-256-A streamed two-kernel
+    path) vs the FP32-pipe path and torch float64 autograd,
     ragged episode lengths, two updates' worth of ratio != 1 (old weights differ from current)."""
     import restate as R
     from trajopt_grpo_b200 import engine as E
     rng = np.random.default_rng(10 + kind)
     O, A = R.OBS_DIM[kind], R.ACT_DIM[kind]
-    dims = [O, 64, 64, A]
+    dims = [O, width, width, A]
     Ws, bs, params = _policy(rng, dims)
     oldWs = [w + 0.02 * rng.standard_normal(w.shape).astype(np.float32) for w in Ws]
     G, Eps, T = 5, 52, 9                       # 260 envs: three tiles per step, the last one partial

@@ -46,6 +46,8 @@ extern "C" int tg_ctx_create(int device, tg_ctx **out) {
         const char *e = getenv("TG_ROLLOUT_TC2");     // diagnostics only (A/B of the two width-64 rollout kernels)
         c->rollout_tc2 = (e && e[0] == '1') ? 1 : 0;
     }
+    c->scratch = nullptr;
+    c->scratch_cap = 0;
     c->order_buf = nullptr;
     c->order_cap = 0;
     c->perm = c->cnt = nullptr;
@@ -59,6 +61,7 @@ extern "C" void tg_ctx_destroy(tg_ctx *ctx) {
     if (ctx->packed) cudaFree(ctx->packed);
     if (ctx->packed_tc) cudaFree(ctx->packed_tc);
     if (ctx->order_buf) cudaFree(ctx->order_buf);
+    if (ctx->scratch) cudaFree(ctx->scratch);
     delete ctx;
 }
 

@@ -40,6 +40,8 @@ struct tg_ctx {
     int rollout_tc2;   // diagnostics: route width-64 rollouts to the two-threads-per-env kernel too
     // length order of the rollout being updated (tg_order.cu): env indices sorted by episode length,
     // longest first, and the number of live envs per step; device, owned by the ctx
+    void *scratch;     // HBM scratch of the wide tensor-core update (tg_update_tcw.cu), device
+    size_t scratch_cap;
     void *order_buf;
     size_t order_cap;
     int32_t *perm, *cnt;
@@ -114,6 +116,12 @@ struct tg_tc_layout {
 bool tg_tc_eligible(const tg_mlp_cfg *mlp);
 int tg_build_tc_layout(const tg_mlp_cfg *mlp, tg_tc_layout *out, bool with_backward = false);
 int tg_pack_weights_tc(tg_ctx *ctx, const tg_tc_layout &lay, const float *params, cudaStream_t st);
+// wide (128 / 256) tensor-core update, two streamed kernels per batch of tiles (tg_update_tcw.cu)
+bool tg_update_tcw_shape_built(const tg_mlp_cfg *mlp);
+int tg_policy_grad_tcw(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, const float *obs, const float *act,
+                       const float *adv, const float *old_logp, const int32_t *len, const float *params,
+                       const float *inv_sd, const float *inv_var, float log_norm, float eps_clip, float scale,
+                       float kl_scale, float *gpart, double *spart, int grid, cudaStream_t st);
 // tensor-core update kernel (tg_update_tc.cu)
 bool tg_update_tc_eligible(const tg_mlp_cfg *mlp);
 int tg_update_tc_grid(const tg_ctx *ctx);

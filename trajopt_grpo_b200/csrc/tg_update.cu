@@ -432,7 +432,23 @@ extern "C" int tg_policy_grad(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int
     a.N = N; a.T = T; a.head = HEAD_POLICY;
     a.obs = obs; a.act = act; a.adv = adv; a.oldlp = old_logp; a.len = len;
     a.eps_clip = eps_clip; a.scale = scale; a.kl_scale = kl_coef;
-    // ---- tensor-core path (3xTF32 tcgen05) for eligible policies
+    // ---- tensor-core paths (3xTF32 tcgen05) for eligible policies
+    if (tg_update_tcw_shape_built(mlp) && ctx->math_mode != TG_MATH_FP32) {      // 128 / 256 wide: streamed, two kernels
+        cudaStream_t st = (cudaStream_t)stream;
+        TG_CUDA(cudaSetDevice(ctx->device));
+        const int grid = ctx->sm_count;
+        const size_t gbytes = (size_t)grid * a.lay.n_params * sizeof(float);
+        float *gpart = reinterpret_cast<float *>(workspace);
+        double *spart = reinterpret_cast<double *>(reinterpret_cast<char *>(workspace) + ((gbytes + 255) / 256) * 256);
+        TG_CUDA(cudaMemsetAsync(gpart, 0, ((gbytes + 255) / 256) * 256 + (size_t)grid * 4 * sizeof(double), st));
+        rc = tg_policy_grad_tcw(ctx, mlp, N, T, obs, act, adv, old_logp, len, params, a.inv_sd, a.inv_var, a.log_norm,
+                                eps_clip, scale, kl_coef, gpart, spart, grid, st);
+        if (rc) return rc;
+        grad_reduce_kernel<<<(unsigned)((a.lay.n_params + 255) / 256), 256, 0, st>>>(grid, a.lay.n_params, gpart, spart,
+                                                                                     out_grad, out_stats);
+        TG_CUDA(cudaGetLastError());
+        return TG_OK;
+    }
     const bool tc_ok = tg_update_tc_eligible(mlp);
     TG_REQUIRE(ctx->math_mode != TG_MATH_3XTF32 || tc_ok, TG_ERR_UNSUPPORTED,
                "TG_MATH_3XTF32 requested but the policy shape has no tensor-core update kernel "

@@ -1,0 +1,921 @@
+// K3 on the tensor cores for WIDE policies (obs -> W -> W -> act, W = 128 or 256; BASELINE cfg 3/4/5).
+//
+// The three W x W GEMMs of a 128-sample tile (forward, backward-data, weight-gradient) cannot share one SM's
+// memories: the weights in both operand layouts are 2 x 2W^2 x 4 bytes (512 KB..1 MB at W = 256) and the
+// weight-gradient operands -- the tile's H1 and dZ2 in MN-major form, hi and lo -- another 4 x 128 x W x 4.
+// So the update is two kernels per batch of tiles, both fed by streams:
+//
+//   kernel A  (update_tcw_fwdbwd_kernel)  forward + objective + backward-data for every tile of the batch.
+//       The weights are STREAMED from L2 every tile through a 4-stage TMA ring (K-major chunks for the
+//       forward, MN-major chunks for the backward), exactly like the 256-wide rollout kernel; activations go
+//       registers -> tensor memory as the A operand (K halves at W = 256).  The first Linear runs on the
+//       tensor core too (obs hi/lo + ones column carrying the bias).  Per tile the kernel leaves in an HBM
+//       scratch, already hi/lo split and in the operand layout of kernel B:  H1, dZ2, dZ1 (MN-major
+//       SW128_32B, 8-sample sub-blocks) and [x, 1] (K-major).  dWo, dbo, db1 (one column sum per column over
+//       the tile) stay on register butterflies here.
+//   kernel B  (update_tcw_wgrad_kernel)   split-K weight-gradient GEMMs over the batch's samples:
+//       dW1[half] += dZ2[:, half]^T . H1   and   [dW0 | db0][half] += dZ1[:, half]^T . [x, 1],
+//       operands streamed from the scratch by TMA (8 samples per stage), accumulators persistent in tensor
+//       memory for all tiles of the launch, added to the CTA-private gradient copy at the end.  One launch
+//       per 128-row half of the outputs (two at W = 256).  HBM-bound by construction (about 8-12 KB per sample).
+//
+// Tiles are enumerated in length order (tg_order.cu): tile k of the compact list is (step t, sorted
+// positions 128*blk ..), found by binary search in the per-step prefix of live tiles; k beyond the live
+// total is a no-op, so the host launches ceil(upper bound / batch) batches without reading anything back.
+#include <math.h>
+
+#include "tg_umma.cuh"
+
+#define TCW_STAGES 4
+#define TCW_BAR_L1 5
+#define TCW_BAR_K0 6
+#define TCW_BAR_K1 7
+
+struct TcwLayout {
+    int O, OKP, A, act, W;
+    int64_t w0hi, w0lo, b1, wo, bo;      // offsets (floats) in the resident block
+    int64_t resident;                     // floats, multiple of 256
+    int64_t chunks_f, chunks_b;           // forward (K-major) / backward (MN-major) chunk streams
+    int64_t chunk_floats;                 // W * 32
+    int64_t total;
+    int64_t flat_w[3], n_params;
+};
+
+struct TcwScratch {                       // per-tile byte strides / bases inside the HBM scratch
+    unsigned char *base;
+    int64_t tile_bytes;                   // all arrays of one tile
+    int64_t arr_bytes;                    // one of H1h,H1l,Z2h,Z2l,Z1h,Z1l per tile = 16 sub-blocks * W/32 KB
+    int64_t x_bytes;                      // one of Xh, Xl per tile = 16 * OKP * 32
+};
+// array order inside a tile: H1h, H1l, Z2h, Z2l, Z1h, Z1l, Xh, Xl
+
+struct TcwArgs {
+    TcwLayout lay;
+    TcwScratch sc;
+    int64_t N;
+    int T;
+    const float *obs, *act, *adv, *oldlp;
+    const int32_t *perm, *cnt;
+    const int64_t *tstart;                // [T+1] prefix of live tiles per step
+    int64_t k_begin, k_count;             // this batch: compact tiles [k_begin, k_begin + k_count)
+    const float *packed;
+    float inv_sd[TG_MAX_ACT], inv_var[TG_MAX_ACT], log_norm;
+    float eps_clip, scale, kl_scale;
+    float *gpart;                         // [grid][n_params], accumulated (+=) across launches
+    double *spart;                        // [grid][4], accumulated
+    int half;                             // kernel B: which 128-row half of the outputs
+};
+
+bool tg_update_tcw_eligible(const tg_mlp_cfg *mlp) {
+    if (!mlp || mlp->n_layers != 3) return false;
+    const int W = mlp->dims[1];
+    return (W == 128 || W == 256) && mlp->dims[2] == W && mlp->dims[0] >= 1 && mlp->dims[0] <= 23 &&
+           (mlp->dims[3] == 1 || mlp->dims[3] == 2 || mlp->dims[3] == 4) && mlp->activation >= 0 && mlp->activation <= 2;
+}
+
+static void build_tcw_layout(const tg_mlp_cfg *mlp, TcwLayout *L) {
+    memset(L, 0, sizeof(*L));
+    L->O = mlp->dims[0];
+    L->OKP = (L->O + 1 + 7) / 8 * 8;
+    L->A = mlp->dims[3];
+    L->act = mlp->activation;
+    L->W = mlp->dims[1];
+    const int W = L->W;
+    int64_t off = 0;
+    L->w0hi = off; off += (int64_t)W * L->OKP;
+    L->w0lo = off; off += (int64_t)W * L->OKP;
+    L->b1 = off; off += W;
+    L->wo = off; off += (int64_t)L->A * W;
+    L->bo = off; off += 4;
+    L->resident = (off + 255) / 256 * 256;
+    L->chunk_floats = (int64_t)W * 32;
+    L->chunks_f = L->resident;
+    L->chunks_b = L->chunks_f + (int64_t)(2 * W / 32) * L->chunk_floats;
+    L->total = L->chunks_b + (int64_t)(2 * W / 32) * L->chunk_floats;
+    int64_t flat = 0;
+    for (int l = 0; l < 3; ++l) {
+        L->flat_w[l] = flat;
+        flat += (int64_t)mlp->dims[l] * mlp->dims[l + 1] + mlp->dims[l + 1];
+    }
+    L->n_params = flat;
+}
+
+TG_D float tcw_hi(float w) {
+    uint32_t hb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));
+    return __uint_as_float(hb & 0xffffe000u);
+}
+TG_D void tcw_core_invert(int C, int64_t idx, int *r, int *c) {
+    const uint32_t b = (uint32_t)idx * 4u;
+    const uint32_t group = (uint32_t)(C >> 2) * 128u;
+    const uint32_t rr = b % group;
+    *r = (int)(b / group) * 8 + (int)((rr % 128u) >> 4);
+    *c = (int)(rr / 128u) * 4 + (int)((rr & 15u) >> 2);
+}
+
+__global__ void pack_tcw_kernel(TcwLayout L, const float *__restrict__ params, float *__restrict__ packed) {
+    const int W = L.W;
+    const float *W0 = params + L.flat_w[0], *b0 = W0 + (int64_t)W * L.O;
+    const float *W1 = params + L.flat_w[1], *b1 = W1 + (int64_t)W * W;
+    const float *Wo = params + L.flat_w[2], *bo = Wo + (int64_t)L.A * W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L.total; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = 0.0f;
+        if (i < L.b1) {
+            const bool lo = i >= L.w0lo;
+            int n, c;
+            tcw_core_invert(L.OKP, i - (lo ? L.w0lo : L.w0hi), &n, &c);
+            const float w = c < L.O ? W0[(int64_t)n * L.O + c] : (c == L.O ? b0[n] : 0.0f);
+            const float h = tcw_hi(w);
+            v = lo ? (w - h) : h;
+        } else if (i < L.wo) {
+            v = b1[i - L.b1];
+        } else if (i < L.bo) {
+            v = Wo[i - L.wo];
+        } else if (i < L.bo + L.A) {
+            v = bo[i - L.bo];
+        } else if (i >= L.chunks_f && i < L.chunks_b) {
+            // forward: chunk = (K-chunk kc, hi/lo); [W rows n][32 k] K-major core-matrix layout
+            const int64_t j = i - L.chunks_f;
+            const int chunk = (int)(j / L.chunk_floats);
+            const bool lo = (chunk & 1) != 0;
+            const int kc = chunk >> 1;
+            int n, kk;
+            tcw_core_invert(32, j % L.chunk_floats, &n, &kk);
+            const float w = W1[(int64_t)n * W + kc * 32 + kk];
+            const float h = tcw_hi(w);
+            v = lo ? (w - h) : h;
+        } else if (i >= L.chunks_b) {
+            // backward: chunk = (32 out-rows kc, hi/lo); [32 rows out][W cols in] MN-major SW128_32B (invert mn32_offset)
+            const int64_t j = i - L.chunks_b;
+            const int chunk = (int)(j / L.chunk_floats);
+            const bool lo = (chunk & 1) != 0;
+            const int kc = chunk >> 1;
+            const uint32_t b = (uint32_t)(j % L.chunk_floats) * 4u;
+            const uint32_t blk = b / (32u * 128u), rr = b % (32u * 128u);
+            const int r = (int)(rr / 128u);
+            const int ch = (int)((rr % 128u) >> 5) ^ (r & 3);
+            const int c = (int)blk * 32 + ch * 8 + (int)((rr & 31u) >> 2);
+            const float w = W1[(int64_t)(kc * 32 + r) * W + c];
+            const float h = tcw_hi(w);
+            v = lo ? (w - h) : h;
+        }
+        packed[i] = v;
+    }
+}
+
+// tstart[t] = number of live tiles of steps < t (tile = 128 sorted positions), tstart[T] = total
+__global__ void tcw_tstart_kernel(int T, const int32_t *__restrict__ cnt, int64_t *__restrict__ tstart) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int64_t s = 0;
+        for (int t = 0; t < T; ++t) {
+            tstart[t] = s;
+            s += (cnt[t] + 127) / 128;
+        }
+        tstart[T] = s;
+    }
+}
+
+// compact tile k -> (t, blk); false when k is beyond the live tiles
+TG_D bool tcw_tile_of(const int64_t *__restrict__ tstart, int T, int64_t k, int *t, int *blk) {
+    if (k >= tstart[T]) return false;
+    int lo = 0, hi = T - 1;             // largest t with tstart[t] <= k
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (tstart[mid] <= k) lo = mid;
+        else hi = mid - 1;
+    }
+    *t = lo;
+    *blk = (int)(k - tstart[lo]);
+    return true;
+}
+
+TG_D void tcw_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+TG_D void tcw_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// butterfly column sum: v[0..32) per lane -> the warp's sum of column `lane`
+template <int HALF, int OFF> TG_D void tcw_colsum_step(float *v, int lane) {
+    const bool up = (lane & OFF) != 0;
+#pragma unroll
+    for (int j = 0; j < HALF; ++j) {
+        const float send = up ? v[j] : v[j + HALF];
+        const float keep = up ? v[j + HALF] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+    }
+}
+TG_D float tcw_colsum32(float *v, int lane) {
+    tcw_colsum_step<16, 16>(v, lane);
+    tcw_colsum_step<8, 8>(v, lane);
+    tcw_colsum_step<4, 4>(v, lane);
+    tcw_colsum_step<2, 2>(v, lane);
+    tcw_colsum_step<1, 1>(v, lane);
+    return v[0];
+}
+
+// byte offset of (sample s, column c) inside one MN-major scratch array of a tile (8-sample sub-blocks)
+template <int W> TG_D uint32_t tcw_sc_off(int s, int c) {
+    const int r = s & 7;
+    return (uint32_t)(s >> 3) * (uint32_t)(W / 32 * 1024) + (uint32_t)(c >> 5) * 1024u + (uint32_t)r * 128u +
+           (uint32_t)((((c & 31) >> 3) ^ (r & 3)) << 5) + (uint32_t)(c & 7) * 4u;
+}
+// 32 consecutive columns (column block cbk) of sample s: hi/lo split, written to two scratch arrays (MN-major
+// sub-block layout) and -- when TM -- also to the tensor-memory A operand (hi at tm_hi, lo at tm_lo), 16 columns
+// at a time so that only 32 split values are live.
+template <int W, bool TM>
+TG_D void tcw_emit32(unsigned char *arr_hi, unsigned char *arr_lo, int s, int cbk, const float *v, uint32_t tm_hi,
+                     uint32_t tm_lo) {
+    const int r = s & 7;
+    unsigned char *ph = arr_hi + (size_t)(s >> 3) * (W / 32 * 1024) + (size_t)cbk * 1024 + (size_t)r * 128;
+    unsigned char *pl = arr_lo + (size_t)(s >> 3) * (W / 32 * 1024) + (size_t)cbk * 1024 + (size_t)r * 128;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+            hi[jj] = tf32_hi(v[hh * 16 + jj]);
+            lo[jj] = v[hh * 16 + jj] - hi[jj];
+        }
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+            const int i = hh * 4 + i4;
+            const uint32_t o = (uint32_t)((((i >> 1) ^ (r & 3)) << 5) + (i & 1) * 16);
+            *reinterpret_cast<float4 *>(ph + o) = make_float4(hi[4 * i4], hi[4 * i4 + 1], hi[4 * i4 + 2], hi[4 * i4 + 3]);
+            *reinterpret_cast<float4 *>(pl + o) = make_float4(lo[4 * i4], lo[4 * i4 + 1], lo[4 * i4 + 2], lo[4 * i4 + 3]);
+        }
+        if (TM) {
+            tmem_st16(tm_hi + (uint32_t)(hh * 16), hi);
+            tmem_st16(tm_lo + (uint32_t)(hh * 16), lo);
+        }
+    }
+}
+// the same 32 columns read back from the scratch (this thread wrote them) into the tensor-memory A operand
+template <int W>
+TG_D void tcw_reload32(const unsigned char *arr_hi, const unsigned char *arr_lo, int s, int cbk, uint32_t tm_hi,
+                       uint32_t tm_lo) {
+    const int r = s & 7;
+    const unsigned char *ph = arr_hi + (size_t)(s >> 3) * (W / 32 * 1024) + (size_t)cbk * 1024 + (size_t)r * 128;
+    const unsigned char *pl = arr_lo + (size_t)(s >> 3) * (W / 32 * 1024) + (size_t)cbk * 1024 + (size_t)r * 128;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+            const int i = hh * 4 + i4;
+            const uint32_t o = (uint32_t)((((i >> 1) ^ (r & 3)) << 5) + (i & 1) * 16);
+            const float4 a4 = *reinterpret_cast<const float4 *>(ph + o);
+            const float4 b4 = *reinterpret_cast<const float4 *>(pl + o);
+            hi[4 * i4] = a4.x; hi[4 * i4 + 1] = a4.y; hi[4 * i4 + 2] = a4.z; hi[4 * i4 + 3] = a4.w;
+            lo[4 * i4] = b4.x; lo[4 * i4 + 1] = b4.y; lo[4 * i4 + 2] = b4.z; lo[4 * i4 + 3] = b4.w;
+        }
+        tmem_st16(tm_hi + (uint32_t)(hh * 16), hi);
+        tmem_st16(tm_lo + (uint32_t)(hh * 16), lo);
+    }
+}
+
+// ============================================================================
+// kernel A
+// ============================================================================
+template <int O, int A, bool RELU, int W>
+__global__ void __launch_bounds__(576, 1) update_tcw_fwdbwd_kernel(const __grid_constant__ TcwArgs a) {
+    constexpr int HW = W / 4, NCH = HW / 32, OKP = (O + 1 + 7) / 8 * 8, KH = W / 128;
+    constexpr int NKC = W / 32;                       // K chunks per direction
+    constexpr uint32_t CB = (uint32_t)W * 128u;       // chunk bytes
+    constexpr uint32_t TM_D = 0u, TM_AHI = (uint32_t)W, TM_ALO = (uint32_t)W + 128u;
+    if (a.k_begin + blockIdx.x >= a.tstart[a.T]) return;      // no live tile for this CTA in this batch (CTA-uniform)
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t wbar, bar_d, bar_k0, full_bar[TCW_STAGES], empty_bar[TCW_STAGES];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float muS[4][A][128];
+    __shared__ float dmuS[A][128];
+    __shared__ double sred[4][16];
+    if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+    unsigned char *ring = smem_raw;
+    float *Rsm = reinterpret_cast<float *>(smem_raw + TCW_STAGES * CB);
+    unsigned char *O_hi = reinterpret_cast<unsigned char *>(Rsm + a.lay.resident);
+    unsigned char *O_lo = O_hi + 128 * OKP * 4;
+    stage_weights_tma(Rsm, a.packed, a.lay.resident, &wbar);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_d, 1);
+        mbar_init(&bar_k0, 1);
+        for (int i = 0; i < TCW_STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_fence_init();
+    }
+    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, 512);
+    for (int i = threadIdx.x; i < 128 * OKP; i += blockDim.x) {
+        const int r = i / OKP, c = i % OKP;
+        *reinterpret_cast<float *>(O_hi + core_offset(OKP, r, c)) = c == O ? 1.0f : 0.0f;
+        *reinterpret_cast<float *>(O_lo + core_offset(OKP, r, c)) = 0.0f;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t N = a.N;
+    // tiles of this CTA inside the batch: slot = blockIdx.x, + gridDim.x, ...
+    const int64_t k_end = a.k_begin + a.k_count;
+
+    if (warp == 16) {
+        // ===== TMA producer: per tile the forward chunks (hi, lo per K chunk) then the backward chunks =====
+        if (lane == 0) {
+            uint32_t gi = 0;
+            const float *srcf = a.packed + a.lay.chunks_f, *srcb = a.packed + a.lay.chunks_b;
+            for (int64_t k = a.k_begin + blockIdx.x; k < k_end; k += gridDim.x) {
+                int t, blk;
+                if (!tcw_tile_of(a.tstart, a.T, k, &t, &blk)) break;
+                for (int dir = 0; dir < 2; ++dir) {
+                    const float *src = dir ? srcb : srcf;
+                    for (int i = 0; i < 2 * NKC; ++i, ++gi) {
+                        const uint32_t st = gi % TCW_STAGES, ph = (gi / TCW_STAGES) & 1u;
+                        mbar_wait(&empty_bar[st], ph ^ 1u);
+                        mbar_expect_tx(&full_bar[st], CB);
+                        tma_bulk_g2s(ring + (size_t)st * CB, src + (size_t)i * a.lay.chunk_floats, CB, &full_bar[st]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 17) {
+        // ===== MMA issuer =====
+        const uint32_t idesc_f = umma_idesc_tf32(128, W, false, false);
+        const uint32_t idesc_b = umma_idesc_tf32(128, W, false, true);
+        const uint32_t r_u = smem_u32(Rsm), ring_u = smem_u32(ring);
+        const uint32_t w0hi = r_u + (uint32_t)a.lay.w0hi * 4u, w0lo = r_u + (uint32_t)a.lay.w0lo * 4u;
+        const uint32_t ohi = smem_u32(O_hi), olo = smem_u32(O_lo);
+        uint32_t gi = 0;
+        for (int64_t k = a.k_begin + blockIdx.x; k < k_end; k += gridDim.x) {
+            int t, blk;
+            if (!tcw_tile_of(a.tstart, a.T, k, &t, &blk)) break;
+            tcw_sync(TCW_BAR_L1, 544);
+            tc_fence_after();
+            if (lane == 0) {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t aa = pass == 2 ? olo : ohi, bb = pass == 1 ? w0lo : w0hi;
+#pragma unroll
+                    for (int kk = 0; kk < OKP; kk += 8) {
+                        umma_tf32(tmem + TM_D, umma_operand_desc(aa, OKP, false, kk), umma_operand_desc(bb, OKP, false, kk),
+                                  idesc_f, acc);
+                        acc = 1u;
+                    }
+                }
+                umma_commit(&bar_d);
+            }
+            __syncwarp();
+            for (int dir = 0; dir < 2; ++dir) {           // 0: forward (K-major B), 1: backward-data (MN-major B)
+                for (int half = 0; half < KH; ++half) {
+                    if (half == 0) tcw_sync(TCW_BAR_K0, 544);
+                    else tcw_sync(TCW_BAR_K1, 288);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        for (int c = 0; c < 4; ++c) {
+                            const uint32_t st_hi = gi % TCW_STAGES, ph_hi = (gi / TCW_STAGES) & 1u;
+                            ++gi;
+                            const uint32_t st_lo = gi % TCW_STAGES, ph_lo = (gi / TCW_STAGES) & 1u;
+                            ++gi;
+                            const uint32_t bhi = ring_u + st_hi * CB, blo = ring_u + st_lo * CB;
+                            const uint32_t acol = (uint32_t)(c * 32);
+                            const uint32_t idesc = dir ? idesc_b : idesc_f;
+                            mbar_wait(&full_bar[st_hi], ph_hi);
+                            tc_fence_after();
+#pragma unroll
+                            for (int ks = 0; ks < 32; ks += 8)
+                                umma_tf32_ts(tmem + TM_D, tmem + TM_AHI + acol + (uint32_t)ks,
+                                             dir ? umma_desc_mn32(bhi + (uint32_t)ks * 128u, 4096u)
+                                                 : umma_operand_desc(bhi, 32, false, ks),
+                                             idesc, (half | c | ks) ? 1u : 0u);
+#pragma unroll
+                            for (int ks = 0; ks < 32; ks += 8)
+                                umma_tf32_ts(tmem + TM_D, tmem + TM_ALO + acol + (uint32_t)ks,
+                                             dir ? umma_desc_mn32(bhi + (uint32_t)ks * 128u, 4096u)
+                                                 : umma_operand_desc(bhi, 32, false, ks),
+                                             idesc, 1u);
+                            umma_commit(&empty_bar[st_hi]);
+                            mbar_wait(&full_bar[st_lo], ph_lo);
+                            tc_fence_after();
+#pragma unroll
+                            for (int ks = 0; ks < 32; ks += 8)
+                                umma_tf32_ts(tmem + TM_D, tmem + TM_AHI + acol + (uint32_t)ks,
+                                             dir ? umma_desc_mn32(blo + (uint32_t)ks * 128u, 4096u)
+                                                 : umma_operand_desc(blo, 32, false, ks),
+                                             idesc, 1u);
+                            umma_commit(&empty_bar[st_lo]);
+                        }
+                        umma_commit((half == KH - 1) ? &bar_d : &bar_k0);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ===== compute warps =====
+        const int q = warp & 3, part = warp >> 2;
+        const int e = q * 32 + lane;                  // sample row of the tile = TMEM lane
+        const int c0 = part * HW;
+        const int my_half = c0 / 128;                 // K half this thread's columns belong to
+        const uint32_t acol0 = (uint32_t)(c0 % 128);
+        const uint32_t my_tm = tmem + ((uint32_t)(q * 32) << 16);
+        const int act_kind = RELU ? TG_ACT_RELU : a.lay.act;
+        const float *b1 = Rsm + a.lay.b1 + c0, *wo = Rsm + a.lay.wo + c0, *bo = Rsm + a.lay.bo;
+        uint32_t ph_d = 0, ph_k0 = 0;
+        // butterfly partials (this warp's sum over its 32 samples of column c0 + 32*ch + lane)
+        float c_b1[NCH], c_wo[A][NCH], c_bo[A];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            c_b1[ch] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < A; ++j) c_wo[j][ch] = 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < A; ++j) c_bo[j] = 0.0f;
+        double s_obj = 0.0, s_cnt = 0.0, s_ratio = 0.0, s_clip = 0.0;
+
+        // K-half protocol of the TMEM A operand (W = 256): threads whose columns belong to half 0 write it while
+        // they process their chunks; threads of half 1 only write the scratch, tell the MMA warp they have read
+        // D, wait until the MMAs of half 0 have consumed the operand, and then reload their chunks from the
+        // scratch they just wrote (nothing is held in registers across the wait).
+        constexpr bool DEFER = KH == 2;
+        const bool deferred = DEFER && my_half == 1;
+        auto finish_A = [&](const unsigned char *arr_hi, const unsigned char *arr_lo) {
+            if (deferred) {
+                tc_fence_before();
+                tcw_arrive(TCW_BAR_K0, 544);
+                mbar_wait(&bar_k0, ph_k0);
+                tc_fence_after();
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch)
+                    tcw_reload32<W>(arr_hi, arr_lo, e, (c0 >> 5) + ch, my_tm + TM_AHI + acol0 + (uint32_t)(ch * 32),
+                                    my_tm + TM_ALO + acol0 + (uint32_t)(ch * 32));
+            }
+            ph_k0 ^= 1u;
+            tmem_st_wait();
+            tc_fence_before();
+            if (deferred) tcw_arrive(TCW_BAR_K1, 288);
+            else tcw_arrive(TCW_BAR_K0, 544);
+        };
+
+        for (int64_t k = a.k_begin + blockIdx.x; k < k_end; k += gridDim.x) {
+            int t, blk;
+            if (!tcw_tile_of(a.tstart, a.T, k, &t, &blk)) break;
+            unsigned char *tile_sc = a.sc.base + (size_t)(k - a.k_begin) * a.sc.tile_bytes;
+            unsigned char *H1h = tile_sc, *H1l = H1h + a.sc.arr_bytes, *Z2h = H1l + a.sc.arr_bytes,
+                          *Z2l = Z2h + a.sc.arr_bytes, *Z1h = Z2l + a.sc.arr_bytes, *Z1l = Z1h + a.sc.arr_bytes;
+            unsigned char *Xh = Z1l + a.sc.arr_bytes, *Xl = Xh + a.sc.x_bytes;
+            // ---- inputs of this thread's sample (part 0 owns the per-sample scalars)
+            const int64_t j = (int64_t)blk * 128 + e;
+            const bool valid = j < a.cnt[t];
+            float av[A], adv = 0.f, olp = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < A; ++jj) av[jj] = 0.0f;
+            if (part == 0) {
+                int64_t n = 0;
+                if (valid) n = a.perm[j];
+                // [x, 1] operand of kernel B: sub-block e/8, K-major [OKP rows][8 samples]
+                unsigned char *xh = Xh + (size_t)(e >> 3) * (OKP * 32), *xl = Xl + (size_t)(e >> 3) * (OKP * 32);
+#pragma unroll
+                for (int i = 0; i < O; ++i) {
+                    const float x = valid ? a.obs[((int64_t)t * O + i) * N + n] : 0.0f;
+                    const float xhi = tf32_hi(x);
+                    *reinterpret_cast<float *>(O_hi + core_offset(OKP, e, i)) = xhi;
+                    *reinterpret_cast<float *>(O_lo + core_offset(OKP, e, i)) = x - xhi;
+                    const uint32_t xo = core_offset(8, i, e & 7);
+                    *reinterpret_cast<float *>(xh + xo) = xhi;
+                    *reinterpret_cast<float *>(xl + xo) = x - xhi;
+                }
+#pragma unroll
+                for (int i = O; i < OKP; ++i) {
+                    const uint32_t xo = core_offset(8, i, e & 7);
+                    *reinterpret_cast<float *>(xh + xo) = (i == O && valid) ? 1.0f : 0.0f;
+                    *reinterpret_cast<float *>(xl + xo) = 0.0f;
+                }
+                if (valid) {
+#pragma unroll
+                    for (int jj = 0; jj < A; ++jj) av[jj] = a.act[((int64_t)t * A + jj) * N + n];
+                    adv = a.adv[(int64_t)t * N + n];
+                    olp = a.oldlp[(int64_t)t * N + n];
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            tcw_arrive(TCW_BAR_L1, 544);
+            mbar_wait(&bar_d, ph_d);
+            ph_d ^= 1u;
+            tc_fence_after();
+            // ---- epilogue 1: H1 = act(D) (bias folded); scratch H1 hi/lo; act'(H1) mask; A operand
+            uint32_t m1[NCH];
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                float z[32];
+                tmem_ld32(my_tm + TM_D + (uint32_t)(c0 + ch * 32), z);
+                uint32_t m = 0;
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) {
+                    z[jj] = valid ? act_fwd(z[jj], act_kind) : 0.0f;   // padding rows contribute nothing
+                    m |= (z[jj] > 0.0f ? 1u : 0u) << jj;
+                }
+                m1[ch] = m;
+                const uint32_t th = my_tm + TM_AHI + acol0 + (uint32_t)(ch * 32), tl = my_tm + TM_ALO + acol0 + (uint32_t)(ch * 32);
+                if (deferred) tcw_emit32<W, false>(H1h, H1l, e, (c0 >> 5) + ch, z, th, tl);
+                else tcw_emit32<W, true>(H1h, H1l, e, (c0 >> 5) + ch, z, th, tl);
+            }
+            finish_A(H1h, H1l);
+            mbar_wait(&bar_d, ph_d);
+            ph_d ^= 1u;
+            tc_fence_after();
+            // ---- epilogue 2a: H2 = act(D + b1), partial output-layer dot products
+            {
+                float pm[A];
+#pragma unroll
+                for (int jj = 0; jj < A; ++jj) pm[jj] = 0.0f;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    float z[32];
+                    tmem_ld32(my_tm + TM_D + (uint32_t)(c0 + ch * 32), z);
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) {
+                        const float h2 = act_fwd(z[jj] + b1[ch * 32 + jj], act_kind);
+#pragma unroll
+                        for (int o = 0; o < A; ++o) pm[o] = fmaf(h2, wo[o * W + ch * 32 + jj], pm[o]);
+                    }
+                }
+#pragma unroll
+                for (int jj = 0; jj < A; ++jj) muS[part][jj][e] = pm[jj];
+            }
+            tcw_sync(q + 1, 128);
+            if (part == 0) {
+                float mu[A], dmu[A];
+#pragma unroll
+                for (int jj = 0; jj < A; ++jj) {
+                    mu[jj] = (((bo[jj] + muS[0][jj][e]) + muS[1][jj][e]) + muS[2][jj][e]) + muS[3][jj][e];
+                    dmu[jj] = 0.0f;
+                }
+                if (valid) {
+                    float m2 = 0.0f;
+#pragma unroll
+                    for (int jj = 0; jj < A; ++jj) {
+                        const float zz = (av[jj] - mu[jj]) * a.inv_sd[jj];
+                        m2 += zz * zz;
+                    }
+                    const float lp = -0.5f * m2 - a.log_norm;
+                    const float ratio = expf(lp - olp);
+                    const float lo = 1.0f - a.eps_clip, hi = 1.0f + a.eps_clip;
+                    const float s1 = ratio * adv, s2 = fminf(fmaxf(ratio, lo), hi) * adv;
+                    const bool in_range = ratio >= lo && ratio <= hi;
+                    float g;
+                    if (s1 < s2) g = adv;
+                    else if (s1 > s2) g = in_range ? adv : 0.0f;
+                    else g = 0.5f * (adv + (in_range ? adv : 0.0f));
+                    float dlp = a.scale * g * ratio;
+                    float eo = 0.0f;
+                    if (a.kl_scale != 0.0f) {
+                        eo = expf(olp);
+                        dlp -= a.kl_scale * eo;
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < A; ++jj) dmu[jj] = dlp * (av[jj] - mu[jj]) * a.inv_var[jj];
+                    s_obj += (double)fminf(s1, s2) * a.scale + (double)a.kl_scale * eo * (olp - lp);
+                    s_cnt += 1.0; s_ratio += ratio; s_clip += in_range ? 0.0 : 1.0;
+#pragma unroll
+                    for (int jj = 0; jj < A; ++jj) c_bo[jj] += dmu[jj];
+                }
+#pragma unroll
+                for (int jj = 0; jj < A; ++jj) dmuS[jj][e] = dmu[jj];
+            }
+            tcw_sync(q + 1, 128);
+            // ---- epilogue 2b: dZ2 = (Wo^T dmu) * act'(H2); column sums for dWo, db1; scratch dZ2; A operand
+            {
+                float dmu[A];
+#pragma unroll
+                for (int jj = 0; jj < A; ++jj) dmu[jj] = dmuS[jj][e];
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    float z[32];
+                    tmem_ld32(my_tm + TM_D + (uint32_t)(c0 + ch * 32), z);
+                    // column sums of dmu_j * H2 (dWo) first, then z becomes dZ2 in place
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) z[jj] = act_fwd(z[jj] + b1[ch * 32 + jj], act_kind);
+#pragma unroll
+                    for (int o = 0; o < A; ++o) {
+                        float v[32];
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) v[jj] = dmu[o] * z[jj];
+                        c_wo[o][ch] += tcw_colsum32(v, lane);
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) {
+                        float g = 0.0f;
+#pragma unroll
+                        for (int o = 0; o < A; ++o) g = fmaf(dmu[o], wo[o * W + ch * 32 + jj], g);
+                        z[jj] = g * act_bwd_from_out(z[jj], act_kind);
+                    }
+                    const uint32_t th = my_tm + TM_AHI + acol0 + (uint32_t)(ch * 32), tl = my_tm + TM_ALO + acol0 + (uint32_t)(ch * 32);
+                    if (deferred) tcw_emit32<W, false>(Z2h, Z2l, e, (c0 >> 5) + ch, z, th, tl);
+                    else tcw_emit32<W, true>(Z2h, Z2l, e, (c0 >> 5) + ch, z, th, tl);
+                    c_b1[ch] += tcw_colsum32(z, lane);
+                }
+            }
+            finish_A(Z2h, Z2l);
+            mbar_wait(&bar_d, ph_d);
+            ph_d ^= 1u;
+            tc_fence_after();
+            // ---- epilogue 3: dZ1 = D * act'(H1) -> scratch (kernel B turns it into dW0 / db0)
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                float z[32];
+                tmem_ld32(my_tm + TM_D + (uint32_t)(c0 + ch * 32), z);
+                if (RELU) {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) z[jj] = ((m1[ch] >> jj) & 1u) ? z[jj] : 0.0f;
+                } else {
+                    // act'(H1) from the H1 this thread stored to the scratch (hi + lo)
+                    const int r = e & 7;
+                    const unsigned char *ph = H1h + (size_t)(e >> 3) * (W / 32 * 1024) + (size_t)((c0 >> 5) + ch) * 1024 + (size_t)r * 128;
+                    const unsigned char *pl = H1l + (size_t)(e >> 3) * (W / 32 * 1024) + (size_t)((c0 >> 5) + ch) * 1024 + (size_t)r * 128;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint32_t o = (uint32_t)((((i >> 1) ^ (r & 3)) << 5) + (i & 1) * 16);
+                        const float4 vh = *reinterpret_cast<const float4 *>(ph + o);
+                        const float4 vl = *reinterpret_cast<const float4 *>(pl + o);
+                        z[4 * i] *= act_bwd_from_out(vh.x + vl.x, act_kind);
+                        z[4 * i + 1] *= act_bwd_from_out(vh.y + vl.y, act_kind);
+                        z[4 * i + 2] *= act_bwd_from_out(vh.z + vl.z, act_kind);
+                        z[4 * i + 3] *= act_bwd_from_out(vh.w + vl.w, act_kind);
+                    }
+                }
+                tcw_emit32<W, false>(Z1h, Z1l, e, (c0 >> 5) + ch, z, 0u, 0u);
+            }
+            tc_fence_before();
+        }
+        // ---- this CTA's butterfly partials and statistics into its private gradient copy (accumulated)
+        float *gp = a.gpart + (int64_t)blockIdx.x * a.lay.n_params;
+        const int64_t f1 = a.lay.flat_w[1], f2 = a.lay.flat_w[2];
+        for (int qs = 0; qs < 4; ++qs) {
+            if (q == qs) {
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    const int col = c0 + ch * 32 + lane;
+                    gp[f1 + (int64_t)W * W + col] += c_b1[ch];
+#pragma unroll
+                    for (int jj = 0; jj < A; ++jj) gp[f2 + (int64_t)jj * W + col] += c_wo[jj][ch];
+                }
+            }
+            asm volatile("bar.sync 8, 512;" ::: "memory");     // the 16 compute warps
+        }
+        {
+            double v[4] = {s_obj, s_cnt, s_ratio, s_clip};
+#pragma unroll
+            for (int kq = 0; kq < 4; ++kq) {
+                for (int off = 16; off > 0; off >>= 1) v[kq] += __shfl_down_sync(0xffffffffu, v[kq], off);
+                if (lane == 0) sred[kq][warp] = v[kq];
+            }
+            asm volatile("bar.sync 8, 512;" ::: "memory");
+            if (threadIdx.x < 4 && a.spart) {
+                double tt = 0.0;
+                for (int w = 0; w < 16; ++w) tt += sred[threadIdx.x][w];
+                a.spart[(int64_t)blockIdx.x * 4 + threadIdx.x] += tt;
+            }
+            asm volatile("bar.sync 8, 512;" ::: "memory");
+#pragma unroll
+            for (int jj = 0; jj < A; ++jj) {
+                float tt = c_bo[jj];
+                for (int off = 16; off > 0; off >>= 1) tt += __shfl_down_sync(0xffffffffu, tt, off);
+                if (lane == 0) sred[0][warp] = (double)tt;
+                asm volatile("bar.sync 8, 512;" ::: "memory");
+                if (threadIdx.x == 0) {
+                    float tot = 0.0f;
+                    for (int w = 0; w < 16; ++w) tot += (float)sred[0][w];
+                    gp[f2 + (int64_t)A * W + jj] += tot;
+                }
+                asm volatile("bar.sync 8, 512;" ::: "memory");
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
+}
+
+// ============================================================================
+// kernel B: split-K weight-gradient GEMMs streamed from the scratch
+//   stage = one 8-sample sub-block: Z2h, Z2l (this half: 4 column blocks), H1h, H1l (all), Z1h, Z1l (this half), Xh, Xl
+// ============================================================================
+template <int O, int W>
+__global__ void __launch_bounds__(192, 1) update_tcw_wgrad_kernel(const __grid_constant__ TcwArgs a) {
+    constexpr int OKP = (O + 1 + 7) / 8 * 8;
+    constexpr uint32_t ZB = 4 * 1024, HB = W / 32 * 1024, XB = OKP * 32;        // bytes per stage piece
+    constexpr uint32_t STAGE = 4 * ZB + 2 * HB + 2 * XB;
+    constexpr uint32_t STAGE_AL = (STAGE + 1023) / 1024 * 1024;
+    constexpr int NST = 5;
+    constexpr uint32_t TM_DW = 0u, TM_D0 = (uint32_t)W;
+    if (a.k_begin + blockIdx.x >= a.tstart[a.T]) return;      // no live tile for this CTA in this batch (CTA-uniform)
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[NST], empty_bar[NST], done_bar;
+    __shared__ uint32_t tmem_slot;
+    if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NST; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(&done_bar, 1);
+        mbar_fence_init();
+    }
+    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t k_end = a.k_begin + a.k_count;
+    const int half = a.half;
+    bool any = false;
+    if (warp == 4) {
+        if (lane == 0) {
+            uint32_t gi = 0;
+            for (int64_t k = a.k_begin + blockIdx.x; k < k_end; k += gridDim.x) {
+                int t, blk;
+                if (!tcw_tile_of(a.tstart, a.T, k, &t, &blk)) break;
+                const unsigned char *tile_sc = a.sc.base + (size_t)(k - a.k_begin) * a.sc.tile_bytes;
+                const unsigned char *arr[6];
+                for (int i = 0; i < 6; ++i) arr[i] = tile_sc + (size_t)i * a.sc.arr_bytes;
+                const unsigned char *Xh = tile_sc + 6 * (size_t)a.sc.arr_bytes, *Xl = Xh + a.sc.x_bytes;
+                for (int sb = 0; sb < 16; ++sb, ++gi) {
+                    const uint32_t st = gi % NST, ph = (gi / NST) & 1u;
+                    mbar_wait(&empty_bar[st], ph ^ 1u);
+                    mbar_expect_tx(&full_bar[st], STAGE);
+                    unsigned char *dst = smem_raw + (size_t)st * STAGE_AL;
+                    const size_t sbo = (size_t)sb * HB, ho = (size_t)half * ZB;
+                    tma_bulk_g2s(dst, arr[2] + sbo + ho, ZB, &full_bar[st]);                 // Z2h (half)
+                    tma_bulk_g2s(dst + ZB, arr[3] + sbo + ho, ZB, &full_bar[st]);            // Z2l
+                    tma_bulk_g2s(dst + 2 * ZB, arr[4] + sbo + ho, ZB, &full_bar[st]);        // Z1h
+                    tma_bulk_g2s(dst + 3 * ZB, arr[5] + sbo + ho, ZB, &full_bar[st]);        // Z1l
+                    tma_bulk_g2s(dst + 4 * ZB, arr[0] + sbo, HB, &full_bar[st]);             // H1h (all columns)
+                    tma_bulk_g2s(dst + 4 * ZB + HB, arr[1] + sbo, HB, &full_bar[st]);        // H1l
+                    tma_bulk_g2s(dst + 4 * ZB + 2 * HB, Xh + (size_t)sb * XB, XB, &full_bar[st]);
+                    tma_bulk_g2s(dst + 4 * ZB + 2 * HB + XB, Xl + (size_t)sb * XB, XB, &full_bar[st]);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        const uint32_t idesc_w = umma_idesc_tf32(128, W, true, true);
+        const uint32_t idesc_x = umma_idesc_tf32(128, OKP, true, false);
+        uint32_t gi = 0, first = 1u;
+        for (int64_t k = a.k_begin + blockIdx.x; k < k_end; k += gridDim.x) {
+            int t, blk;
+            if (!tcw_tile_of(a.tstart, a.T, k, &t, &blk)) break;
+            any = true;
+            if (lane == 0) {
+                for (int sb = 0; sb < 16; ++sb, ++gi) {
+                    const uint32_t st = gi % NST, ph = (gi / NST) & 1u;
+                    mbar_wait(&full_bar[st], ph);
+                    tc_fence_after();
+                    const uint32_t base = smem_u32(smem_raw) + st * STAGE_AL;
+                    const uint32_t z2h = base, z2l = base + ZB, z1h = base + 2 * ZB, z1l = base + 3 * ZB;
+                    const uint32_t h1h = base + 4 * ZB, h1l = h1h + HB, xh = h1l + HB, xl = xh + XB;
+                    const uint32_t acc0 = first ? 0u : 1u;
+                    // dW1[half] += dZ2^T . H1   (A, B MN-major: 8 reduction rows, 32-column blocks 1 KB apart)
+                    umma_tf32(tmem + TM_DW, umma_desc_mn32(z2h, 1024u), umma_desc_mn32(h1h, 1024u), idesc_w, acc0);
+                    umma_tf32(tmem + TM_DW, umma_desc_mn32(z2h, 1024u), umma_desc_mn32(h1l, 1024u), idesc_w, 1u);
+                    umma_tf32(tmem + TM_DW, umma_desc_mn32(z2l, 1024u), umma_desc_mn32(h1h, 1024u), idesc_w, 1u);
+                    // [dW0 | db0][half] += dZ1^T . [x, 1]   (B K-major [OKP][8])
+                    umma_tf32(tmem + TM_D0, umma_desc_mn32(z1h, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, acc0);
+                    umma_tf32(tmem + TM_D0, umma_desc_mn32(z1h, 1024u), umma_operand_desc(xl, 8, false, 0), idesc_x, 1u);
+                    umma_tf32(tmem + TM_D0, umma_desc_mn32(z1l, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, 1u);
+                    first = 0u;
+                    umma_commit(&empty_bar[st]);
+                }
+            }
+            __syncwarp();
+        }
+        if (lane == 0 && any) umma_commit(&done_bar);
+        __syncwarp();
+    }
+    // did this CTA process any tile?  (uniform: its first tile index is live or not)
+    {
+        int t, blk;
+        any = (a.k_begin + blockIdx.x < k_end) && tcw_tile_of(a.tstart, a.T, a.k_begin + blockIdx.x, &t, &blk);
+    }
+    if (warp < 4 && any) {
+        mbar_wait(&done_bar, 0);
+        tc_fence_after();
+        float *gp = a.gpart + (int64_t)blockIdx.x * a.lay.n_params;
+        const int64_t f0 = a.lay.flat_w[0], f1 = a.lay.flat_w[1];
+        const int row = half * 128 + warp * 32 + lane;       // out index (dW1) / hidden-1 index (dW0)
+        const uint32_t my_tm = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int c = 0; c < W; c += 32) {
+            float z[32];
+            tmem_ld32(my_tm + TM_DW + (uint32_t)c, z);
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) gp[f1 + (int64_t)row * W + c + jj] += z[jj];
+        }
+        {
+            float z[32];
+            tmem_ld32(my_tm + TM_D0, z);
+#pragma unroll
+            for (int o = 0; o < O; ++o) gp[f0 + (int64_t)row * O + o] += z[o];
+            gp[f0 + (int64_t)W * O + row] += z[O];
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
+}
+
+// ============================================================================
+// host side
+// ============================================================================
+template <int O, int A, int W>
+static int launch_tcw(const TcwArgs &a0, int grid, int64_t total_upper, int64_t batch_tiles, cudaStream_t st) {
+    constexpr int OKP = (O + 1 + 7) / 8 * 8;
+    const size_t smemA = (size_t)TCW_STAGES * W * 128 + (size_t)a0.lay.resident * 4 + 2 * (size_t)128 * OKP * 4;
+    constexpr uint32_t STAGE = 4 * 4096 + 2 * (W / 32 * 1024) + 2 * (OKP * 32);
+    const size_t smemB = (size_t)5 * ((STAGE + 1023) / 1024 * 1024);
+    void (*kA)(const TcwArgs) = a0.lay.act == TG_ACT_RELU ? update_tcw_fwdbwd_kernel<O, A, true, W>
+                                                          : update_tcw_fwdbwd_kernel<O, A, false, W>;
+    void (*kB)(const TcwArgs) = update_tcw_wgrad_kernel<O, W>;
+    TG_CUDA(cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+    TG_CUDA(cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+    for (int64_t k0 = 0; k0 < total_upper; k0 += batch_tiles) {
+        TcwArgs a = a0;
+        a.k_begin = k0;
+        a.k_count = (total_upper - k0) < batch_tiles ? (total_upper - k0) : batch_tiles;
+        kA<<<grid, 576, smemA, st>>>(a);
+        for (int half = 0; half < W / 128; ++half) {
+            a.half = half;
+            kB<<<grid, 192, smemB, st>>>(a);
+        }
+    }
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}
+
+static int reserve_bytes(void **p, size_t *cap, size_t bytes) {
+    if (bytes <= *cap) return TG_OK;
+    if (*p) {
+        TG_CUDA(cudaDeviceSynchronize());
+        TG_CUDA(cudaFree(*p));
+        *p = nullptr;
+        *cap = 0;
+    }
+    TG_CUDA(cudaMalloc(p, bytes));
+    *cap = bytes;
+    return TG_OK;
+}
+
+// gpart [sm_count][n_params] and spart [sm_count][4] must be zeroed by the caller.
+int tg_policy_grad_tcw(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, const float *obs, const float *act,
+                       const float *adv, const float *old_logp, const int32_t *len, const float *params,
+                       const float *inv_sd, const float *inv_var, float log_norm, float eps_clip, float scale,
+                       float kl_scale, float *gpart, double *spart, int grid, cudaStream_t st) {
+    TcwArgs a;
+    memset(&a, 0, sizeof(a));
+    build_tcw_layout(mlp, &a.lay);
+    const int W = a.lay.W, O = a.lay.O, A = a.lay.A;
+    int rc = reserve_bytes((void **)&ctx->packed_tc, &ctx->packed_tc_cap, (size_t)a.lay.total * 4);
+    if (rc) return rc;
+    pack_tcw_kernel<<<296, 256, 0, st>>>(a.lay, params, ctx->packed_tc);
+    TG_CUDA(cudaGetLastError());
+    rc = tg_len_order(ctx, N, T, len, st);
+    if (rc) return rc;
+    // per-tile scratch; batch = as many tiles as fit the budget (a multiple of the grid)
+    a.sc.arr_bytes = (int64_t)16 * (W / 32) * 1024;
+    a.sc.x_bytes = (int64_t)16 * a.lay.OKP * 32;
+    a.sc.tile_bytes = 6 * a.sc.arr_bytes + 2 * a.sc.x_bytes;
+    const int64_t NB = (N + 127) / 128;
+    const int64_t total_upper = NB * T;                       // live tiles <= this
+    const int64_t budget = (int64_t)1 << 30;
+    int64_t batch_tiles = budget / a.sc.tile_bytes / grid * grid;
+    if (batch_tiles < grid) batch_tiles = grid;
+    if (batch_tiles > total_upper) batch_tiles = (total_upper + grid - 1) / grid * grid;
+    const size_t tstart_bytes = ((size_t)(T + 1) * 8 + 255) / 256 * 256;
+    rc = reserve_bytes(&ctx->scratch, &ctx->scratch_cap, tstart_bytes + (size_t)batch_tiles * a.sc.tile_bytes);
+    if (rc) return rc;
+    int64_t *tstart = reinterpret_cast<int64_t *>(ctx->scratch);
+    a.sc.base = reinterpret_cast<unsigned char *>(ctx->scratch) + tstart_bytes;
+    tcw_tstart_kernel<<<1, 32, 0, st>>>(T, ctx->cnt, tstart);
+    TG_CUDA(cudaGetLastError());
+    a.N = N; a.T = T; a.obs = obs; a.act = act; a.adv = adv; a.oldlp = old_logp;
+    a.perm = ctx->perm; a.cnt = ctx->cnt; a.tstart = tstart;
+    a.packed = ctx->packed_tc;
+    for (int j = 0; j < TG_MAX_ACT; ++j) { a.inv_sd[j] = inv_sd[j]; a.inv_var[j] = inv_var[j]; }
+    a.log_norm = log_norm; a.eps_clip = eps_clip; a.scale = scale; a.kl_scale = kl_scale;
+    a.gpart = gpart; a.spart = spart;
+#define TCW_CASE(OO, AA)                                                                                  \
+    if (O == OO && A == AA)                                                                               \
+        return W == 128 ? launch_tcw<OO, AA, 128>(a, grid, total_upper, batch_tiles, st)                  \
+                        : launch_tcw<OO, AA, 256>(a, grid, total_upper, batch_tiles, st);
+    TCW_CASE(3, 1) TCW_CASE(5, 1) TCW_CASE(10, 2) TCW_CASE(20, 4)
+#undef TCW_CASE
+    tg_set_error("no wide tensor-core update kernel instance for obs %d / act %d", O, A);
+    return TG_ERR_UNSUPPORTED;
+}
+
+bool tg_update_tcw_shape_built(const tg_mlp_cfg *mlp) {
+    if (!tg_update_tcw_eligible(mlp)) return false;
+    const int O = mlp->dims[0], A = mlp->dims[3];
+    return (O == 3 && A == 1) || (O == 5 && A == 1) || (O == 10 && A == 2) || (O == 20 && A == 4);
+}
