@@ -217,6 +217,20 @@ template <int W> TG_D uint32_t tcw_sc_off(int s, int c) {
     return (uint32_t)(s >> 3) * (uint32_t)(W / 32 * 1024) + (uint32_t)(c >> 5) * 1024u + (uint32_t)r * 128u +
            (uint32_t)((((c & 31) >> 3) ^ (r & 3)) << 5) + (uint32_t)(c & 7) * 4u;
 }
+// 256-bit global accesses (sm_100): one lane moves a whole 32-byte sector, so the row-per-thread scratch traffic
+// is made of full sectors instead of 16-byte halves
+TG_D void stg256(void *p, const float *v) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+TG_D void ldg256(const void *p, float *v) {
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p)
+                 : "memory");
+}
+
 // 32 consecutive columns (column block cbk) of sample s: hi/lo split, written to two scratch arrays (MN-major
 // sub-block layout) and -- when TM -- also to the tensor-memory A operand (hi at tm_hi, lo at tm_lo), 16 columns
 // at a time so that only 32 split values are live.
@@ -235,11 +249,10 @@ TG_D void tcw_emit32(unsigned char *arr_hi, unsigned char *arr_lo, int s, int cb
             lo[jj] = v[hh * 16 + jj] - hi[jj];
         }
 #pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-            const int i = hh * 4 + i4;
-            const uint32_t o = (uint32_t)((((i >> 1) ^ (r & 3)) << 5) + (i & 1) * 16);
-            *reinterpret_cast<float4 *>(ph + o) = make_float4(hi[4 * i4], hi[4 * i4 + 1], hi[4 * i4 + 2], hi[4 * i4 + 3]);
-            *reinterpret_cast<float4 *>(pl + o) = make_float4(lo[4 * i4], lo[4 * i4 + 1], lo[4 * i4 + 2], lo[4 * i4 + 3]);
+        for (int c8 = 0; c8 < 2; ++c8) {              // 32-byte chunk (8 columns) hh*2 + c8 of the 128-byte row
+            const uint32_t o = (uint32_t)(((hh * 2 + c8) ^ (r & 3)) << 5);
+            stg256(ph + o, hi + 8 * c8);
+            stg256(pl + o, lo + 8 * c8);
         }
         if (TM) {
             tmem_st16(tm_hi + (uint32_t)(hh * 16), hi);
@@ -258,13 +271,10 @@ TG_D void tcw_reload32(const unsigned char *arr_hi, const unsigned char *arr_lo,
     for (int hh = 0; hh < 2; ++hh) {
         float hi[16], lo[16];
 #pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-            const int i = hh * 4 + i4;
-            const uint32_t o = (uint32_t)((((i >> 1) ^ (r & 3)) << 5) + (i & 1) * 16);
-            const float4 a4 = *reinterpret_cast<const float4 *>(ph + o);
-            const float4 b4 = *reinterpret_cast<const float4 *>(pl + o);
-            hi[4 * i4] = a4.x; hi[4 * i4 + 1] = a4.y; hi[4 * i4 + 2] = a4.z; hi[4 * i4 + 3] = a4.w;
-            lo[4 * i4] = b4.x; lo[4 * i4 + 1] = b4.y; lo[4 * i4 + 2] = b4.z; lo[4 * i4 + 3] = b4.w;
+        for (int c8 = 0; c8 < 2; ++c8) {
+            const uint32_t o = (uint32_t)(((hh * 2 + c8) ^ (r & 3)) << 5);
+            ldg256(ph + o, hi + 8 * c8);
+            ldg256(pl + o, lo + 8 * c8);
         }
         tmem_st16(tm_hi + (uint32_t)(hh * 16), hi);
         tmem_st16(tm_lo + (uint32_t)(hh * 16), lo);
@@ -274,9 +284,15 @@ TG_D void tcw_reload32(const unsigned char *arr_hi, const unsigned char *arr_lo,
 // ============================================================================
 // kernel A
 // ============================================================================
-template <int O, int A, bool RELU, int W>
-__global__ void __launch_bounds__(576, 1) update_tcw_fwdbwd_kernel(const __grid_constant__ TcwArgs a) {
-    constexpr int HW = W / 4, NCH = HW / 32, OKP = (O + 1 + 7) / 8 * 8, KH = W / 128;
+// NP threads serve one sample (NP * 4 compute warps, each thread owning W / NP columns) + producer + MMA warp.
+// NP = 2 keeps the CTA at 10 warps = 3 per SM sub-partition, i.e. 168 registers per thread and no spills; with
+// NP = 4 (18 warps, 96 registers) the epilogues spilled ~0.8 KB per thread into an L1 that the 222 KB of shared
+// memory leave almost no room for, and the serial step chain paid the L2 latency of every reload.
+template <int O, int A, bool RELU, int W, int NP>
+__global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(const __grid_constant__ TcwArgs a) {
+    constexpr int HW = W / NP, NCH = HW / 32, OKP = (O + 1 + 7) / 8 * 8, KH = W / 128;
+    constexpr int NCT = NP * 128;                     // compute threads
+    constexpr int CNT_ALL = NCT + 32, CNT_H1 = (KH == 2 ? NCT / 2 : NCT) + 32;
     constexpr int NKC = W / 32;                       // K chunks per direction
     constexpr uint32_t CB = (uint32_t)W * 128u;       // chunk bytes
     constexpr uint32_t TM_D = 0u, TM_AHI = (uint32_t)W, TM_ALO = (uint32_t)W + 128u;
@@ -284,7 +300,7 @@ __global__ void __launch_bounds__(576, 1) update_tcw_fwdbwd_kernel(const __grid_
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t wbar, bar_d, bar_k0, full_bar[TCW_STAGES], empty_bar[TCW_STAGES];
     __shared__ uint32_t tmem_slot;
-    __shared__ float muS[4][A][128];
+    __shared__ float muS[NP][A][128];
     __shared__ float dmuS[A][128];
     __shared__ double sred[4][16];
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
@@ -318,7 +334,7 @@ __global__ void __launch_bounds__(576, 1) update_tcw_fwdbwd_kernel(const __grid_
     // tiles of this CTA inside the batch: slot = blockIdx.x, + gridDim.x, ...
     const int64_t k_end = a.k_begin + a.k_count;
 
-    if (warp == 16) {
+    if (warp == NP * 4) {
         // ===== TMA producer: per tile the forward chunks (hi, lo per K chunk) then the backward chunks =====
         if (lane == 0) {
             uint32_t gi = 0;
@@ -337,7 +353,7 @@ __global__ void __launch_bounds__(576, 1) update_tcw_fwdbwd_kernel(const __grid_
                 }
             }
         }
-    } else if (warp == 17) {
+    } else if (warp == NP * 4 + 1) {
         // ===== MMA issuer =====
         const uint32_t idesc_f = umma_idesc_tf32(128, W, false, false);
         const uint32_t idesc_b = umma_idesc_tf32(128, W, false, true);
@@ -348,7 +364,7 @@ __global__ void __launch_bounds__(576, 1) update_tcw_fwdbwd_kernel(const __grid_
         for (int64_t k = a.k_begin + blockIdx.x; k < k_end; k += gridDim.x) {
             int t, blk;
             if (!tcw_tile_of(a.tstart, a.T, k, &t, &blk)) break;
-            tcw_sync(TCW_BAR_L1, 544);
+            tcw_sync(TCW_BAR_L1, CNT_ALL);
             tc_fence_after();
             if (lane == 0) {
                 uint32_t acc = 0;
@@ -367,8 +383,8 @@ __global__ void __launch_bounds__(576, 1) update_tcw_fwdbwd_kernel(const __grid_
             __syncwarp();
             for (int dir = 0; dir < 2; ++dir) {           // 0: forward (K-major B), 1: backward-data (MN-major B)
                 for (int half = 0; half < KH; ++half) {
-                    if (half == 0) tcw_sync(TCW_BAR_K0, 544);
-                    else tcw_sync(TCW_BAR_K1, 288);
+                    if (half == 0) tcw_sync(TCW_BAR_K0, CNT_ALL);
+                    else tcw_sync(TCW_BAR_K1, CNT_H1);
                     tc_fence_after();
                     if (lane == 0) {
                         for (int c = 0; c < 4; ++c) {
@@ -442,7 +458,7 @@ __global__ void __launch_bounds__(576, 1) update_tcw_fwdbwd_kernel(const __grid_
         auto finish_A = [&](const unsigned char *arr_hi, const unsigned char *arr_lo) {
             if (deferred) {
                 tc_fence_before();
-                tcw_arrive(TCW_BAR_K0, 544);
+                tcw_arrive(TCW_BAR_K0, CNT_ALL);
                 mbar_wait(&bar_k0, ph_k0);
                 tc_fence_after();
 #pragma unroll
@@ -453,8 +469,8 @@ __global__ void __launch_bounds__(576, 1) update_tcw_fwdbwd_kernel(const __grid_
             ph_k0 ^= 1u;
             tmem_st_wait();
             tc_fence_before();
-            if (deferred) tcw_arrive(TCW_BAR_K1, 288);
-            else tcw_arrive(TCW_BAR_K0, 544);
+            if (deferred) tcw_arrive(TCW_BAR_K1, CNT_H1);
+            else tcw_arrive(TCW_BAR_K0, CNT_ALL);
         };
 
         for (int64_t k = a.k_begin + blockIdx.x; k < k_end; k += gridDim.x) {
@@ -500,7 +516,7 @@ __global__ void __launch_bounds__(576, 1) update_tcw_fwdbwd_kernel(const __grid_
             }
             fence_proxy_async();
             tc_fence_before();
-            tcw_arrive(TCW_BAR_L1, 544);
+            tcw_arrive(TCW_BAR_L1, CNT_ALL);
             mbar_wait(&bar_d, ph_d);
             ph_d ^= 1u;
             tc_fence_after();
@@ -544,12 +560,15 @@ __global__ void __launch_bounds__(576, 1) update_tcw_fwdbwd_kernel(const __grid_
 #pragma unroll
                 for (int jj = 0; jj < A; ++jj) muS[part][jj][e] = pm[jj];
             }
-            tcw_sync(q + 1, 128);
+            tcw_sync(q + 1, NP * 32);
             if (part == 0) {
                 float mu[A], dmu[A];
 #pragma unroll
                 for (int jj = 0; jj < A; ++jj) {
-                    mu[jj] = (((bo[jj] + muS[0][jj][e]) + muS[1][jj][e]) + muS[2][jj][e]) + muS[3][jj][e];
+                    float m = bo[jj];
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) m += muS[p][jj][e];
+                    mu[jj] = m;
                     dmu[jj] = 0.0f;
                 }
                 if (valid) {
@@ -584,7 +603,7 @@ __global__ void __launch_bounds__(576, 1) update_tcw_fwdbwd_kernel(const __grid_
 #pragma unroll
                 for (int jj = 0; jj < A; ++jj) dmuS[jj][e] = dmu[jj];
             }
-            tcw_sync(q + 1, 128);
+            tcw_sync(q + 1, NP * 32);
             // ---- epilogue 2b: dZ2 = (Wo^T dmu) * act'(H2); column sums for dWo, db1; scratch dZ2; A operand
             {
                 float dmu[A];
@@ -662,7 +681,7 @@ __global__ void __launch_bounds__(576, 1) update_tcw_fwdbwd_kernel(const __grid_
                     for (int jj = 0; jj < A; ++jj) gp[f2 + (int64_t)jj * W + col] += c_wo[jj][ch];
                 }
             }
-            asm volatile("bar.sync 8, 512;" ::: "memory");     // the 16 compute warps
+            asm volatile("bar.sync 8, %0;" ::"n"(NCT) : "memory");     // the 16 compute warps
         }
         {
             double v[4] = {s_obj, s_cnt, s_ratio, s_clip};
@@ -671,25 +690,25 @@ __global__ void __launch_bounds__(576, 1) update_tcw_fwdbwd_kernel(const __grid_
                 for (int off = 16; off > 0; off >>= 1) v[kq] += __shfl_down_sync(0xffffffffu, v[kq], off);
                 if (lane == 0) sred[kq][warp] = v[kq];
             }
-            asm volatile("bar.sync 8, 512;" ::: "memory");
+            asm volatile("bar.sync 8, %0;" ::"n"(NCT) : "memory");
             if (threadIdx.x < 4 && a.spart) {
                 double tt = 0.0;
-                for (int w = 0; w < 16; ++w) tt += sred[threadIdx.x][w];
+                for (int w = 0; w < NP * 4; ++w) tt += sred[threadIdx.x][w];
                 a.spart[(int64_t)blockIdx.x * 4 + threadIdx.x] += tt;
             }
-            asm volatile("bar.sync 8, 512;" ::: "memory");
+            asm volatile("bar.sync 8, %0;" ::"n"(NCT) : "memory");
 #pragma unroll
             for (int jj = 0; jj < A; ++jj) {
                 float tt = c_bo[jj];
                 for (int off = 16; off > 0; off >>= 1) tt += __shfl_down_sync(0xffffffffu, tt, off);
                 if (lane == 0) sred[0][warp] = (double)tt;
-                asm volatile("bar.sync 8, 512;" ::: "memory");
+                asm volatile("bar.sync 8, %0;" ::"n"(NCT) : "memory");
                 if (threadIdx.x == 0) {
                     float tot = 0.0f;
-                    for (int w = 0; w < 16; ++w) tot += (float)sred[0][w];
+                    for (int w = 0; w < NP * 4; ++w) tot += (float)sred[0][w];
                     gp[f2 + (int64_t)A * W + jj] += tot;
                 }
-                asm volatile("bar.sync 8, 512;" ::: "memory");
+                asm volatile("bar.sync 8, %0;" ::"n"(NCT) : "memory");
             }
         }
     }
@@ -834,8 +853,9 @@ static int launch_tcw(const TcwArgs &a0, int grid, int64_t total_upper, int64_t 
     const size_t smemA = (size_t)TCW_STAGES * W * 128 + (size_t)a0.lay.resident * 4 + 2 * (size_t)128 * OKP * 4;
     constexpr uint32_t STAGE = 4 * 4096 + 2 * (W / 32 * 1024) + 2 * (OKP * 32);
     const size_t smemB = (size_t)5 * ((STAGE + 1023) / 1024 * 1024);
-    void (*kA)(const TcwArgs) = a0.lay.act == TG_ACT_RELU ? update_tcw_fwdbwd_kernel<O, A, true, W>
-                                                          : update_tcw_fwdbwd_kernel<O, A, false, W>;
+    constexpr int NP = W == 256 ? 4 : 2;      // measured: 4 threads per sample wins at 256, 2 at 128
+    void (*kA)(const TcwArgs) = a0.lay.act == TG_ACT_RELU ? update_tcw_fwdbwd_kernel<O, A, true, W, NP>
+                                                          : update_tcw_fwdbwd_kernel<O, A, false, W, NP>;
     void (*kB)(const TcwArgs) = update_tcw_wgrad_kernel<O, W>;
     TG_CUDA(cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
     TG_CUDA(cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
@@ -843,7 +863,7 @@ static int launch_tcw(const TcwArgs &a0, int grid, int64_t total_upper, int64_t 
         TcwArgs a = a0;
         a.k_begin = k0;
         a.k_count = (total_upper - k0) < batch_tiles ? (total_upper - k0) : batch_tiles;
-        kA<<<grid, 576, smemA, st>>>(a);
+        kA<<<grid, NP * 128 + 64, smemA, st>>>(a);
         for (int half = 0; half < W / 128; ++half) {
             a.half = half;
             kB<<<grid, 192, smemB, st>>>(a);
