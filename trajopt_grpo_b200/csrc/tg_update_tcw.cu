@@ -189,6 +189,17 @@ TG_D bool tcw_tile_of(const int64_t *__restrict__ tstart, int T, int64_t k, int 
     return true;
 }
 
+// the same for the NEXT tile of a CTA (k grows by the grid size): walk forward from the previous step instead of
+// a fresh 16-load binary search -- the lookup sits on the serial per-tile chain of every warp
+TG_D bool tcw_tile_next(const int64_t *__restrict__ tstart, int T, int64_t k, int *t, int *blk) {
+    if (k >= tstart[T]) return false;
+    int tt = *t;
+    while (tt + 1 < T && tstart[tt + 1] <= k) ++tt;
+    *t = tt;
+    *blk = (int)(k - tstart[tt]);
+    return true;
+}
+
 TG_D void tcw_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 TG_D void tcw_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
@@ -339,9 +350,11 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
         if (lane == 0) {
             uint32_t gi = 0;
             const float *srcf = a.packed + a.lay.chunks_f, *srcb = a.packed + a.lay.chunks_b;
+            int t = 0, blk = 0;
+            bool first_tile = true;
             for (int64_t k = a.k_begin + blockIdx.x; k < k_end; k += gridDim.x) {
-                int t, blk;
-                if (!tcw_tile_of(a.tstart, a.T, k, &t, &blk)) break;
+                if (!(first_tile ? tcw_tile_of(a.tstart, a.T, k, &t, &blk) : tcw_tile_next(a.tstart, a.T, k, &t, &blk))) break;
+                first_tile = false;
                 for (int dir = 0; dir < 2; ++dir) {
                     const float *src = dir ? srcb : srcf;
                     for (int i = 0; i < 2 * NKC; ++i, ++gi) {
@@ -361,9 +374,11 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
         const uint32_t w0hi = r_u + (uint32_t)a.lay.w0hi * 4u, w0lo = r_u + (uint32_t)a.lay.w0lo * 4u;
         const uint32_t ohi = smem_u32(O_hi), olo = smem_u32(O_lo);
         uint32_t gi = 0;
+        int t = 0, blk = 0;
+        bool first_tile = true;
         for (int64_t k = a.k_begin + blockIdx.x; k < k_end; k += gridDim.x) {
-            int t, blk;
-            if (!tcw_tile_of(a.tstart, a.T, k, &t, &blk)) break;
+            if (!(first_tile ? tcw_tile_of(a.tstart, a.T, k, &t, &blk) : tcw_tile_next(a.tstart, a.T, k, &t, &blk))) break;
+            first_tile = false;
             tcw_sync(TCW_BAR_L1, CNT_ALL);
             tc_fence_after();
             if (lane == 0) {
@@ -473,9 +488,11 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
             else tcw_arrive(TCW_BAR_K0, CNT_ALL);
         };
 
+        int t = 0, blk = 0;
+        bool first_tile = true;
         for (int64_t k = a.k_begin + blockIdx.x; k < k_end; k += gridDim.x) {
-            int t, blk;
-            if (!tcw_tile_of(a.tstart, a.T, k, &t, &blk)) break;
+            if (!(first_tile ? tcw_tile_of(a.tstart, a.T, k, &t, &blk) : tcw_tile_next(a.tstart, a.T, k, &t, &blk))) break;
+            first_tile = false;
             unsigned char *tile_sc = a.sc.base + (size_t)(k - a.k_begin) * a.sc.tile_bytes;
             unsigned char *H1h = tile_sc, *H1l = H1h + a.sc.arr_bytes, *Z2h = H1l + a.sc.arr_bytes,
                           *Z2l = Z2h + a.sc.arr_bytes, *Z1h = Z2l + a.sc.arr_bytes, *Z1l = Z1h + a.sc.arr_bytes;
@@ -514,7 +531,7 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
                     olp = a.oldlp[(int64_t)t * N + n];
                 }
             }
-            fence_proxy_async();
+            if (part == 0) fence_proxy_async();       // only these threads wrote the shared-memory obs operand
             tc_fence_before();
             tcw_arrive(TCW_BAR_L1, CNT_ALL);
             mbar_wait(&bar_d, ph_d);
@@ -754,9 +771,11 @@ __global__ void __launch_bounds__(192, 1) update_tcw_wgrad_kernel(const __grid_c
     if (warp == 4) {
         if (lane == 0) {
             uint32_t gi = 0;
+            int t = 0, blk = 0;
+            bool first_tile = true;
             for (int64_t k = a.k_begin + blockIdx.x; k < k_end; k += gridDim.x) {
-                int t, blk;
-                if (!tcw_tile_of(a.tstart, a.T, k, &t, &blk)) break;
+                if (!(first_tile ? tcw_tile_of(a.tstart, a.T, k, &t, &blk) : tcw_tile_next(a.tstart, a.T, k, &t, &blk))) break;
+                first_tile = false;
                 const unsigned char *tile_sc = a.sc.base + (size_t)(k - a.k_begin) * a.sc.tile_bytes;
                 const unsigned char *arr[6];
                 for (int i = 0; i < 6; ++i) arr[i] = tile_sc + (size_t)i * a.sc.arr_bytes;
@@ -782,9 +801,11 @@ __global__ void __launch_bounds__(192, 1) update_tcw_wgrad_kernel(const __grid_c
         const uint32_t idesc_w = umma_idesc_tf32(128, W, true, true);
         const uint32_t idesc_x = umma_idesc_tf32(128, OKP, true, false);
         uint32_t gi = 0, first = 1u;
+        int t = 0, blk = 0;
+        bool first_tile = true;
         for (int64_t k = a.k_begin + blockIdx.x; k < k_end; k += gridDim.x) {
-            int t, blk;
-            if (!tcw_tile_of(a.tstart, a.T, k, &t, &blk)) break;
+            if (!(first_tile ? tcw_tile_of(a.tstart, a.T, k, &t, &blk) : tcw_tile_next(a.tstart, a.T, k, &t, &blk))) break;
+            first_tile = false;
             any = true;
             if (lane == 0) {
                 for (int sb = 0; sb < 16; ++sb, ++gi) {
