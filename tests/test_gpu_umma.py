@@ -199,3 +199,43 @@ def test_policy_grad_tensor_core_path_matches_fp32_path_and_oracle(kind, act_nam
         assert int(st[1]) == int(mask.sum()), mode
         assert abs(st[0] - J) <= 2e-4 * max(1.0, abs(J)), (mode, st[0], J)
     assert np.abs(out["fp32"][0] - out["3xtf32"][0]).max() <= 5e-5 * scale
+
+
+@pytest.mark.parametrize("O,width,act_name", [(10, 128, "ReLU"), (20, 256, "ReLU"), (20, 128, "Tanh")])
+def test_value_grad_wide_tensor_core_path_matches_fp32_path(O, width, act_name):
+    """tg_value_grad (critic MSE, ppo.py:168-169) for 128/256-wide critics on the streamed tensor-core path vs the
+    FP32-pipe kernel and torch float64 autograd; ragged lengths."""
+    from trajopt_grpo_b200 import engine as E
+    rng = np.random.default_rng(O + width)
+    dims = [O, width, width, 1]
+    Ws, bs, params = _policy(rng, dims)
+    N, T = 300, 7
+    obs = rng.standard_normal((T, O, N)).astype(np.float32)
+    tgt = rng.standard_normal((T, N)).astype(np.float32)
+    ln = rng.integers(1, T + 1, N).astype(np.int32)
+    mask = (np.arange(T)[:, None] < ln[None, :])
+    scale = 0.5 / mask.sum()
+    # float64 reference
+    tW = [torch.tensor(w, dtype=torch.float64, requires_grad=True) for w in Ws]
+    tb = [torch.tensor(b, dtype=torch.float64, requires_grad=True) for b in bs]
+    x = torch.tensor(obs.transpose(0, 2, 1).reshape(T * N, O), dtype=torch.float64)
+    actf = {"ReLU": torch.relu, "Tanh": torch.tanh}[act_name]
+    h = actf(x @ tW[0].T + tb[0]); h = actf(h @ tW[1].T + tb[1]); v = (h @ tW[2].T + tb[2]).reshape(T, N)
+    loss = scale * (((v - torch.tensor(tgt, dtype=torch.float64)) ** 2) * torch.tensor(mask)).sum()
+    loss.backward()
+    ref = np.concatenate([np.concatenate([w.grad.numpy().reshape(-1), b.grad.numpy()]) for w, b in zip(tW, tb)])
+    dobs, dtgt, dlen = torch.from_numpy(obs).cuda(), torch.from_numpy(tgt).cuda(), torch.from_numpy(ln).cuda()
+    out = {}
+    try:
+        for mode in ("fp32", "3xtf32"):
+            E.set_math(mode)
+            g, st = E.value_grad(dims, act_name, params, dobs, dtgt, dlen, scale)
+            torch.cuda.synchronize()
+            out[mode] = (g.cpu().numpy(), st.cpu().numpy())
+    finally:
+        E.set_math("auto")
+    sc = np.abs(ref).max()
+    for mode, (g, st) in out.items():
+        assert np.abs(g - ref).max() <= 2e-4 * sc, (mode, np.abs(g - ref).max(), sc)
+        assert int(st[1]) == int(mask.sum()), mode
+    assert np.abs(out["fp32"][0] - out["3xtf32"][0]).max() <= 5e-5 * sc

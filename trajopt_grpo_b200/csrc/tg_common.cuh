@@ -119,7 +119,7 @@ int tg_pack_weights_tc(tg_ctx *ctx, const tg_tc_layout &lay, const float *params
 // wide (128 / 256) tensor-core update, two streamed kernels per batch of tiles (tg_update_tcw.cu)
 bool tg_update_tcw_shape_built(const tg_mlp_cfg *mlp);
 int tg_policy_grad_tcw(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, const float *obs, const float *act,
-                       const float *adv, const float *old_logp, const int32_t *len, const float *params,
+                       const float *adv, const float *old_logp, const float *target, const int32_t *len, const float *params,
                        const float *inv_sd, const float *inv_var, float log_norm, float eps_clip, float scale,
                        float kl_scale, float *gpart, double *spart, int grid, cudaStream_t st);
 // tensor-core update kernel (tg_update_tc.cu)

@@ -441,7 +441,7 @@ extern "C" int tg_policy_grad(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int
         float *gpart = reinterpret_cast<float *>(workspace);
         double *spart = reinterpret_cast<double *>(reinterpret_cast<char *>(workspace) + ((gbytes + 255) / 256) * 256);
         TG_CUDA(cudaMemsetAsync(gpart, 0, ((gbytes + 255) / 256) * 256 + (size_t)grid * 4 * sizeof(double), st));
-        rc = tg_policy_grad_tcw(ctx, mlp, N, T, obs, act, adv, old_logp, len, params, a.inv_sd, a.inv_var, a.log_norm,
+        rc = tg_policy_grad_tcw(ctx, mlp, N, T, obs, act, adv, old_logp, nullptr, len, params, a.inv_sd, a.inv_var, a.log_norm,
                                 eps_clip, scale, kl_coef, gpart, spart, grid, st);
         if (rc) return rc;
         grad_reduce_kernel<<<(unsigned)((a.lay.n_params + 255) / 256), 256, 0, st>>>(grid, a.lay.n_params, gpart, spart,
@@ -526,6 +526,22 @@ extern "C" int tg_value_grad(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int 
     if (rc) return rc;
     a.N = N; a.T = T; a.head = HEAD_VALUE;
     a.obs = obs; a.target = target; a.len = len; a.scale = scale;
+    if (tg_update_tcw_shape_built(mlp) && ctx->math_mode != TG_MATH_FP32) {      // wide critic: streamed tensor-core path
+        cudaStream_t st = (cudaStream_t)stream;
+        TG_CUDA(cudaSetDevice(ctx->device));
+        const int grid = ctx->sm_count;
+        const size_t gbytes = (size_t)grid * a.lay.n_params * sizeof(float);
+        float *gpart = reinterpret_cast<float *>(workspace);
+        double *spart = reinterpret_cast<double *>(reinterpret_cast<char *>(workspace) + ((gbytes + 255) / 256) * 256);
+        TG_CUDA(cudaMemsetAsync(gpart, 0, ((gbytes + 255) / 256) * 256 + (size_t)grid * 4 * sizeof(double), st));
+        rc = tg_policy_grad_tcw(ctx, mlp, N, T, obs, nullptr, nullptr, nullptr, target, len, params, nullptr, nullptr, 0.0f,
+                                0.0f, scale, 0.0f, gpart, spart, grid, st);
+        if (rc) return rc;
+        grad_reduce_kernel<<<(unsigned)((a.lay.n_params + 255) / 256), 256, 0, st>>>(grid, a.lay.n_params, gpart, spart,
+                                                                                     out_grad, out_stats);
+        TG_CUDA(cudaGetLastError());
+        return TG_OK;
+    }
     return run_grad(ctx, a, params, out_grad, out_stats, workspace, (cudaStream_t)stream);
 }
 

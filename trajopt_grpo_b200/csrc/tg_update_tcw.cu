@@ -55,6 +55,7 @@ struct TcwArgs {
     int64_t N;
     int T;
     const float *obs, *act, *adv, *oldlp;
+    const float *target;                  // value head (critic regression, ppo.py:168-169) when non-null
     const int32_t *perm, *cnt;
     const int64_t *tstart;                // [T+1] prefix of live tiles per step
     int64_t k_begin, k_count;             // this batch: compact tiles [k_begin, k_begin + k_count)
@@ -525,10 +526,14 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
                     *reinterpret_cast<float *>(xl + xo) = 0.0f;
                 }
                 if (valid) {
+                    if (a.target != nullptr) {
+                        adv = a.target[(int64_t)t * N + n];          // the regression target rides in `adv`
+                    } else {
 #pragma unroll
-                    for (int jj = 0; jj < A; ++jj) av[jj] = a.act[((int64_t)t * A + jj) * N + n];
-                    adv = a.adv[(int64_t)t * N + n];
-                    olp = a.oldlp[(int64_t)t * N + n];
+                        for (int jj = 0; jj < A; ++jj) av[jj] = a.act[((int64_t)t * A + jj) * N + n];
+                        adv = a.adv[(int64_t)t * N + n];
+                        olp = a.oldlp[(int64_t)t * N + n];
+                    }
                 }
             }
             if (part == 0) fence_proxy_async();       // only these threads wrote the shared-memory obs operand
@@ -588,7 +593,13 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
                     mu[jj] = m;
                     dmu[jj] = 0.0f;
                 }
-                if (valid) {
+                if (valid && a.target != nullptr) {
+                    const float err = mu[0] - adv;                   // MSELoss(V, target), ppo.py:168-169
+                    s_obj += (double)err * err;
+                    s_cnt += 1.0;
+                    dmu[0] = 2.0f * a.scale * err;
+                    c_bo[0] += dmu[0];
+                } else if (valid) {
                     float m2 = 0.0f;
 #pragma unroll
                     for (int jj = 0; jj < A; ++jj) {
@@ -909,7 +920,7 @@ static int reserve_bytes(void **p, size_t *cap, size_t bytes) {
 
 // gpart [sm_count][n_params] and spart [sm_count][4] must be zeroed by the caller.
 int tg_policy_grad_tcw(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, const float *obs, const float *act,
-                       const float *adv, const float *old_logp, const int32_t *len, const float *params,
+                       const float *adv, const float *old_logp, const float *target, const int32_t *len, const float *params,
                        const float *inv_sd, const float *inv_var, float log_norm, float eps_clip, float scale,
                        float kl_scale, float *gpart, double *spart, int grid, cudaStream_t st) {
     TcwArgs a;
@@ -939,17 +950,17 @@ int tg_policy_grad_tcw(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, con
     a.sc.base = reinterpret_cast<unsigned char *>(ctx->scratch) + tstart_bytes;
     tcw_tstart_kernel<<<1, 32, 0, st>>>(T, ctx->cnt, tstart);
     TG_CUDA(cudaGetLastError());
-    a.N = N; a.T = T; a.obs = obs; a.act = act; a.adv = adv; a.oldlp = old_logp;
+    a.N = N; a.T = T; a.obs = obs; a.act = act; a.adv = adv; a.oldlp = old_logp; a.target = target;
     a.perm = ctx->perm; a.cnt = ctx->cnt; a.tstart = tstart;
     a.packed = ctx->packed_tc;
-    for (int j = 0; j < TG_MAX_ACT; ++j) { a.inv_sd[j] = inv_sd[j]; a.inv_var[j] = inv_var[j]; }
+    for (int j = 0; j < TG_MAX_ACT; ++j) { a.inv_sd[j] = inv_sd ? inv_sd[j] : 1.0f; a.inv_var[j] = inv_var ? inv_var[j] : 1.0f; }
     a.log_norm = log_norm; a.eps_clip = eps_clip; a.scale = scale; a.kl_scale = kl_scale;
     a.gpart = gpart; a.spart = spart;
 #define TCW_CASE(OO, AA)                                                                                  \
     if (O == OO && A == AA)                                                                               \
         return W == 128 ? launch_tcw<OO, AA, 128>(a, grid, total_upper, batch_tiles, st)                  \
                         : launch_tcw<OO, AA, 256>(a, grid, total_upper, batch_tiles, st);
-    TCW_CASE(3, 1) TCW_CASE(5, 1) TCW_CASE(10, 2) TCW_CASE(20, 4)
+    TCW_CASE(3, 1) TCW_CASE(5, 1) TCW_CASE(10, 2) TCW_CASE(20, 4) TCW_CASE(10, 1) TCW_CASE(20, 1)
 #undef TCW_CASE
     tg_set_error("no wide tensor-core update kernel instance for obs %d / act %d", O, A);
     return TG_ERR_UNSUPPORTED;
@@ -958,5 +969,6 @@ int tg_policy_grad_tcw(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, con
 bool tg_update_tcw_shape_built(const tg_mlp_cfg *mlp) {
     if (!tg_update_tcw_eligible(mlp)) return false;
     const int O = mlp->dims[0], A = mlp->dims[3];
-    return (O == 3 && A == 1) || (O == 5 && A == 1) || (O == 10 && A == 2) || (O == 20 && A == 4);
+    return (O == 3 && A == 1) || (O == 5 && A == 1) || (O == 10 && A == 2) || (O == 20 && A == 4) ||
+           (O == 10 && A == 1) || (O == 20 && A == 1);         // the last two: critics of the quadrotor envs
 }
