@@ -507,33 +507,38 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
             if (part == 0) {
                 int64_t n = 0;
                 if (valid) n = a.perm[j];
+                // every global load of the tile first (they are independent gathers, mostly HBM misses), THEN the
+                // stores: interleaved, the compiler must keep each load behind the previous scratch store (possible
+                // aliasing) and the tile start paid O serial DRAM latencies (measured 13-25k clocks per tile)
+                float x[O];
+#pragma unroll
+                for (int i = 0; i < O; ++i) x[i] = valid ? __ldg(a.obs + ((int64_t)t * O + i) * N + n) : 0.0f;
+                if (valid) {
+                    if (a.target != nullptr) {
+                        adv = __ldg(a.target + (int64_t)t * N + n);       // the regression target rides in `adv`
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < A; ++jj) av[jj] = __ldg(a.act + ((int64_t)t * A + jj) * N + n);
+                        adv = __ldg(a.adv + (int64_t)t * N + n);
+                        olp = __ldg(a.oldlp + (int64_t)t * N + n);
+                    }
+                }
                 // [x, 1] operand of kernel B: sub-block e/8, K-major [OKP rows][8 samples]
                 unsigned char *xh = Xh + (size_t)(e >> 3) * (OKP * 32), *xl = Xl + (size_t)(e >> 3) * (OKP * 32);
 #pragma unroll
                 for (int i = 0; i < O; ++i) {
-                    const float x = valid ? a.obs[((int64_t)t * O + i) * N + n] : 0.0f;
-                    const float xhi = tf32_hi(x);
+                    const float xhi = tf32_hi(x[i]);
                     *reinterpret_cast<float *>(O_hi + core_offset(OKP, e, i)) = xhi;
-                    *reinterpret_cast<float *>(O_lo + core_offset(OKP, e, i)) = x - xhi;
+                    *reinterpret_cast<float *>(O_lo + core_offset(OKP, e, i)) = x[i] - xhi;
                     const uint32_t xo = core_offset(8, i, e & 7);
                     *reinterpret_cast<float *>(xh + xo) = xhi;
-                    *reinterpret_cast<float *>(xl + xo) = x - xhi;
+                    *reinterpret_cast<float *>(xl + xo) = x[i] - xhi;
                 }
 #pragma unroll
                 for (int i = O; i < OKP; ++i) {
                     const uint32_t xo = core_offset(8, i, e & 7);
                     *reinterpret_cast<float *>(xh + xo) = (i == O && valid) ? 1.0f : 0.0f;
                     *reinterpret_cast<float *>(xl + xo) = 0.0f;
-                }
-                if (valid) {
-                    if (a.target != nullptr) {
-                        adv = a.target[(int64_t)t * N + n];          // the regression target rides in `adv`
-                    } else {
-#pragma unroll
-                        for (int jj = 0; jj < A; ++jj) av[jj] = a.act[((int64_t)t * A + jj) * N + n];
-                        adv = a.adv[(int64_t)t * N + n];
-                        olp = a.oldlp[(int64_t)t * N + n];
-                    }
                 }
             }
             if (part == 0) fence_proxy_async();       // only these threads wrote the shared-memory obs operand
