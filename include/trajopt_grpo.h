@@ -113,6 +113,11 @@ int tg_ctx_set_math(tg_ctx *ctx, int math_mode);
  * register-tiled MLP GEMMs; bench.py reports K1/K3 against it. */
 int tg_fp32_peak(tg_ctx *ctx, double *out_tflops);
 
+/* Microbenchmark behind a design rule of the tensor-core kernels: clocks taken by a tcgen05.ld and
+ * a tcgen05.st issued right after n_mma tcgen05.mma (M=128, N=64, K=8) were put in flight by another thread.
+ * out[0] = ld, out[1] = st (+wait::st), out[2] = issue-to-retire of the MMAs, out[3] = issue time (host array of 4). */
+int tg_tmem_probe(tg_ctx *ctx, int n_mma, long long *out_host4);
+
 /* Tensor-core self test (row-major fp32 in/out) through tcgen05.mma kind::tf32 with fp32 TMEM
  * accumulation; passes = 1 (plain TF32) or 3 (3xTF32 hi/lo split, fp32-faithful):
  *   mode 0  D[128][N] = A[128][K] * B[N][K]^T   (forward layer: both operands K-major)

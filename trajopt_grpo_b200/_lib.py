@@ -47,6 +47,7 @@ _SIGS = {
     "tg_ctx_sm_count": (C.c_int, [_vp]),
     "tg_ctx_set_math": (C.c_int, [_vp, _i32]),
     "tg_fp32_peak": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "tg_tmem_probe": (C.c_int, [_vp, _i32, C.POINTER(C.c_longlong)]),
     "tg_umma_selftest": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "tg_env_dims": (C.c_int, [_i32, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "tg_mlp_param_count": (_i64, [C.POINTER(MlpCfg)]),

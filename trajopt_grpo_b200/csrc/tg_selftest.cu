@@ -130,3 +130,89 @@ extern "C" int tg_umma_selftest(tg_ctx *ctx, const float *A, const float *B, flo
     TG_CUDA(cudaGetLastError());
     return TG_OK;
 }
+
+// ---------------------------------------------------------------------------
+// tg_tmem_probe: does a tensor-memory load / store issued while tcgen05.mma instructions are in flight wait for
+// them?  One CTA: thread 0 issues n_mma MMAs (M = 128, N = 64, K = 8, zero operands) into columns 0..63 and
+// commits; every warp then immediately does a tcgen05.ld (32 columns of an UNTOUCHED region) followed by a
+// tcgen05.st, each timed with clock64; finally the commit barrier is awaited and timed as well.
+//   out[0] = cycles of the ld, out[1] = cycles of the st (+wait::st), out[2] = cycles until the MMAs retired
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) tmem_probe_kernel(int n_mma, int variant, long long *out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    float *A = reinterpret_cast<float *>(smem_raw);              // [128][64] K-major core-matrix layout, zeros
+    float *B = A + 128 * 64;                                     // [64][64]
+    for (int i = threadIdx.x; i < 128 * 64 + 64 * 64; i += 128) A[i] = 0.0f;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t my_tm = tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16);
+    const uint32_t idesc = umma_idesc_tf32(128, 64);
+    const uint32_t a_u = smem_u32(A), b_u = smem_u32(B);
+    const long long t0 = clock64();
+    if (variant == 0) {
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < n_mma; ++i)
+                umma_tf32(tmem, umma_operand_desc(a_u, 64, false, (i % 8) * 8), umma_operand_desc(b_u, 64, false, (i % 8) * 8),
+                          idesc, i ? 1u : 0u);
+            umma_commit(&bar);
+        }
+    } else if (threadIdx.x < 32) {
+        // warp-uniform issue: descriptors advance in uniform registers, one elected lane issues.  A warp broadcast
+        // (__shfl_sync from lane 0) is what tells ptxas that the base addresses are warp-uniform.
+        const uint32_t au = variant == 2 ? __shfl_sync(0xffffffffu, a_u, 0) : a_u;
+        const uint32_t bu = variant == 2 ? __shfl_sync(0xffffffffu, b_u, 0) : b_u;
+        const uint32_t tmem_u = variant == 2 ? __shfl_sync(0xffffffffu, tmem, 0) : tmem;
+        const uint64_t a0 = umma_operand_desc(au, 64, false, 0), b0 = umma_operand_desc(bu, 64, false, 0);
+        for (int i = 0; i < n_mma; i += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                umma_tf32_w(tmem_u, a0 + (uint64_t)(k * 16), b0 + (uint64_t)(k * 16), idesc, (i | k) ? 1u : 0u);
+        }
+        umma_commit_w(&bar);
+    }
+    __syncthreads();
+    const long long t1 = clock64();
+    float v[32];
+    tmem_ld32(my_tm + 256u, v);
+    const long long t2 = clock64();
+    tmem_st32(my_tm + 320u, v);
+    tmem_st_wait();
+    const long long t3 = clock64();
+    mbar_wait(&bar, 0);
+    const long long t4 = clock64();
+    if (threadIdx.x == 0) {
+        out[0] = t2 - t1;
+        out[1] = t3 - t2;
+        out[2] = t4 - t0;
+        out[3] = t1 - t0;
+    }
+    if (v[0] == 123.0f) out[4] = 1;
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
+}
+
+extern "C" int tg_tmem_probe(tg_ctx *ctx, int n_mma, long long *out_host4) {
+    TG_REQUIRE(ctx && out_host4 && n_mma >= -20000 && n_mma <= 4096, TG_ERR_ARG, "tg_tmem_probe: bad argument");   // n_mma < 0: warp-uniform issue variant
+    TG_CUDA(cudaSetDevice(ctx->device));
+    long long *d = nullptr;
+    TG_CUDA(cudaMalloc(&d, 64));
+    TG_CUDA(cudaMemset(d, 0, 64));
+    const size_t smem = (128 * 64 + 64 * 64) * 4;
+    TG_CUDA(cudaFuncSetAttribute(tmem_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int rep = 0; rep < 2; ++rep) tmem_probe_kernel<<<1, 128, smem>>>(n_mma < 0 ? (-n_mma) % 10000 : n_mma, n_mma < -10000 ? 2 : (n_mma < 0 ? 1 : 0), d);
+    TG_CUDA(cudaDeviceSynchronize());
+    TG_CUDA(cudaMemcpy(out_host4, d, 32, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return TG_OK;
+}

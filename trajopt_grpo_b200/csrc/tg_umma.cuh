@@ -97,6 +97,37 @@ TG_D void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t id
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Warp-uniform issue: the WHOLE warp executes the call with identical arguments and one elected lane issues the
+// instruction.  With every operand warp-uniform, ptxas keeps the descriptors in uniform registers and advances
+// them with the uniform datapath; issuing from inside `if (lane == 0)` instead costs R2UR moves plus 64-bit vector
+// arithmetic per descriptor -- measured ~70 clocks per tcgen05.mma, more than twice the 32 clocks the MMA itself
+// takes (tg_tmem_probe), so the issuing thread, not the tensor pipe, was the bottleneck.
+TG_D void umma_tf32_w(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+TG_D void umma_tf32_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+TG_D void umma_commit_w(uint64_t *bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+        : "memory");
+}
+
 // Same with the A operand read from tensor memory: A[M=128][K] fp32/tf32 lives in TMEM with row m in
 // lane m and element k in column (a_col0 + k); one MMA consumes 8 columns.
 TG_D void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -191,6 +222,20 @@ TG_D void umma_gemm_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, int a_
         const uint32_t b = (pass == 1) ? b_lo : b_hi;
         for (int k = 0; k < K; k += 8) {
             umma_tf32(tmem_d, umma_operand_desc(a, a_C, a_mn, k), umma_operand_desc(b, b_C, b_mn, k), idesc, acc);
+            acc = 1u;
+        }
+    }
+}
+
+// warp-uniform version of umma_gemm_3xtf32 (whole warp calls it, one elected lane issues)
+TG_D void umma_gemm_3xtf32_w(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, int a_C, bool a_mn, uint32_t b_hi,
+                             uint32_t b_lo, int b_C, bool b_mn, int K, uint32_t idesc, bool accumulate_first, int passes) {
+    uint32_t acc = accumulate_first ? 1u : 0u;
+    for (int pass = 0; pass < passes; ++pass) {
+        const uint32_t a = (pass == 2) ? a_lo : a_hi;
+        const uint32_t b = (pass == 1) ? b_lo : b_hi;
+        for (int k = 0; k < K; k += 8) {
+            umma_tf32_w(tmem_d, umma_operand_desc(a, a_C, a_mn, k), umma_operand_desc(b, b_C, b_mn, k), idesc, acc);
             acc = 1u;
         }
     }

@@ -160,49 +160,79 @@ __global__ void __launch_bounds__(NPART * 128 + 32, 1) update_tc_kernel(const __
     const int64_t ntiles = NB * a.T;
     bool have_prev = false;      // a tile has been processed before the current one (CTA-uniform)
     if (warp == NCW) {
-        // ===== MMA issuer warp: one elected lane issues every tcgen05.mma of the CTA; it meets the compute
-        // warps on named barriers.  Tensor-pipe order per tile i:
-        //   fwd(i) | bwd(i), wgrad1(i)
+        // ===== MMA issuer warp.  The whole warp runs the issue loops with warp-uniform operands and ONE elected lane
+        // issues each tcgen05.mma (umma_*_w): issuing from inside `if (lane == 0)` made ptxas move every descriptor
+        // and TMEM address from vector to uniform registers through an ELECT / R2UR.BROADCAST waterfall, ~70 clocks
+        // per MMA against the 32 clocks a [128x64x8] MMA takes (tg_tmem_probe) -- the issuing thread, not the
+        // tensor pipe, bounded the kernel.  Loops are kept rolled (descriptors advance by a constant) so that the
+        // uniform register file does not spill.  Tensor-pipe order per tile i:  fwd(i) | bwd(i), wgrad1(i)
         uint32_t buf = 0, first_w = 1u;
+        const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+        const uint64_t d_wf_hi = umma_operand_desc(__shfl_sync(0xffffffffu, wf_hi, 0), W, false, 0);
+        const uint64_t d_wf_lo = umma_operand_desc(__shfl_sync(0xffffffffu, wf_lo, 0), W, false, 0);
+        const uint64_t d_wb_hi = umma_operand_desc(__shfl_sync(0xffffffffu, wb_hi, 0), W, true, 0);
+        const uint64_t d_wb_lo = umma_operand_desc(__shfl_sync(0xffffffffu, wb_lo, 0), W, true, 0);
+        const uint64_t d_c_hi = umma_operand_desc(__shfl_sync(0xffffffffu, C_hi, 0), 128, true, 0);
+        const uint64_t d_c_lo = umma_operand_desc(__shfl_sync(0xffffffffu, C_lo, 0), 128, true, 0);
+        const uint64_t d_b_hi = umma_operand_desc(__shfl_sync(0xffffffffu, B_hi, 0), 128, true, 0);
+        const uint64_t d_b_lo = umma_operand_desc(__shfl_sync(0xffffffffu, B_lo, 0), 128, true, 0);
+        // descriptor address field is in 16-byte units: one K step (8 elements) = 256 B K-major, 1024 B MN-major
+        constexpr uint64_t STEP_K = 16, STEP_MN = 64;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             if ((tile % NB) * 128 >= a.cnt[tile / NB]) continue;
-            const uint32_t acol = tmem + TM_A0 + buf * 128u;
+            const uint32_t acol = tm + TM_A0 + buf * 128u;
             named_sync(BAR_FWD, NT);
             tc_fence_after();
-            if (lane == 0) {
+            {
                 uint32_t acc = 0;
-#pragma unroll
+#pragma unroll 1
                 for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t ac = acol + (pass == 2 ? 64u : 0u);
-                    const uint32_t b = pass == 1 ? wf_lo : wf_hi;
-#pragma unroll
+                    uint32_t ac = acol + (pass == 2 ? 64u : 0u);
+                    uint64_t b = pass == 1 ? d_wf_lo : d_wf_hi;
+#pragma unroll 2
                     for (int k = 0; k < W; k += 8) {
-                        umma_tf32_ts(tmem + TM_DF, ac + (uint32_t)k, umma_operand_desc(b, W, false, k), idesc_f, acc);
+                        umma_tf32_ts_w(tm + TM_DF, ac, b, idesc_f, acc);
                         acc = 1u;
+                        ac += 8u;
+                        b += STEP_K;
                     }
                 }
-                umma_commit(&bar_a);
+                umma_commit_w(&bar_a);
             }
             __syncwarp();
             named_sync(BAR_BWD, NT);
             tc_fence_after();
-            if (lane == 0) {
+            {
                 uint32_t acc = 0;
-#pragma unroll
+#pragma unroll 1
                 for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t ac = acol + (pass == 2 ? 64u : 0u);
-                    const uint32_t b = pass == 1 ? wb_lo : wb_hi;
-#pragma unroll
+                    uint32_t ac = acol + (pass == 2 ? 64u : 0u);
+                    uint64_t b = pass == 1 ? d_wb_lo : d_wb_hi;
+#pragma unroll 2
                     for (int k = 0; k < W; k += 8) {
-                        umma_tf32_ts(tmem + TM_DB, ac + (uint32_t)k, umma_operand_desc(b, W, true, k), idesc_b, acc);
+                        umma_tf32_ts_w(tm + TM_DB, ac, b, idesc_b, acc);
                         acc = 1u;
+                        ac += 8u;
+                        b += STEP_MN;
                     }
                 }
-                umma_commit(&bar_b);
+                umma_commit_w(&bar_b);
                 // dW1 += dZ2^T . H1, accumulated in tensor memory over all of this CTA's tiles
-                umma_gemm_3xtf32(tmem + TM_DW, C_hi, C_lo, 128, true, B_hi, B_lo, 128, true, 128, idesc_w, first_w == 0u, 3);
+                uint32_t accw = first_w ? 0u : 1u;
+#pragma unroll 1
+                for (int pass = 0; pass < 3; ++pass) {
+                    uint64_t da = pass == 2 ? d_c_lo : d_c_hi;
+                    uint64_t db = pass == 1 ? d_b_lo : d_b_hi;
+#pragma unroll 2
+                    for (int k = 0; k < 128; k += 8) {
+                        umma_tf32_w(tm + TM_DW, da, db, idesc_w, accw);
+                        accw = 1u;
+                        da += STEP_MN;
+                        db += STEP_MN;
+                    }
+                }
                 first_w = 0u;
-                umma_commit(&bar_w);
+                umma_commit_w(&bar_w);
             }
             __syncwarp();
             have_prev = true;
