@@ -296,11 +296,11 @@ __global__ void __launch_bounds__(128) rollout_tc_kernel(const __grid_constant__
             fence_proxy_async();
             tc_fence_before();
             __syncthreads();
-            if (threadIdx.x == 0) {
+            if (threadIdx.x < 32) {        // warp 0 issues with warp-uniform operands, one elected lane per MMA
                 tc_fence_after();
-                umma_gemm_3xtf32(tmem, a_hi_u, a_lo_u, W, false, w_u + (uint32_t)a.lay.whi[l] * 4u,
-                                 w_u + (uint32_t)a.lay.wlo[l] * 4u, W, false, W, idesc, false, 3);
-                umma_commit(&mbar);
+                umma_gemm_3xtf32_w(tmem, a_hi_u, a_lo_u, W, false, w_u + (uint32_t)a.lay.whi[l] * 4u,
+                                   w_u + (uint32_t)a.lay.wlo[l] * 4u, W, false, W, idesc, false, 3);
+                umma_commit_w(&mbar);
             }
             mbar_wait(&mbar, phase);
             phase ^= 1u;
@@ -488,21 +488,23 @@ __global__ void __launch_bounds__(256, 1) rollout_tc2_kernel(const __grid_consta
             tmem_st_wait();
             tc_fence_before();
             __syncthreads();
-            if (threadIdx.x == 0) {
+            if (threadIdx.x < 32) {        // warp 0 issues with warp-uniform operands, one elected lane per MMA
                 tc_fence_after();
                 const uint32_t b_hi = w_u + (uint32_t)a.lay.whi[l] * 4u, b_lo = w_u + (uint32_t)a.lay.wlo[l] * 4u;
                 uint32_t acc = 0;
-#pragma unroll
+#pragma unroll 1
                 for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t acol = tmem + (pass == 2 ? TM_ALO : TM_AHI);
-                    const uint32_t b = pass == 1 ? b_lo : b_hi;
-#pragma unroll 4
+                    uint32_t acol = tmem + (pass == 2 ? TM_ALO : TM_AHI);
+                    uint64_t b = umma_operand_desc(pass == 1 ? b_lo : b_hi, W, false, 0);
+#pragma unroll 2
                     for (int k = 0; k < W; k += 8) {
-                        umma_tf32_ts(tmem + TM_D, acol + (uint32_t)k, umma_operand_desc(b, W, false, k), idesc, acc);
+                        umma_tf32_ts_w(tmem + TM_D, acol, b, idesc, acc);
                         acc = 1u;
+                        acol += 8u;
+                        b += 16;               // one K step = 256 B in the K-major core-matrix layout (16-byte units)
                     }
                 }
-                umma_commit(&mbar);
+                umma_commit_w(&mbar);
             }
             mbar_wait(&mbar, phase);
             phase ^= 1u;
