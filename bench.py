@@ -394,8 +394,8 @@ def run_ours(args, w):
             "bound": "tensor", "achieved": k3_tf, "peak": bf16_peak, "unit": "TFLOP/s", "frac": k3_tf / bf16_peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else
                            "fallback of /opt/skills/guides/B200_PROFILING.md (MEASURED_PEAKS.json absent)",
-            "traffic": 324.0e6 if w is WORKLOADS["pendulum"] else None,
-            "traffic_source": "profiles/r1d_ncu_details_pendulum_kernels.csv: dram read 315.5 MB + write 8.5 MB "
+            "traffic": 322.1e6 if w is WORKLOADS["pendulum"] else None,
+            "traffic_source": "profiles/r1f_ncu_details_pendulum_kernels.csv: dram read 315.4 MB + write 6.7 MB "
                               "per launch (algorithmic: 315 MB of obs+act+adv+old logp)",
             "achieved_note": "algorithmic FLOPs (6*P per valid step, SURVEY 8d) / CUDA-event time of the launch",
             "frac_of_3xtf32_ceiling": k3_tf / (bf16_peak / 6.0),

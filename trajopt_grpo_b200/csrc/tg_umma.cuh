@@ -240,3 +240,4 @@ TG_D void umma_gemm_3xtf32_w(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, int 
         }
     }
 }
+
