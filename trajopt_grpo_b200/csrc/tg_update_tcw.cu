@@ -44,10 +44,10 @@ struct TcwLayout {
 struct TcwScratch {                       // per-tile byte strides / bases inside the HBM scratch
     unsigned char *base;
     int64_t tile_bytes;                   // all arrays of one tile
-    int64_t arr_bytes;                    // one of H1h,H1l,Z2h,Z2l,Z1h,Z1l per tile = 16 sub-blocks * W/32 KB
+    int64_t arr_bytes;                    // one of H1, dZ2, dZ1 (fp32) per tile = 16 sub-blocks * W/32 KB
     int64_t x_bytes;                      // one of Xh, Xl per tile = 16 * OKP * 32
 };
-// array order inside a tile: H1h, H1l, Z2h, Z2l, Z1h, Z1l, Xh, Xl
+// array order inside a tile: H1, dZ2, dZ1 (fp32, MN-major sub-blocks), Xh, Xl
 
 struct TcwArgs {
     TcwLayout lay;
@@ -243,50 +243,44 @@ TG_D void ldg256(const void *p, float *v) {
                  : "memory");
 }
 
-// 32 consecutive columns (column block cbk) of sample s: hi/lo split, written to two scratch arrays (MN-major
-// sub-block layout) and -- when TM -- also to the tensor-memory A operand (hi at tm_hi, lo at tm_lo), 16 columns
-// at a time so that only 32 split values are live.
+// 32 consecutive columns (column block cbk) of sample s: written as fp32 to the scratch array (MN-major sub-block
+// layout; kernel B splits into tf32 hi/lo after its TMA load, which halves the HBM traffic of both kernels) and --
+// when TM -- hi/lo split into the tensor-memory A operand (hi at tm_hi, lo at tm_lo), 16 columns at a time.
 template <int W, bool TM>
-TG_D void tcw_emit32(unsigned char *arr_hi, unsigned char *arr_lo, int s, int cbk, const float *v, uint32_t tm_hi,
-                     uint32_t tm_lo) {
+TG_D void tcw_emit32(unsigned char *arr, int s, int cbk, const float *v, uint32_t tm_hi, uint32_t tm_lo) {
     const int r = s & 7;
-    unsigned char *ph = arr_hi + (size_t)(s >> 3) * (W / 32 * 1024) + (size_t)cbk * 1024 + (size_t)r * 128;
-    unsigned char *pl = arr_lo + (size_t)(s >> 3) * (W / 32 * 1024) + (size_t)cbk * 1024 + (size_t)r * 128;
+    unsigned char *p = arr + (size_t)(s >> 3) * (W / 32 * 1024) + (size_t)cbk * 1024 + (size_t)r * 128;
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-        float hi[16], lo[16];
+    for (int c8 = 0; c8 < 4; ++c8)                    // 32-byte chunk (8 columns) c8 of the 128-byte row
+        stg256(p + (uint32_t)((c8 ^ (r & 3)) << 5), v + 8 * c8);
+    if (TM) {
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-            hi[jj] = tf32_hi(v[hh * 16 + jj]);
-            lo[jj] = v[hh * 16 + jj] - hi[jj];
-        }
+        for (int hh = 0; hh < 2; ++hh) {
+            float hi[16], lo[16];
 #pragma unroll
-        for (int c8 = 0; c8 < 2; ++c8) {              // 32-byte chunk (8 columns) hh*2 + c8 of the 128-byte row
-            const uint32_t o = (uint32_t)(((hh * 2 + c8) ^ (r & 3)) << 5);
-            stg256(ph + o, hi + 8 * c8);
-            stg256(pl + o, lo + 8 * c8);
-        }
-        if (TM) {
+            for (int jj = 0; jj < 16; ++jj) {
+                hi[jj] = tf32_hi(v[hh * 16 + jj]);
+                lo[jj] = v[hh * 16 + jj] - hi[jj];
+            }
             tmem_st16(tm_hi + (uint32_t)(hh * 16), hi);
             tmem_st16(tm_lo + (uint32_t)(hh * 16), lo);
         }
     }
 }
-// the same 32 columns read back from the scratch (this thread wrote them) into the tensor-memory A operand
+// the same 32 columns read back from the scratch (this thread wrote them), split, into the tensor-memory A operand
 template <int W>
-TG_D void tcw_reload32(const unsigned char *arr_hi, const unsigned char *arr_lo, int s, int cbk, uint32_t tm_hi,
-                       uint32_t tm_lo) {
+TG_D void tcw_reload32(const unsigned char *arr, int s, int cbk, uint32_t tm_hi, uint32_t tm_lo) {
     const int r = s & 7;
-    const unsigned char *ph = arr_hi + (size_t)(s >> 3) * (W / 32 * 1024) + (size_t)cbk * 1024 + (size_t)r * 128;
-    const unsigned char *pl = arr_lo + (size_t)(s >> 3) * (W / 32 * 1024) + (size_t)cbk * 1024 + (size_t)r * 128;
+    const unsigned char *p = arr + (size_t)(s >> 3) * (W / 32 * 1024) + (size_t)cbk * 1024 + (size_t)r * 128;
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
-        float hi[16], lo[16];
+        float v[16], hi[16], lo[16];
 #pragma unroll
-        for (int c8 = 0; c8 < 2; ++c8) {
-            const uint32_t o = (uint32_t)(((hh * 2 + c8) ^ (r & 3)) << 5);
-            ldg256(ph + o, hi + 8 * c8);
-            ldg256(pl + o, lo + 8 * c8);
+        for (int c8 = 0; c8 < 2; ++c8) ldg256(p + (uint32_t)(((hh * 2 + c8) ^ (r & 3)) << 5), v + 8 * c8);
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+            hi[jj] = tf32_hi(v[jj]);
+            lo[jj] = v[jj] - hi[jj];
         }
         tmem_st16(tm_hi + (uint32_t)(hh * 16), hi);
         tmem_st16(tm_lo + (uint32_t)(hh * 16), lo);
@@ -471,7 +465,7 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
         // scratch they just wrote (nothing is held in registers across the wait).
         constexpr bool DEFER = KH == 2;
         const bool deferred = DEFER && my_half == 1;
-        auto finish_A = [&](const unsigned char *arr_hi, const unsigned char *arr_lo) {
+        auto finish_A = [&](const unsigned char *arr) {
             if (deferred) {
                 tc_fence_before();
                 tcw_arrive(TCW_BAR_K0, CNT_ALL);
@@ -479,7 +473,7 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
                 tc_fence_after();
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch)
-                    tcw_reload32<W>(arr_hi, arr_lo, e, (c0 >> 5) + ch, my_tm + TM_AHI + acol0 + (uint32_t)(ch * 32),
+                    tcw_reload32<W>(arr, e, (c0 >> 5) + ch, my_tm + TM_AHI + acol0 + (uint32_t)(ch * 32),
                                     my_tm + TM_ALO + acol0 + (uint32_t)(ch * 32));
             }
             ph_k0 ^= 1u;
@@ -495,9 +489,8 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
             if (!(first_tile ? tcw_tile_of(a.tstart, a.T, k, &t, &blk) : tcw_tile_next(a.tstart, a.T, k, &t, &blk))) break;
             first_tile = false;
             unsigned char *tile_sc = a.sc.base + (size_t)(k - a.k_begin) * a.sc.tile_bytes;
-            unsigned char *H1h = tile_sc, *H1l = H1h + a.sc.arr_bytes, *Z2h = H1l + a.sc.arr_bytes,
-                          *Z2l = Z2h + a.sc.arr_bytes, *Z1h = Z2l + a.sc.arr_bytes, *Z1l = Z1h + a.sc.arr_bytes;
-            unsigned char *Xh = Z1l + a.sc.arr_bytes, *Xl = Xh + a.sc.x_bytes;
+            unsigned char *H1s = tile_sc, *Z2s = H1s + a.sc.arr_bytes, *Z1s = Z2s + a.sc.arr_bytes;
+            unsigned char *Xh = Z1s + a.sc.arr_bytes, *Xl = Xh + a.sc.x_bytes;
             // ---- inputs of this thread's sample (part 0 owns the per-sample scalars)
             const int64_t j = (int64_t)blk * 128 + e;
             const bool valid = j < a.cnt[t];
@@ -561,10 +554,10 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
                 }
                 m1[ch] = m;
                 const uint32_t th = my_tm + TM_AHI + acol0 + (uint32_t)(ch * 32), tl = my_tm + TM_ALO + acol0 + (uint32_t)(ch * 32);
-                if (deferred) tcw_emit32<W, false>(H1h, H1l, e, (c0 >> 5) + ch, z, th, tl);
-                else tcw_emit32<W, true>(H1h, H1l, e, (c0 >> 5) + ch, z, th, tl);
+                if (deferred) tcw_emit32<W, false>(H1s, e, (c0 >> 5) + ch, z, th, tl);
+                else tcw_emit32<W, true>(H1s, e, (c0 >> 5) + ch, z, th, tl);
             }
-            finish_A(H1h, H1l);
+            finish_A(H1s);
             mbar_wait(&bar_d, ph_d);
             ph_d ^= 1u;
             tc_fence_after();
@@ -664,12 +657,12 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
                         z[jj] = g * act_bwd_from_out(z[jj], act_kind);
                     }
                     const uint32_t th = my_tm + TM_AHI + acol0 + (uint32_t)(ch * 32), tl = my_tm + TM_ALO + acol0 + (uint32_t)(ch * 32);
-                    if (deferred) tcw_emit32<W, false>(Z2h, Z2l, e, (c0 >> 5) + ch, z, th, tl);
-                    else tcw_emit32<W, true>(Z2h, Z2l, e, (c0 >> 5) + ch, z, th, tl);
+                    if (deferred) tcw_emit32<W, false>(Z2s, e, (c0 >> 5) + ch, z, th, tl);
+                    else tcw_emit32<W, true>(Z2s, e, (c0 >> 5) + ch, z, th, tl);
                     c_b1[ch] += tcw_colsum32(z, lane);
                 }
             }
-            finish_A(Z2h, Z2l);
+            finish_A(Z2s);
             mbar_wait(&bar_d, ph_d);
             ph_d ^= 1u;
             tc_fence_after();
@@ -682,22 +675,18 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
 #pragma unroll
                     for (int jj = 0; jj < 32; ++jj) z[jj] = ((m1[ch] >> jj) & 1u) ? z[jj] : 0.0f;
                 } else {
-                    // act'(H1) from the H1 this thread stored to the scratch (hi + lo)
+                    // act'(H1) from the H1 this thread stored to the scratch
                     const int r = e & 7;
-                    const unsigned char *ph = H1h + (size_t)(e >> 3) * (W / 32 * 1024) + (size_t)((c0 >> 5) + ch) * 1024 + (size_t)r * 128;
-                    const unsigned char *pl = H1l + (size_t)(e >> 3) * (W / 32 * 1024) + (size_t)((c0 >> 5) + ch) * 1024 + (size_t)r * 128;
+                    const unsigned char *ph = H1s + (size_t)(e >> 3) * (W / 32 * 1024) + (size_t)((c0 >> 5) + ch) * 1024 + (size_t)r * 128;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const uint32_t o = (uint32_t)((((i >> 1) ^ (r & 3)) << 5) + (i & 1) * 16);
-                        const float4 vh = *reinterpret_cast<const float4 *>(ph + o);
-                        const float4 vl = *reinterpret_cast<const float4 *>(pl + o);
-                        z[4 * i] *= act_bwd_from_out(vh.x + vl.x, act_kind);
-                        z[4 * i + 1] *= act_bwd_from_out(vh.y + vl.y, act_kind);
-                        z[4 * i + 2] *= act_bwd_from_out(vh.z + vl.z, act_kind);
-                        z[4 * i + 3] *= act_bwd_from_out(vh.w + vl.w, act_kind);
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        float hv[8];
+                        ldg256(ph + (uint32_t)((c8 ^ (r & 3)) << 5), hv);
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) z[8 * c8 + jj] *= act_bwd_from_out(hv[jj], act_kind);
                     }
                 }
-                tcw_emit32<W, false>(Z1h, Z1l, e, (c0 >> 5) + ch, z, 0u, 0u);
+                tcw_emit32<W, false>(Z1s, e, (c0 >> 5) + ch, z, 0u, 0u);
             }
             tc_fence_before();
         }
@@ -764,12 +753,13 @@ __global__ void __launch_bounds__(192, 1) update_tcw_wgrad_kernel(const __grid_c
     constexpr uint32_t TM_DW = 0u, TM_D0 = (uint32_t)W;
     if (a.k_begin + blockIdx.x >= a.tstart[a.T]) return;      // no live tile for this CTA in this batch (CTA-uniform)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[NST], empty_bar[NST], done_bar;
+    __shared__ __align__(8) uint64_t full_bar[NST], conv_bar[NST], empty_bar[NST], done_bar;
     __shared__ uint32_t tmem_slot;
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
     if (threadIdx.x == 0) {
         for (int i = 0; i < NST; ++i) {
             mbar_init(&full_bar[i], 1);
+            mbar_init(&conv_bar[i], 128);
             mbar_init(&empty_bar[i], 1);
         }
         mbar_init(&done_bar, 1);
@@ -793,21 +783,19 @@ __global__ void __launch_bounds__(192, 1) update_tcw_wgrad_kernel(const __grid_c
                 if (!(first_tile ? tcw_tile_of(a.tstart, a.T, k, &t, &blk) : tcw_tile_next(a.tstart, a.T, k, &t, &blk))) break;
                 first_tile = false;
                 const unsigned char *tile_sc = a.sc.base + (size_t)(k - a.k_begin) * a.sc.tile_bytes;
-                const unsigned char *arr[6];
-                for (int i = 0; i < 6; ++i) arr[i] = tile_sc + (size_t)i * a.sc.arr_bytes;
-                const unsigned char *Xh = tile_sc + 6 * (size_t)a.sc.arr_bytes, *Xl = Xh + a.sc.x_bytes;
+                const unsigned char *arr[3];
+                for (int i = 0; i < 3; ++i) arr[i] = tile_sc + (size_t)i * a.sc.arr_bytes;
+                const unsigned char *Xh = tile_sc + 3 * (size_t)a.sc.arr_bytes, *Xl = Xh + a.sc.x_bytes;
                 for (int sb = 0; sb < 16; ++sb, ++gi) {
                     const uint32_t st = gi % NST, ph = (gi / NST) & 1u;
                     mbar_wait(&empty_bar[st], ph ^ 1u);
-                    mbar_expect_tx(&full_bar[st], STAGE);
+                    mbar_expect_tx(&full_bar[st], 2 * ZB + HB + 2 * XB);
                     unsigned char *dst = smem_raw + (size_t)st * STAGE_AL;
                     const size_t sbo = (size_t)sb * HB, ho = (size_t)half * ZB;
-                    tma_bulk_g2s(dst, arr[2] + sbo + ho, ZB, &full_bar[st]);                 // Z2h (half)
-                    tma_bulk_g2s(dst + ZB, arr[3] + sbo + ho, ZB, &full_bar[st]);            // Z2l
-                    tma_bulk_g2s(dst + 2 * ZB, arr[4] + sbo + ho, ZB, &full_bar[st]);        // Z1h
-                    tma_bulk_g2s(dst + 3 * ZB, arr[5] + sbo + ho, ZB, &full_bar[st]);        // Z1l
-                    tma_bulk_g2s(dst + 4 * ZB, arr[0] + sbo, HB, &full_bar[st]);             // H1h (all columns)
-                    tma_bulk_g2s(dst + 4 * ZB + HB, arr[1] + sbo, HB, &full_bar[st]);        // H1l
+                    // fp32 rows land in the "hi" slots; the converter warps split them in place (hi) and into the lo slots
+                    tma_bulk_g2s(dst, arr[1] + sbo + ho, ZB, &full_bar[st]);                 // dZ2 (this half)
+                    tma_bulk_g2s(dst + 2 * ZB, arr[2] + sbo + ho, ZB, &full_bar[st]);        // dZ1 (this half)
+                    tma_bulk_g2s(dst + 4 * ZB, arr[0] + sbo, HB, &full_bar[st]);             // H1 (all columns)
                     tma_bulk_g2s(dst + 4 * ZB + 2 * HB, Xh + (size_t)sb * XB, XB, &full_bar[st]);
                     tma_bulk_g2s(dst + 4 * ZB + 2 * HB + XB, Xl + (size_t)sb * XB, XB, &full_bar[st]);
                 }
@@ -826,7 +814,7 @@ __global__ void __launch_bounds__(192, 1) update_tcw_wgrad_kernel(const __grid_c
             if (lane == 0) {
                 for (int sb = 0; sb < 16; ++sb, ++gi) {
                     const uint32_t st = gi % NST, ph = (gi / NST) & 1u;
-                    mbar_wait(&full_bar[st], ph);
+                    mbar_wait(&conv_bar[st], ph);             // landed AND split by the converter warps
                     tc_fence_after();
                     const uint32_t base = smem_u32(smem_raw) + st * STAGE_AL;
                     const uint32_t z2h = base, z2l = base + ZB, z1h = base + 2 * ZB, z1l = base + 3 * ZB;
@@ -848,6 +836,39 @@ __global__ void __launch_bounds__(192, 1) update_tcw_wgrad_kernel(const __grid_c
         }
         if (lane == 0 && any) umma_commit(&done_bar);
         __syncwarp();
+    }
+    if (warp < 4) {
+        // ===== converter warps: tf32 hi/lo split of the fp32 rows of every stage, in shared memory =====
+        uint32_t gi = 0;
+        int t = 0, blk = 0;
+        bool first_tile = true;
+        constexpr int NF4 = (2 * ZB + HB) / 16;            // float4 items per stage: dZ2 | dZ1 | H1
+        for (int64_t k = a.k_begin + blockIdx.x; k < k_end; k += gridDim.x) {
+            if (!(first_tile ? tcw_tile_of(a.tstart, a.T, k, &t, &blk) : tcw_tile_next(a.tstart, a.T, k, &t, &blk))) break;
+            first_tile = false;
+            for (int sb = 0; sb < 16; ++sb, ++gi) {
+                const uint32_t st = gi % NST, ph = (gi / NST) & 1u;
+                mbar_wait(&full_bar[st], ph);
+                unsigned char *base = smem_raw + (size_t)st * STAGE_AL;
+#pragma unroll 2
+                for (int f = threadIdx.x; f < NF4; f += 128) {
+                    const uint32_t b = (uint32_t)f * 16u;
+                    // slot of this item: dZ2 at 0 (lo at ZB), dZ1 at 2 ZB (lo at 3 ZB), H1 at 4 ZB (lo at 4 ZB + HB)
+                    unsigned char *hp, *lp;
+                    if (b < ZB) { hp = base + b; lp = hp + ZB; }
+                    else if (b < 2 * ZB) { hp = base + 2 * ZB + (b - ZB); lp = hp + ZB; }
+                    else { hp = base + 4 * ZB + (b - 2 * ZB); lp = hp + HB; }
+                    const float4 v = *reinterpret_cast<const float4 *>(hp);
+                    float4 h4, l4;
+                    h4.x = tf32_hi(v.x); h4.y = tf32_hi(v.y); h4.z = tf32_hi(v.z); h4.w = tf32_hi(v.w);
+                    l4.x = v.x - h4.x; l4.y = v.y - h4.y; l4.z = v.z - h4.z; l4.w = v.w - h4.w;
+                    *reinterpret_cast<float4 *>(hp) = h4;
+                    *reinterpret_cast<float4 *>(lp) = l4;
+                }
+                fence_proxy_async();
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv_bar[st])) : "memory");
+            }
+        }
     }
     // did this CTA process any tile?  (uniform: its first tile index is live or not)
     {
@@ -941,7 +962,7 @@ int tg_policy_grad_tcw(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, con
     // per-tile scratch; batch = as many tiles as fit the budget (a multiple of the grid)
     a.sc.arr_bytes = (int64_t)16 * (W / 32) * 1024;
     a.sc.x_bytes = (int64_t)16 * a.lay.OKP * 32;
-    a.sc.tile_bytes = 6 * a.sc.arr_bytes + 2 * a.sc.x_bytes;
+    a.sc.tile_bytes = 3 * a.sc.arr_bytes + 2 * a.sc.x_bytes;
     const int64_t NB = (N + 127) / 128;
     const int64_t total_upper = NB * T;                       // live tiles <= this
     const int64_t budget = (int64_t)1 << 30;
