@@ -11,10 +11,10 @@
 //       registers -> tensor memory as the A operand (K halves at W = 256).  The first Linear runs on the
 //       tensor core too (obs hi/lo + ones column carrying the bias).  Per tile the kernel leaves in an HBM
 //       scratch, already hi/lo split and in the operand layout of kernel B:  H1, dZ2, dZ1 (MN-major
-//       SW128_32B, 8-sample sub-blocks) and [x, 1] (K-major).  dWo, dbo, db1 (one column sum per column over
-//       the tile) stay on register butterflies here.
+//       SW128_32B, 8-sample sub-blocks) and [x, 1] (K-major).  dWo and dbo (column sums over the tile) stay on register
+//       butterflies here.
 //   kernel B  (update_tcw_wgrad_kernel)   split-K weight-gradient GEMMs over the batch's samples:
-//       dW1[half] += dZ2[:, half]^T . H1   and   [dW0 | db0][half] += dZ1[:, half]^T . [x, 1],
+//       dW1[half] += dZ2[:, half]^T . H1,   [dW0 | db0][half] += dZ1[:, half]^T . [x, 1],   db1[half] = (dZ2[:, half]^T . [x, 1])[:, ones],
 //       operands streamed from the scratch by TMA (8 samples per stage), accumulators persistent in tensor
 //       memory for all tiles of the launch, added to the CTA-private gradient copy at the end.  One launch
 //       per 128-row half of the outputs (two at W = 256).  HBM-bound by construction (about 8-12 KB per sample).
@@ -448,10 +448,9 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
         const float *b1 = Rsm + a.lay.b1 + c0, *wo = Rsm + a.lay.wo + c0, *bo = Rsm + a.lay.bo;
         uint32_t ph_d = 0, ph_k0 = 0;
         // butterfly partials (this warp's sum over its 32 samples of column c0 + 32*ch + lane)
-        float c_b1[NCH], c_wo[A][NCH], c_bo[A];
+        float c_wo[A][NCH], c_bo[A];
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
-            c_b1[ch] = 0.0f;
 #pragma unroll
             for (int j = 0; j < A; ++j) c_wo[j][ch] = 0.0f;
         }
@@ -659,7 +658,6 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
                     const uint32_t th = my_tm + TM_AHI + acol0 + (uint32_t)(ch * 32), tl = my_tm + TM_ALO + acol0 + (uint32_t)(ch * 32);
                     if (deferred) tcw_emit32<W, false>(Z2s, e, (c0 >> 5) + ch, z, th, tl);
                     else tcw_emit32<W, true>(Z2s, e, (c0 >> 5) + ch, z, th, tl);
-                    c_b1[ch] += tcw_colsum32(z, lane);
                 }
             }
             finish_A(Z2s);
@@ -692,13 +690,12 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
         }
         // ---- this CTA's butterfly partials and statistics into its private gradient copy (accumulated)
         float *gp = a.gpart + (int64_t)blockIdx.x * a.lay.n_params;
-        const int64_t f1 = a.lay.flat_w[1], f2 = a.lay.flat_w[2];
+        const int64_t f2 = a.lay.flat_w[2];
         for (int qs = 0; qs < 4; ++qs) {
             if (q == qs) {
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch) {
                     const int col = c0 + ch * 32 + lane;
-                    gp[f1 + (int64_t)W * W + col] += c_b1[ch];
 #pragma unroll
                     for (int jj = 0; jj < A; ++jj) gp[f2 + (int64_t)jj * W + col] += c_wo[jj][ch];
                 }
@@ -750,7 +747,7 @@ __global__ void __launch_bounds__(192, 1) update_tcw_wgrad_kernel(const __grid_c
     constexpr uint32_t STAGE = 4 * ZB + 2 * HB + 2 * XB;
     constexpr uint32_t STAGE_AL = (STAGE + 1023) / 1024 * 1024;
     constexpr int NST = 5;
-    constexpr uint32_t TM_DW = 0u, TM_D0 = (uint32_t)W;
+    constexpr uint32_t TM_DW = 0u, TM_D0 = (uint32_t)W, TM_D1 = (uint32_t)W + 32u;
     if (a.k_begin + blockIdx.x >= a.tstart[a.T]) return;      // no live tile for this CTA in this batch (CTA-uniform)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[NST], conv_bar[NST], empty_bar[NST], done_bar;
@@ -828,6 +825,9 @@ __global__ void __launch_bounds__(192, 1) update_tcw_wgrad_kernel(const __grid_c
                     umma_tf32(tmem + TM_D0, umma_desc_mn32(z1h, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, acc0);
                     umma_tf32(tmem + TM_D0, umma_desc_mn32(z1h, 1024u), umma_operand_desc(xl, 8, false, 0), idesc_x, 1u);
                     umma_tf32(tmem + TM_D0, umma_desc_mn32(z1l, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, 1u);
+                    // db1[half] = column O of dZ2^T . [x, 1] (the ones column is exact in tf32: two passes)
+                    umma_tf32(tmem + TM_D1, umma_desc_mn32(z2h, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, acc0);
+                    umma_tf32(tmem + TM_D1, umma_desc_mn32(z2l, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, 1u);
                     first = 0u;
                     umma_commit(&empty_bar[st]);
                 }
@@ -894,6 +894,8 @@ __global__ void __launch_bounds__(192, 1) update_tcw_wgrad_kernel(const __grid_c
 #pragma unroll
             for (int o = 0; o < O; ++o) gp[f0 + (int64_t)row * O + o] += z[o];
             gp[f0 + (int64_t)W * O + row] += z[O];
+            tmem_ld32(my_tm + TM_D1, z);
+            gp[f1 + (int64_t)W * W + row] += z[O];
         }
         tc_fence_before();
     }
