@@ -383,14 +383,18 @@ def run_ours(args, w):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     bf16_peak = peaks.get("bf16_tflops", 1590.0)
-    tc = w["hidden"] == [64, 64]          # the shapes the tcgen05 kernels cover (tg_update_tc_eligible)
+    tc = w["hidden"] in ([64, 64], [128, 128], [256, 256])     # shapes with a tcgen05 update path (fused 64, streamed 128/256)
+    k3_name = ("update_tc_kernel (tg_policy_grad: fused fwd + clipped surrogate + MLP backward, tcgen05 3xTF32)"
+               if w["hidden"] == [64, 64] else
+               "update_tcw_fwdbwd_kernel + update_tcw_wgrad_kernel (tg_policy_grad: streamed forward/backward + split-K "
+               "weight gradients, tcgen05 3xTF32)")
     k3_tf = k3_flops / (k3_ms * 1e-3) / 1e12
     k1_tf = k1_flops / (k1_ms * 1e-3) / 1e12
     if tc:
         # K3/K1 hidden GEMMs run on the tensor cores as 3xTF32: every algorithmic MAC costs 3 tf32 MMA-MACs and
         # tf32 peaks at half the bf16 rate, so an fp32-faithful kernel tops out at bf16_peak / 6.
         roofline = {
-            "kernel": "update_tc_kernel (tg_policy_grad: fused fwd + clipped surrogate + MLP backward, tcgen05 3xTF32)",
+            "kernel": k3_name,
             "bound": "tensor", "achieved": k3_tf, "peak": bf16_peak, "unit": "TFLOP/s", "frac": k3_tf / bf16_peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else
                            "fallback of /opt/skills/guides/B200_PROFILING.md (MEASURED_PEAKS.json absent)",

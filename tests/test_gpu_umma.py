@@ -239,3 +239,36 @@ def test_value_grad_wide_tensor_core_path_matches_fp32_path(O, width, act_name):
         assert np.abs(g - ref).max() <= 2e-4 * sc, (mode, np.abs(g - ref).max(), sc)
         assert int(st[1]) == int(mask.sum()), mode
     assert np.abs(out["fp32"][0] - out["3xtf32"][0]).max() <= 5e-5 * sc
+
+
+def test_wide_update_spans_several_scratch_batches():
+    """The streamed 128-wide update at a size whose tiles do not fit one 1 GB scratch batch (6,400 tiles of
+    198 KB), ragged lengths: gradient and statistics vs the FP32-pipe kernel, and run-to-run determinism."""
+    from trajopt_grpo_b200 import engine as E
+    rng = np.random.default_rng(77)
+    O, A, W = 10, 2, 128
+    dims = [O, W, W, A]
+    Ws, bs, params = _policy(rng, dims)
+    N, T = 4096, 200
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    obs = torch.randn((T, O, N), device="cuda", generator=gen)
+    act = torch.randn((T, A, N), device="cuda", generator=gen)
+    adv = torch.randn((T, N), device="cuda", generator=gen)
+    olp = -1.5 + 0.1 * torch.randn((T, N), device="cuda", generator=gen)
+    ln = torch.randint(1, T + 1, (N,), device="cuda", generator=gen, dtype=torch.int32)
+    out = {}
+    try:
+        for mode in ("fp32", "3xtf32", "3xtf32"):
+            E.set_math(mode)
+            g, st = E.policy_grad(dims, "ReLU", params, [0.4, 0.4], obs, act, adv, olp, ln, 0.2, 1.0 / 256)
+            torch.cuda.synchronize()
+            out.setdefault(mode, []).append((g.clone(), st.clone()))
+    finally:
+        E.set_math("auto")
+    (g1, s1), (g2, s2) = out["3xtf32"]
+    assert torch.equal(g1, g2) and torch.equal(s1, s2)            # deterministic
+    gf, sf = out["fp32"][0]
+    assert int(s1[1]) == int(ln.sum()) == int(sf[1])
+    scale = gf.abs().max().item()
+    assert (g1 - gf).abs().max().item() <= 2e-4 * scale
+    assert abs(float(s1[0]) - float(sf[0])) <= 2e-4 * max(1.0, abs(float(sf[0])))
