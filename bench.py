@@ -45,6 +45,12 @@ WORKLOADS = {
     "quadpole2d": dict(kind=2, cls="QuadPole2D", T=500, E=16, G=16384, hidden=[128, 128], cov=1e-4, gamma=0.99,
                        eps=0.2, lr=2e-4, updates=2, hover_init=True,
                        desc="QuadPole2D GRPO, 262,144 envs x 500 steps, group 16, MLP 128x128, hover-biased init"),
+    # BASELINE configs[2] names PPO as well: the shipped quadpole2d_pipeline_ppo.py setting (full batch, GAE off =
+    # Monte-Carlo returns, c1 0.5, kl 0.5) with 2 instead of 24 updates per epoch to keep the run short
+    "quadpole2d_ppo": dict(kind=2, cls="QuadPole2D", T=500, E=16, G=16384, hidden=[128, 128], cov=1e-4, gamma=0.99,
+                           eps=0.2, lr=2e-4, updates=2, hover_init=True, algo="ppo",
+                           desc="QuadPole2D PPO (actor + critic 128x128, full batch), 262,144 envs x 500 steps, "
+                                "hover-biased init"),
     "quadpole": dict(kind=3, cls="QuadPole", T=1000, E=64, G=1024, hidden=[256, 256], cov=1e-4, gamma=0.999, eps=0.2,
                      lr=3e-4, updates=1, hover_init=True,
                      desc="3D QuadPole GRPO, 65,536 envs x 1000 steps, group 64, MLP 256x256, hover-biased init"),
@@ -193,13 +199,19 @@ def run_ours(args, w):
     P = mlp_macs(dims)
 
     torch.manual_seed(1234)                      # identical initial weights on every rank
-    policy = tg.GaussianActor_NeuralNetwork(O, A, w["hidden"], "ReLU", w["cov"])
+    ppo = w.get("algo") == "ppo"
+    policy = (tg.GaussianActorCritic_NeuralNetwork if ppo else tg.GaussianActor_NeuralNetwork)(O, A, w["hidden"], "ReLU",
+                                                                                              w["cov"])
     if w.get("hover_init"):
         with torch.no_grad():
             last = policy.actor.network[-1]
             last.weight.zero_(); last.bias.zero_()
     opt = torch.optim.Adam(policy.parameters(), lr=w["lr"] * (1e-3 if w.get("hover_init") else 1.0))
-    algo = tg.GRPO(w["eps"], 0.01, w["gamma"], policy, opt, None, updates_per_iter=w["updates"])
+    if ppo:
+        algo = tg.PPO(w["eps"], policy, opt, None, w["updates"], c1=0.5, kl_coeff=0.5, gamma=w["gamma"], lam=0.95,
+                      entropy=0.01, batch_size=None, monte_carlo=True)
+    else:
+        algo = tg.GRPO(w["eps"], 0.01, w["gamma"], policy, opt, None, updates_per_iter=w["updates"])
     env_cls = getattr(tg, w["cls"])
     mgr = tg.RolloutManager(lambda: env_cls(max_steps=T), policy, restart=True, num_workers=G * world,
                             num_episodes_per_worker=E, use_multiprocessing=False, seed=7, rank=rank, world_size=world)
@@ -283,7 +295,7 @@ def run_ours(args, w):
     # ---------------- dominant-kernel timing: K3 alone, CUDA events on its stream -------------
     r = buf.device_rollout
     adv, _ = engine.advantage(0, r.G, r.E, r.T, w["gamma"], 0.0, r.rew, r.len)
-    flat = policy.flat_parameters()
+    flat = policy.actor.flat_params() if ppo else policy.flat_parameters()
     k3 = []
     for i in range(3 + 5):
         a, b = ev(), ev()
