@@ -45,6 +45,12 @@ WORKLOADS = {
     "quadpole2d": dict(kind=2, cls="QuadPole2D", T=500, E=16, G=16384, hidden=[128, 128], cov=1e-4, gamma=0.99,
                        eps=0.2, lr=2e-4, updates=2, hover_init=True,
                        desc="QuadPole2D GRPO, 262,144 envs x 500 steps, group 16, MLP 128x128, hover-biased init"),
+    # BASELINE configs[3] at its full size when run on 8 GPUs: 8 x 524,288 = 4,194,304 envs x 1000 steps, group 64
+    # (55 GB of trajectory per GPU); `python -m torch.distributed.run --nproc-per-node 8 bench.py --gpus 8 --workload quadpole_cfg4`
+    "quadpole_cfg4": dict(kind=3, cls="QuadPole", T=1000, E=64, G=8192, hidden=[256, 256], cov=1e-4, gamma=0.999, eps=0.2,
+                          lr=3e-4, updates=1, hover_init=True,
+                          desc="3D QuadPole GRPO, 524,288 envs per GPU x 1000 steps (4,194,304 envs on 8 GPUs), group 64, "
+                               "MLP 256x256, hover-biased init"),
     # BASELINE configs[2] names PPO as well: the shipped quadpole2d_pipeline_ppo.py setting (full batch, GAE off =
     # Monte-Carlo returns, c1 0.5, kl 0.5) with 2 instead of 24 updates per epoch to keep the run short
     "quadpole2d_ppo": dict(kind=2, cls="QuadPole2D", T=500, E=16, G=16384, hidden=[128, 128], cov=1e-4, gamma=0.99,
