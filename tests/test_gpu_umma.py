@@ -272,3 +272,19 @@ def test_wide_update_spans_several_scratch_batches():
     scale = gf.abs().max().item()
     assert (g1 - gf).abs().max().item() <= 2e-4 * scale
     assert abs(float(s1[0]) - float(sf[0])) <= 2e-4 * max(1.0, abs(float(sf[0])))
+
+
+def test_tmem_probe_reports_cheap_tensor_memory_accesses():
+    """tg_tmem_probe (the microbenchmark behind DESIGN's issue-cost rule): a tcgen05.ld / st pair stays cheap with
+    MMAs in flight, and the MMAs retire in a time that grows with their number."""
+    import ctypes as C
+    from trajopt_grpo_b200 import _lib as L
+    lib = L.load()
+    res = {}
+    for n in (0, 48, -48):
+        out = (C.c_longlong * 4)()
+        L.check(lib.tg_tmem_probe(L.ctx(torch.device("cuda", 0)), n, out), "tg_tmem_probe")
+        res[n] = list(out)
+    assert 0 < res[48][0] < 500 and 0 < res[48][1] < 1000          # ld, st(+wait) clocks
+    assert res[48][2] > res[0][2]                                    # 48 MMAs take longer than none
+    assert res[-48][3] < res[48][3]                                  # warp-uniform issue is cheaper than the lane-0 branch
