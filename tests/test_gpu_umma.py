@@ -288,3 +288,32 @@ def test_tmem_probe_reports_cheap_tensor_memory_accesses():
     assert 0 < res[48][0] < 500 and 0 < res[48][1] < 1000          # ld, st(+wait) clocks
     assert res[48][2] > res[0][2]                                    # 48 MMAs take longer than none
     assert res[-48][3] < res[48][3]                                  # warp-uniform issue is cheaper than the lane-0 branch
+
+
+@pytest.mark.parametrize("O,A,width,act_name", [(10, 2, 128, "ReLU"), (20, 4, 256, "Tanh"), (20, 1, 256, "ReLU")])
+def test_policy_forward_traj_wide_tensor_core_path_matches_fp32_path(O, A, width, act_name):
+    """tg_policy_forward_traj (critic values / old log-probs over a rollout) for 128/256-wide nets on the streamed
+    tensor-core forward vs the FP32-pipe kernel; ragged lengths, rows past the length stay zero."""
+    from trajopt_grpo_b200 import engine as E
+    rng = np.random.default_rng(O * A + width)
+    dims = [O, width, width, A]
+    Ws, bs, params = _policy(rng, dims)
+    N, T = 333, 6
+    obs = torch.from_numpy(rng.standard_normal((T, O, N)).astype(np.float32)).cuda()
+    act = torch.from_numpy(rng.standard_normal((T, A, N)).astype(np.float32)).cuda()
+    ln = torch.from_numpy(rng.integers(1, T + 1, N).astype(np.int32)).cuda()
+    out = {}
+    try:
+        for mode in ("fp32", "3xtf32"):
+            E.set_math(mode)
+            mu, lp = E.policy_forward_traj(dims, act_name, params, obs, [0.3] * A, act, ln, want_mu=True, want_logp=True)
+            torch.cuda.synchronize()
+            out[mode] = (mu.clone(), lp.clone())
+    finally:
+        E.set_math("auto")
+    mask = (torch.arange(T, device="cuda")[:, None] < ln[None, :])
+    for k in (0, 1):
+        a32, atc = out["fp32"][k], out["3xtf32"][k]
+        assert (a32 - atc).abs().max().item() <= 2e-5 * max(1.0, a32.abs().max().item())
+    assert float(out["3xtf32"][1][~mask].abs().max()) == 0.0
+    assert float(out["3xtf32"][0].permute(0, 2, 1)[~mask].abs().max()) == 0.0

@@ -121,7 +121,8 @@ bool tg_update_tcw_shape_built(const tg_mlp_cfg *mlp);
 int tg_policy_grad_tcw(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, const float *obs, const float *act,
                        const float *adv, const float *old_logp, const float *target, const int32_t *len, const float *params,
                        const float *inv_sd, const float *inv_var, float log_norm, float eps_clip, float scale,
-                       float kl_scale, float *gpart, double *spart, int grid, cudaStream_t st);
+                       float kl_scale, float *gpart, double *spart, int grid, cudaStream_t st, float *out_mu = nullptr,
+                       float *out_logp = nullptr);   // out_mu / out_logp non-null: forward only (no gradients)
 // tensor-core update kernel (tg_update_tc.cu)
 bool tg_update_tc_eligible(const tg_mlp_cfg *mlp);
 int tg_update_tc_grid(const tg_ctx *ctx);

@@ -596,6 +596,9 @@ extern "C" int tg_policy_forward_traj(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_
     a.obs = obs; a.act = act; a.len = len; a.out_mu = out_mu; a.out_logp = out_logp;
     cudaStream_t st = (cudaStream_t)stream;
     TG_CUDA(cudaSetDevice(ctx->device));
+    if (len != nullptr && tg_update_tcw_shape_built(mlp) && ctx->math_mode != TG_MATH_FP32)   // wide: streamed tensor-core forward
+        return tg_policy_grad_tcw(ctx, mlp, N, T, obs, act, nullptr, nullptr, nullptr, len, params, a.inv_sd, a.inv_var,
+                                  a.log_norm, 0.0f, 0.0f, 0.0f, nullptr, nullptr, ctx->sm_count, st, out_mu, out_logp);
     rc = tg_pack_weights(ctx, a.lay, params, st);
     if (rc) return rc;
     a.packed = ctx->packed;

@@ -65,6 +65,10 @@ struct TcwArgs {
     float *gpart;                         // [grid][n_params], accumulated (+=) across launches
     double *spart;                        // [grid][4], accumulated
     int half;                             // kernel B: which 128-row half of the outputs
+    // forward-only mode (tg_policy_forward_traj: critic values over a rollout ppo.py:93-94, old log-probs
+    // ppo.py:142-143 / grpo.py:118-119): kernel A stops after the output layer and writes these; no kernel B
+    int forward_only;
+    float *out_mu, *out_logp;
 };
 
 bool tg_update_tcw_eligible(const tg_mlp_cfg *mlp) {
@@ -350,7 +354,7 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
             for (int64_t k = a.k_begin + blockIdx.x; k < k_end; k += gridDim.x) {
                 if (!(first_tile ? tcw_tile_of(a.tstart, a.T, k, &t, &blk) : tcw_tile_next(a.tstart, a.T, k, &t, &blk))) break;
                 first_tile = false;
-                for (int dir = 0; dir < 2; ++dir) {
+                for (int dir = 0; dir < (a.forward_only ? 1 : 2); ++dir) {
                     const float *src = dir ? srcb : srcf;
                     for (int i = 0; i < 2 * NKC; ++i, ++gi) {
                         const uint32_t st = gi % TCW_STAGES, ph = (gi / TCW_STAGES) & 1u;
@@ -391,7 +395,7 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
                 umma_commit(&bar_d);
             }
             __syncwarp();
-            for (int dir = 0; dir < 2; ++dir) {           // 0: forward (K-major B), 1: backward-data (MN-major B)
+            for (int dir = 0; dir < (a.forward_only ? 1 : 2); ++dir) {   // 0: forward (K-major B), 1: backward-data (MN-major B)
                 for (int half = 0; half < KH; ++half) {
                     if (half == 0) tcw_sync(TCW_BAR_K0, CNT_ALL);
                     else tcw_sync(TCW_BAR_K1, CNT_H1);
@@ -494,11 +498,13 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
             const int64_t j = (int64_t)blk * 128 + e;
             const bool valid = j < a.cnt[t];
             float av[A], adv = 0.f, olp = 0.f;
+            int64_t n_own = 0;
 #pragma unroll
             for (int jj = 0; jj < A; ++jj) av[jj] = 0.0f;
             if (part == 0) {
                 int64_t n = 0;
                 if (valid) n = a.perm[j];
+                n_own = n;
                 // every global load of the tile first (they are independent gathers, mostly HBM misses), THEN the
                 // stores: interleaved, the compiler must keep each load behind the previous scratch store (possible
                 // aliasing) and the tile start paid O serial DRAM latencies (measured 13-25k clocks per tile)
@@ -508,6 +514,11 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
                 if (valid) {
                     if (a.target != nullptr) {
                         adv = __ldg(a.target + (int64_t)t * N + n);       // the regression target rides in `adv`
+                    } else if (a.forward_only) {
+                        if (a.act != nullptr) {
+#pragma unroll
+                            for (int jj = 0; jj < A; ++jj) av[jj] = __ldg(a.act + ((int64_t)t * A + jj) * N + n);
+                        }
                     } else {
 #pragma unroll
                         for (int jj = 0; jj < A; ++jj) av[jj] = __ldg(a.act + ((int64_t)t * A + jj) * N + n);
@@ -590,7 +601,23 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
                     mu[jj] = m;
                     dmu[jj] = 0.0f;
                 }
-                if (valid && a.target != nullptr) {
+                if (a.forward_only) {
+                    if (valid) {
+                        if (a.out_mu) {
+#pragma unroll
+                            for (int jj = 0; jj < A; ++jj) a.out_mu[((int64_t)t * A + jj) * N + n_own] = mu[jj];
+                        }
+                        if (a.out_logp) {
+                            float m2 = 0.0f;
+#pragma unroll
+                            for (int jj = 0; jj < A; ++jj) {
+                                const float zz = (av[jj] - mu[jj]) * a.inv_sd[jj];
+                                m2 += zz * zz;
+                            }
+                            a.out_logp[(int64_t)t * N + n_own] = -0.5f * m2 - a.log_norm;
+                        }
+                    }
+                } else if (valid && a.target != nullptr) {
                     const float err = mu[0] - adv;                   // MSELoss(V, target), ppo.py:168-169
                     s_obj += (double)err * err;
                     s_cnt += 1.0;
@@ -627,6 +654,10 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
                 }
 #pragma unroll
                 for (int jj = 0; jj < A; ++jj) dmuS[jj][e] = dmu[jj];
+            }
+            if (a.forward_only) {           // CTA-uniform: the next tile's L1 GEMM may overwrite D once everybody read it
+                tc_fence_before();
+                continue;
             }
             tcw_sync(q + 1, NP * 32);
             // ---- epilogue 2b: dZ2 = (Wo^T dmu) * act'(H2); column sums for dWo, db1; scratch dZ2; A operand
@@ -688,6 +719,7 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
             }
             tc_fence_before();
         }
+        if (!a.forward_only) {
         // ---- this CTA's butterfly partials and statistics into its private gradient copy (accumulated)
         float *gp = a.gpart + (int64_t)blockIdx.x * a.lay.n_params;
         const int64_t f2 = a.lay.flat_w[2];
@@ -729,6 +761,7 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
                 }
                 asm volatile("bar.sync 8, %0;" ::"n"(NCT) : "memory");
             }
+        }
         }
     }
     tc_fence_before();
@@ -924,7 +957,7 @@ static int launch_tcw(const TcwArgs &a0, int grid, int64_t total_upper, int64_t 
         a.k_begin = k0;
         a.k_count = (total_upper - k0) < batch_tiles ? (total_upper - k0) : batch_tiles;
         kA<<<grid, NP * 128 + 64, smemA, st>>>(a);
-        for (int half = 0; half < W / 128; ++half) {
+        for (int half = 0; half < (a.forward_only ? 0 : W / 128); ++half) {
             a.half = half;
             kB<<<grid, 192, smemB, st>>>(a);
         }
@@ -950,7 +983,8 @@ static int reserve_bytes(void **p, size_t *cap, size_t bytes) {
 int tg_policy_grad_tcw(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, const float *obs, const float *act,
                        const float *adv, const float *old_logp, const float *target, const int32_t *len, const float *params,
                        const float *inv_sd, const float *inv_var, float log_norm, float eps_clip, float scale,
-                       float kl_scale, float *gpart, double *spart, int grid, cudaStream_t st) {
+                       float kl_scale, float *gpart, double *spart, int grid, cudaStream_t st, float *out_mu,
+                       float *out_logp) {
     TcwArgs a;
     memset(&a, 0, sizeof(a));
     build_tcw_layout(mlp, &a.lay);
@@ -984,6 +1018,8 @@ int tg_policy_grad_tcw(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, con
     for (int j = 0; j < TG_MAX_ACT; ++j) { a.inv_sd[j] = inv_sd ? inv_sd[j] : 1.0f; a.inv_var[j] = inv_var ? inv_var[j] : 1.0f; }
     a.log_norm = log_norm; a.eps_clip = eps_clip; a.scale = scale; a.kl_scale = kl_scale;
     a.gpart = gpart; a.spart = spart;
+    a.out_mu = out_mu; a.out_logp = out_logp;
+    a.forward_only = (out_mu != nullptr || out_logp != nullptr) ? 1 : 0;
 #define TCW_CASE(OO, AA)                                                                                  \
     if (O == OO && A == AA)                                                                               \
         return W == 128 ? launch_tcw<OO, AA, 128>(a, grid, total_upper, batch_tiles, st)                  \
