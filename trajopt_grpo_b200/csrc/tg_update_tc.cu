@@ -78,6 +78,33 @@ TG_D float colsum16(float *v, int lane) {
     const float other = __shfl_xor_sync(0xffffffffu, v[0], 1);
     return (lane & 1) ? other + v[0] : v[0] + other;
 }
+// Two independent column sums interleaved level by level: a butterfly is a chain of 5 dependent shuffle rounds and
+// a single one runs at ~0.15 instructions per clock; two in flight hide each other's shuffle latency.
+template <int HALF, int OFF> TG_D void colsum_step2(float *v0, float *v1, int lane) {
+    const bool up = (lane & OFF) != 0;
+#pragma unroll
+    for (int j = 0; j < HALF; ++j) {
+        const float s0 = up ? v0[j] : v0[j + HALF], k0 = up ? v0[j + HALF] : v0[j];
+        const float s1 = up ? v1[j] : v1[j + HALF], k1 = up ? v1[j + HALF] : v1[j];
+        const float r0 = __shfl_xor_sync(0xffffffffu, s0, OFF), r1 = __shfl_xor_sync(0xffffffffu, s1, OFF);
+        v0[j] = k0 + r0;
+        v1[j] = k1 + r1;
+    }
+}
+template <int NC> TG_D void colsumN2(float *v0, float *v1, int lane, float &r0, float &r1) {
+    if (NC == 32) {
+        colsum_step2<16, 16>(v0, v1, lane);
+        colsum_step2<8, 8>(v0, v1, lane);
+        colsum_step2<4, 4>(v0, v1, lane);
+        colsum_step2<2, 2>(v0, v1, lane);
+        colsum_step2<1, 1>(v0, v1, lane);
+        r0 = v0[0];
+        r1 = v1[0];
+    } else {
+        r0 = colsum16(v0, lane);
+        r1 = colsum16(v1, lane);
+    }
+}
 template <int NC> TG_D float colsumN(float *v, int lane) {
     if (NC == 32) return colsum32(v, lane);
     return colsum16(v, lane);
@@ -287,14 +314,28 @@ __global__ void __launch_bounds__(NPART * 128 + 32, 1) update_tc_kernel(const __
                 d1[4 * i + 3] *= act_bwd_from_out(vh.w + vl.w, act_kind);
             }
         }
+        // O + 1 column sums (dW0 columns and db0), two at a time
 #pragma unroll
-        for (int o = 0; o < O; ++o) {
-            float v[HW];
+        for (int o = 0; o + 1 < O; o += 2) {
+            float v0[HW], v1[HW];
 #pragma unroll
-            for (int e = 0; e < HW; ++e) v[e] = d1[e] * xp[o];
-            c_w0[o] += colsumN<HW>(v, lane);
+            for (int e = 0; e < HW; ++e) { v0[e] = d1[e] * xp[o]; v1[e] = d1[e] * xp[o + 1]; }
+            float r0, r1;
+            colsumN2<HW>(v0, v1, lane, r0, r1);
+            c_w0[o] += r0;
+            c_w0[o + 1] += r1;
         }
-        c_b0 += colsumN<HW>(d1, lane);
+        if (O % 2 == 1) {
+            float v0[HW];
+#pragma unroll
+            for (int e = 0; e < HW; ++e) v0[e] = d1[e] * xp[O - 1];
+            float r0, r1;
+            colsumN2<HW>(v0, d1, lane, r0, r1);
+            c_w0[O - 1] += r0;
+            c_b0 += r1;
+        } else {
+            c_b0 += colsumN<HW>(d1, lane);
+        }
         // the previous tile's weight-gradient GEMM has consumed bufB / bufC
         mbar_wait(&bar_w, ph_w);
         ph_w ^= 1u;
@@ -456,9 +497,17 @@ __global__ void __launch_bounds__(NPART * 128 + 32, 1) update_tc_kernel(const __
         named_arrive(BAR_BWD, NT);          // -> issuer warp: dZ2 (TMEM + bufC) and H1 (bufB) are in place
         // in the shadow of the GEMMs: next tile's inputs, column sums for dWo and db1
         prefetch(tile + gridDim.x);
-        c_b1 += colsumN<HW>(dz, lane);
+        {
+            float v0[HW];
 #pragma unroll
-        for (int j = 0; j < A; ++j) {
+            for (int e = 0; e < HW; ++e) v0[e] = dmu[0] * h[e];
+            float r0, r1;
+            colsumN2<HW>(v0, dz, lane, r0, r1);
+            c_wo[0] += r0;
+            c_b1 += r1;
+        }
+#pragma unroll
+        for (int j = 1; j < A; ++j) {
             float v[HW];
 #pragma unroll
             for (int e = 0; e < HW; ++e) v[e] = dmu[j] * h[e];
