@@ -774,7 +774,8 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
 //   stage = one 8-sample sub-block: Z2h, Z2l (this half: 4 column blocks), H1h, H1l (all), Z1h, Z1l (this half), Xh, Xl
 // ============================================================================
 template <int O, int W>
-__global__ void __launch_bounds__(192, 1) update_tcw_wgrad_kernel(const __grid_constant__ TcwArgs a) {
+__global__ void __launch_bounds__(320, 1) update_tcw_wgrad_kernel(const __grid_constant__ TcwArgs a) {
+    constexpr int NCV = 8;                         // converter warps (0..7); warp 8 = TMA producer, warp 9 = MMA issuer
     constexpr int OKP = (O + 1 + 7) / 8 * 8;
     constexpr uint32_t ZB = 4 * 1024, HB = W / 32 * 1024, XB = OKP * 32;        // bytes per stage piece
     constexpr uint32_t STAGE = 4 * ZB + 2 * HB + 2 * XB;
@@ -789,7 +790,7 @@ __global__ void __launch_bounds__(192, 1) update_tcw_wgrad_kernel(const __grid_c
     if (threadIdx.x == 0) {
         for (int i = 0; i < NST; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&conv_bar[i], 128);
+            mbar_init(&conv_bar[i], NCV * 32);
             mbar_init(&empty_bar[i], 1);
         }
         mbar_init(&done_bar, 1);
@@ -804,7 +805,7 @@ __global__ void __launch_bounds__(192, 1) update_tcw_wgrad_kernel(const __grid_c
     const int64_t k_end = a.k_begin + a.k_count;
     const int half = a.half;
     bool any = false;
-    if (warp == 4) {
+    if (warp == NCV) {
         if (lane == 0) {
             uint32_t gi = 0;
             int t = 0, blk = 0;
@@ -831,7 +832,7 @@ __global__ void __launch_bounds__(192, 1) update_tcw_wgrad_kernel(const __grid_c
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == NCV + 1) {
         const uint32_t idesc_w = umma_idesc_tf32(128, W, true, true);
         const uint32_t idesc_x = umma_idesc_tf32(128, OKP, true, false);
         uint32_t gi = 0, first = 1u;
@@ -870,7 +871,7 @@ __global__ void __launch_bounds__(192, 1) update_tcw_wgrad_kernel(const __grid_c
         if (lane == 0 && any) umma_commit(&done_bar);
         __syncwarp();
     }
-    if (warp < 4) {
+    if (warp < NCV) {
         // ===== converter warps: tf32 hi/lo split of the fp32 rows of every stage, in shared memory =====
         uint32_t gi = 0;
         int t = 0, blk = 0;
@@ -884,7 +885,7 @@ __global__ void __launch_bounds__(192, 1) update_tcw_wgrad_kernel(const __grid_c
                 mbar_wait(&full_bar[st], ph);
                 unsigned char *base = smem_raw + (size_t)st * STAGE_AL;
 #pragma unroll 2
-                for (int f = threadIdx.x; f < NF4; f += 128) {
+                for (int f = threadIdx.x; f < NF4; f += NCV * 32) {
                     const uint32_t b = (uint32_t)f * 16u;
                     // slot of this item: dZ2 at 0 (lo at ZB), dZ1 at 2 ZB (lo at 3 ZB), H1 at 4 ZB (lo at 4 ZB + HB)
                     unsigned char *hp, *lp;
@@ -959,7 +960,7 @@ static int launch_tcw(const TcwArgs &a0, int grid, int64_t total_upper, int64_t 
         kA<<<grid, NP * 128 + 64, smemA, st>>>(a);
         for (int half = 0; half < (a.forward_only ? 0 : W / 128); ++half) {
             a.half = half;
-            kB<<<grid, 192, smemB, st>>>(a);
+            kB<<<grid, 320, smemB, st>>>(a);
         }
     }
     TG_CUDA(cudaGetLastError());
