@@ -380,19 +380,19 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
             first_tile = false;
             tcw_sync(TCW_BAR_L1, CNT_ALL);
             tc_fence_after();
-            if (lane == 0) {
+            {
                 uint32_t acc = 0;
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
                     const uint32_t aa = pass == 2 ? olo : ohi, bb = pass == 1 ? w0lo : w0hi;
 #pragma unroll
                     for (int kk = 0; kk < OKP; kk += 8) {
-                        umma_tf32(tmem + TM_D, umma_operand_desc(aa, OKP, false, kk), umma_operand_desc(bb, OKP, false, kk),
+                        umma_tf32_w(tmem + TM_D, umma_operand_desc(aa, OKP, false, kk), umma_operand_desc(bb, OKP, false, kk),
                                   idesc_f, acc);
                         acc = 1u;
                     }
                 }
-                umma_commit(&bar_d);
+                umma_commit_w(&bar_d);
             }
             __syncwarp();
             for (int dir = 0; dir < (a.forward_only ? 1 : 2); ++dir) {   // 0: forward (K-major B), 1: backward-data (MN-major B)
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
                     if (half == 0) tcw_sync(TCW_BAR_K0, CNT_ALL);
                     else tcw_sync(TCW_BAR_K1, CNT_H1);
                     tc_fence_after();
-                    if (lane == 0) {
+                    {
                         for (int c = 0; c < 4; ++c) {
                             const uint32_t st_hi = gi % TCW_STAGES, ph_hi = (gi / TCW_STAGES) & 1u;
                             ++gi;
@@ -413,28 +413,28 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
                             tc_fence_after();
 #pragma unroll
                             for (int ks = 0; ks < 32; ks += 8)
-                                umma_tf32_ts(tmem + TM_D, tmem + TM_AHI + acol + (uint32_t)ks,
+                                umma_tf32_ts_w(tmem + TM_D, tmem + TM_AHI + acol + (uint32_t)ks,
                                              dir ? umma_desc_mn32(bhi + (uint32_t)ks * 128u, 4096u)
                                                  : umma_operand_desc(bhi, 32, false, ks),
                                              idesc, (half | c | ks) ? 1u : 0u);
 #pragma unroll
                             for (int ks = 0; ks < 32; ks += 8)
-                                umma_tf32_ts(tmem + TM_D, tmem + TM_ALO + acol + (uint32_t)ks,
+                                umma_tf32_ts_w(tmem + TM_D, tmem + TM_ALO + acol + (uint32_t)ks,
                                              dir ? umma_desc_mn32(bhi + (uint32_t)ks * 128u, 4096u)
                                                  : umma_operand_desc(bhi, 32, false, ks),
                                              idesc, 1u);
-                            umma_commit(&empty_bar[st_hi]);
+                            umma_commit_w(&empty_bar[st_hi]);
                             mbar_wait(&full_bar[st_lo], ph_lo);
                             tc_fence_after();
 #pragma unroll
                             for (int ks = 0; ks < 32; ks += 8)
-                                umma_tf32_ts(tmem + TM_D, tmem + TM_AHI + acol + (uint32_t)ks,
+                                umma_tf32_ts_w(tmem + TM_D, tmem + TM_AHI + acol + (uint32_t)ks,
                                              dir ? umma_desc_mn32(blo + (uint32_t)ks * 128u, 4096u)
                                                  : umma_operand_desc(blo, 32, false, ks),
                                              idesc, 1u);
-                            umma_commit(&empty_bar[st_lo]);
+                            umma_commit_w(&empty_bar[st_lo]);
                         }
-                        umma_commit((half == KH - 1) ? &bar_d : &bar_k0);
+                        umma_commit_w((half == KH - 1) ? &bar_d : &bar_k0);
                     }
                     __syncwarp();
                 }
