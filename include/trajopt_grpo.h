@@ -8,9 +8,9 @@
  * INTEGRATION.md for the stub a reference maintainer would add).
  *
  * Conventions
- *   - every function returns an int status: 0 ok, <0 argument/shape error
- *     (TG_ERR_*), >0 a cudaError_t; tg_last_error() returns the message of the
- *     last failure on the calling thread;
+ *   - every function returns an int status: 0 ok, <0 a TG_ERR_* code (a failing CUDA runtime call
+ *     is TG_ERR_CUDA; its cudaError_t name and string are in the message); tg_last_error()
+ *     returns the message of the last failure on the calling thread;
  *   - the CALLER allocates every buffer (device pointers unless stated), the
  *     library never frees caller memory; calls are asynchronous on `stream`
  *     (a cudaStream_t passed as void*);
@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TG_ABI_VERSION 1
+#define TG_ABI_VERSION 2
 
 /* status codes */
 #define TG_OK 0
@@ -40,6 +40,7 @@ extern "C" {
 #define TG_ERR_SHAPE (-2)       /* dimension out of the supported range */
 #define TG_ERR_UNSUPPORTED (-3) /* configuration the kernels do not cover */
 #define TG_ERR_NO_DEVICE (-4)   /* no CUDA device / not sm_100 */
+#define TG_ERR_CUDA (-5)        /* a CUDA runtime call failed; tg_last_error() carries cudaGetErrorString */
 
 /* environments (environments/*.py) */
 #define TG_ENV_CARTPOLE 0   /* cartpole_env.py:6-182   obs 5  act 1 */
@@ -51,6 +52,7 @@ extern "C" {
 #define TG_ACT_RELU 0
 #define TG_ACT_TANH 1
 #define TG_ACT_SIGMOID 2
+#define TG_ACT_PER_LAYER (-1) /* tg_mlp_cfg.activation: read layer_activation[l] per hidden layer instead */
 
 /* arithmetic of the env state */
 #define TG_PREC_F32 0 /* throughput mode: state, dynamics and reward in fp32 */
@@ -84,11 +86,15 @@ typedef struct tg_env_cfg {
 } tg_env_cfg;
 
 /* models/neural_network.py:36-65 -- n_layers Linear layers, dims[0]=input_dim,
- * dims[n_layers]=output_dim, one activation for every hidden layer. */
+ * dims[n_layers]=output_dim; `activation` is the torch.nn class applied after every hidden Linear
+ * (a string in the reference), or TG_ACT_PER_LAYER with layer_activation[l] = the activation after
+ * hidden Linear l (the reference's list form, neural_network.py:41-45).  Per-layer lists run on the
+ * FP32-pipe kernels; the tensor-core kernels take one activation for all layers. */
 typedef struct tg_mlp_cfg {
     int32_t n_layers;
     int32_t dims[TG_MAX_LAYERS + 1];
-    int32_t activation; /* TG_ACT_* */
+    int32_t activation; /* TG_ACT_* or TG_ACT_PER_LAYER */
+    int32_t layer_activation[TG_MAX_LAYERS]; /* read only when activation == TG_ACT_PER_LAYER */
 } tg_mlp_cfg;
 
 int tg_abi_version(void);

@@ -133,13 +133,21 @@ class Injector:
         return torch.from_numpy(self.noise[t, w * self.E + e].copy()).to(dtype).reshape(shape)
 
 
-def make_policy(kind, hidden, cov, seed, critic=False):
+def make_policy(kind, hidden, cov, seed, critic=False, activation="ReLU", weights=None):
+    """`weights`: path (relative to the reference root) of a shipped policy.pt to load (reports/**)."""
     from policies.actor_critic import GaussianActor_NeuralNetwork, GaussianActorCritic_NeuralNetwork
     O = {0: 5, 1: 3, 2: 10, 3: 20}[kind]
     A = {0: 1, 1: 1, 2: 2, 3: 4}[kind]
     torch.manual_seed(seed)
     cls = GaussianActorCritic_NeuralNetwork if critic else GaussianActor_NeuralNetwork
-    return cls(O, A, hidden, "ReLU", cov)
+    pol = cls(O, A, hidden, activation, cov)
+    if weights is not None:
+        sd = torch.load(os.path.join(ref_shims.REFERENCE_ROOT, weights), weights_only=True)
+        if critic:
+            pol.actor.load_state_dict(sd["actor"]); pol.critic.load_state_dict(sd["critic"])
+        else:
+            pol.actor.load_state_dict(sd)
+    return pol
 
 
 def policy_arrays(policy):
@@ -186,20 +194,23 @@ class Buf:
     pass
 
 
-def gen_rollout_and_learn(kind, hidden, cov, G, E, T, restart, seed, gamma, eps_clip, noise_scale=1.0):
+def gen_rollout_and_learn(kind, hidden, cov, G, E, T, restart, seed, gamma, eps_clip, noise_scale=1.0,
+                          activation="ReLU", weights=None):
     rng = np.random.default_rng(seed)
     sys.path.insert(0, HERE)
     import restate
-    policy = make_policy(kind, hidden, cov, seed)
+    policy = make_policy(kind, hidden, cov, seed, activation=activation, weights=weights)
     A = {0: 1, 1: 1, 2: 2, 3: 4}[kind]
     n_init = G if restart else G * E
     init_small = restate.reset_states(kind, n_init, rng)
     init = np.repeat(init_small, E, axis=0) if restart else init_small
     noise = (noise_scale * rng.standard_normal((T, G * E, A))).astype(np.float32)
     obs, act, rew, ln, mask = run_rollout(kind, policy, init, noise, G, E, T, restart)
-    out = dict(kind=kind, hidden=np.array(hidden), cov=np.float32(cov), G=G, E=E, T=T,
+    out = dict(kind=kind, hidden=np.array(hidden, dtype=np.int64), cov=np.float32(cov), G=G, E=E, T=T,
                restart=restart, gamma=gamma, eps_clip=eps_clip, init=init, noise=noise,
                obs=obs, act=act, rew=rew, len=ln, mask=mask, **policy_arrays(policy))
+    if activation != "ReLU":
+        out["activation"] = np.array(activation if isinstance(activation, str) else ",".join(activation))
 
     # --- log_prob KAT on the rollout's own samples
     with torch.no_grad():
@@ -234,13 +245,13 @@ def gen_rollout_and_learn(kind, hidden, cov, G, E, T, restart, seed, gamma, eps_
     return out
 
 
-def gen_ppo(kind, hidden, cov, G, E, T, seed, gamma, lam, eps_clip, monte_carlo):
+def gen_ppo(kind, hidden, cov, G, E, T, seed, gamma, lam, eps_clip, monte_carlo, weights=None):
     """PPO.learn full-batch (batch_size=None), SGD(lr=1) one update and Adam 3 updates."""
     import copy
     from algorithms.ppo import PPO
     rng = np.random.default_rng(seed)
     import restate
-    policy = make_policy(kind, hidden, cov, seed, critic=True)
+    policy = make_policy(kind, hidden, cov, seed, critic=True, weights=weights)
     A = {0: 1, 1: 1, 2: 2, 3: 4}[kind]
     init = restate.reset_states(kind, G * E, rng)
     noise = rng.standard_normal((T, G * E, A)).astype(np.float32)
@@ -293,57 +304,120 @@ def gen_ppo_minibatch(kind, hidden, cov, G, E, T, seed, gamma, lam, eps_clip, ba
     return out
 
 
+def _same(a, b):
+    return a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b, equal_nan=a.dtype.kind == "f")
+
+
+def emit(name, arrays, check, report):
+    """Write tests/golden/<name>.npz, or (--check) compare with the committed file bit for bit."""
+    path = os.path.join(OUT, name + ".npz")
+    if check:
+        old = dict(np.load(path, allow_pickle=False))
+        new = {k: np.asarray(v) for k, v in arrays.items()}
+        bad = sorted(set(old) ^ set(new)) + [k for k in old if k in new and not _same(old[k], new[k])]
+        report[name] = bad
+        print(f"{name}: {'bit-identical' if not bad else 'DIFFERS in ' + str(bad)}")
+    else:
+        np.savez_compressed(path, **arrays)
+
+
+# name -> (generator, kwargs).  Every generator seeds its own numpy Generator / torch seed, and main()
+# seeds numpy's GLOBAL RNG per fixture (the reference's env.reset() draws from it), so each file
+# regenerates bit-identically on its own (`--only name`, `--check`).
+CP_GRPO = "reports/CartPole/cartpole_nn_grpo/001/policy.pt"
+CP_PPO = "reports/CartPole/cartpole_nn_ppo/001/policy.pt"
+QP2_PPO = "reports/QuadPole2D/quadpole2d_nn_ppo/001/policy.pt"
+
+
+def fixtures():
+    F = {}
+
+    def transitions(kind):
+        def gen():
+            rng = np.random.default_rng(20261018 + kind)
+            if kind == 1:
+                a = gen_transitions(1, rng, episodes=2, scale=0.8, max_steps=200)
+                b = gen_transitions(1, rng, episodes=1, scale=0.0, max_steps=200, pd=True)   # 101 balanced steps
+                return {k: np.concatenate([a[k], b[k]]) for k in a}
+            return gen_transitions(kind, rng, episodes=6, scale=1.0, max_steps={0: 120, 2: 150, 3: 150}[kind])
+        return gen
+    for k in range(4):
+        F[f"transitions_env{k}"] = transitions(k)
+    F["quadrotor12_dynamics"] = lambda: gen_quadrotor12(np.random.default_rng(20261019))
+
+    roll = {
+        # round 1: small policies, one per env
+        "cartpole": dict(kind=0, hidden=[32, 32], cov=0.5, G=3, E=4, T=40, restart=False, seed=1, gamma=0.5, eps_clip=0.15),
+        "pendulum": dict(kind=1, hidden=[64, 64], cov=0.5, G=4, E=4, T=30, restart=True, seed=2, gamma=0.99, eps_clip=0.2),
+        "quadpole2d": dict(kind=2, hidden=[32, 32], cov=0.5, G=3, E=3, T=60, restart=True, seed=3, gamma=0.99, eps_clip=0.2),
+        "quadpole": dict(kind=3, hidden=[64, 64], cov=0.3, G=3, E=4, T=80, restart=True, seed=4, gamma=0.999, eps_clip=0.2),
+        # round 2: the BASELINE.json shapes.  cfg 1 at FULL size with the shipped trained weights
+        # (pipelines/cartpole_pipeline_grpo.py:54-76: 10 workers x 10 episodes x 500 steps, 5-128^4-1, cov 0.5,
+        # eps 0.15, gamma 0.5, restart=False)
+        "cartpole_cfg1": dict(kind=0, hidden=[128, 128, 128, 128], cov=0.5, G=10, E=10, T=500, restart=False, seed=21,
+                              gamma=0.5, eps_clip=0.15, weights=CP_GRPO),
+        # cfg 3 / cfg 4 policy shapes (tensor-core kernels) at small N
+        "quadpole2d_w128": dict(kind=2, hidden=[128, 128], cov=0.5, G=3, E=4, T=60, restart=True, seed=22, gamma=0.99,
+                                eps_clip=0.2),
+        "quadpole_w256": dict(kind=3, hidden=[256, 256], cov=0.3, G=3, E=4, T=80, restart=True, seed=23, gamma=0.999,
+                              eps_clip=0.2),
+        # depth 1 / 3 / 0, odd widths, other activations
+        "pendulum_h1": dict(kind=1, hidden=[48], cov=0.5, G=3, E=4, T=30, restart=True, seed=24, gamma=0.99, eps_clip=0.2),
+        "cartpole_h3": dict(kind=0, hidden=[32, 48, 24], cov=0.5, G=3, E=4, T=40, restart=False, seed=25, gamma=0.5,
+                            eps_clip=0.15),
+        "pendulum_h0": dict(kind=1, hidden=[], cov=0.5, G=3, E=4, T=30, restart=True, seed=26, gamma=0.99, eps_clip=0.2),
+        "cartpole_tanh": dict(kind=0, hidden=[32, 32], cov=0.5, G=3, E=4, T=40, restart=False, seed=27, gamma=0.5,
+                              eps_clip=0.15, activation="Tanh"),
+        "pendulum_mixed_act": dict(kind=1, hidden=[32, 24], cov=0.5, G=3, E=4, T=30, restart=True, seed=28, gamma=0.99,
+                                   eps_clip=0.2, activation=["Tanh", "ReLU"]),
+    }
+    for name, kw in roll.items():
+        F[f"rollout_grpo_{name}"] = (lambda kw=kw: gen_rollout_and_learn(**kw))
+
+    ppo = dict(kind=2, hidden=[32, 32], cov=0.5, G=2, E=3, T=40, seed=7, gamma=0.99, lam=0.95, eps_clip=0.2)
+    F["ppo_mc_quadpole2d"] = lambda: gen_ppo(monte_carlo=True, **ppo)
+    F["ppo_gae_quadpole2d"] = lambda: gen_ppo(monte_carlo=False, **ppo)
+    # ragged full batch (T = 120: episodes end by leaving the box at different steps)
+    rag = dict(kind=2, hidden=[32, 32], cov=0.5, G=3, E=4, T=120, seed=12, gamma=0.99, lam=0.95, eps_clip=0.2)
+    F["ppo_mc_ragged_quadpole2d"] = lambda: gen_ppo(monte_carlo=True, **rag)
+    F["ppo_gae_ragged_quadpole2d"] = lambda: gen_ppo(monte_carlo=False, **rag)
+    # the shipped QuadPole2D PPO checkpoint: actor + critic 10-128-128-128-{2,1} (three hidden layers), trained
+    # weights => long episodes (pipelines/quadpole2d_pipeline_ppo.py:54-80; GAE off = Monte-Carlo is its default)
+    F["ppo_mc_quadpole2d_shipped"] = lambda: gen_ppo(kind=2, hidden=[128, 128, 128], cov=0.5, G=2, E=3, T=150, seed=13,
+                                                     gamma=0.99, lam=0.95, eps_clip=0.2, monte_carlo=True, weights=QP2_PPO)
+    F["ppo_gae_cartpole_shipped"] = lambda: gen_ppo(kind=0, hidden=[128, 128, 128], cov=0.5, G=2, E=3, T=120, seed=14,
+                                                    gamma=0.99, lam=0.95, eps_clip=0.2, monte_carlo=False, weights=CP_PPO)
+    F["ppo_minibatch_quadpole2d"] = lambda: gen_ppo_minibatch(kind=2, hidden=[32, 32], cov=0.5, G=3, E=4, T=120, seed=11,
+                                                              gamma=0.99, lam=0.95, eps_clip=0.2, batch_size=64, updates=2,
+                                                              torch_seed=4321)
+    return F
+
+
 def main():
-    if "--only-ppo-minibatch" in sys.argv:
-        if not ref_shims.available():
-            raise SystemExit("reference not mounted; fixtures can only be regenerated in the build container")
-        ref_shims.install()
-        out = gen_ppo_minibatch(kind=2, hidden=[32, 32], cov=0.5, G=3, E=4, T=120, seed=11, gamma=0.99, lam=0.95,
-                                eps_clip=0.2, batch_size=64, updates=2, torch_seed=4321)
-        np.savez_compressed(os.path.join(OUT, "ppo_minibatch_quadpole2d.npz"), **out)
-        print(f"ppo_minibatch: lens={out['len'].reshape(-1).tolist()}")
-        return
+    """python oracle/make_golden.py [--only a,b] [--check]"""
     if not ref_shims.available():
         raise SystemExit("reference not mounted; fixtures can only be regenerated in the build container")
     ref_shims.install()
     os.makedirs(OUT, exist_ok=True)
-    rng = np.random.default_rng(20261018)
-
-    # 1. env transitions
-    tr = {}
-    tr[0] = gen_transitions(0, rng, episodes=6, scale=1.0, max_steps=120)
-    pend_a = gen_transitions(1, rng, episodes=2, scale=0.8, max_steps=200)
-    pend_b = gen_transitions(1, rng, episodes=1, scale=0.0, max_steps=200, pd=True)   # reaches 101 balanced steps
-    tr[1] = {k: np.concatenate([pend_a[k], pend_b[k]]) for k in pend_a}
-    tr[2] = gen_transitions(2, rng, episodes=6, scale=1.0, max_steps=150)
-    tr[3] = gen_transitions(3, rng, episodes=6, scale=1.0, max_steps=150)
-    for k, v in tr.items():
-        np.savez_compressed(os.path.join(OUT, f"transitions_env{k}.npz"), **v)
-        print(f"transitions env{k}: {len(v['reward'])} rows, done={int(v['done'].sum())}")
-    np.savez_compressed(os.path.join(OUT, "quadrotor12_dynamics.npz"), **gen_quadrotor12(rng))
-
-    # 2. rollouts + GRPO learn (small shapes; T is the env's max_steps)
-    cases = [
-        ("cartpole", dict(kind=0, hidden=[32, 32], cov=0.5, G=3, E=4, T=40, restart=False, seed=1, gamma=0.5, eps_clip=0.15)),
-        ("pendulum", dict(kind=1, hidden=[64, 64], cov=0.5, G=4, E=4, T=30, restart=True, seed=2, gamma=0.99, eps_clip=0.2)),
-        ("quadpole2d", dict(kind=2, hidden=[32, 32], cov=0.5, G=3, E=3, T=60, restart=True, seed=3, gamma=0.99, eps_clip=0.2)),
-        ("quadpole", dict(kind=3, hidden=[64, 64], cov=0.3, G=3, E=4, T=80, restart=True, seed=4, gamma=0.999, eps_clip=0.2)),
-    ]
-    for name, kw in cases:
-        out = gen_rollout_and_learn(**kw)
-        np.savez_compressed(os.path.join(OUT, f"rollout_grpo_{name}.npz"), **out)
-        print(f"rollout_grpo_{name}: lens={out['len'].reshape(-1).tolist()}")
-
-    # 3. PPO learn
-    for name, mc in (("mc", True), ("gae", False)):
-        out = gen_ppo(kind=2, hidden=[32, 32], cov=0.5, G=2, E=3, T=40, seed=7, gamma=0.99, lam=0.95,
-                      eps_clip=0.2, monte_carlo=mc)
-        np.savez_compressed(os.path.join(OUT, f"ppo_{name}_quadpole2d.npz"), **out)
-        print(f"ppo_{name}: lens={out['len'].reshape(-1).tolist()}")
-    out = gen_ppo_minibatch(kind=2, hidden=[32, 32], cov=0.5, G=3, E=4, T=120, seed=11, gamma=0.99, lam=0.95,
-                            eps_clip=0.2, batch_size=64, updates=2, torch_seed=4321)
-    np.savez_compressed(os.path.join(OUT, "ppo_minibatch_quadpole2d.npz"), **out)
-    print(f"ppo_minibatch: lens={out['len'].reshape(-1).tolist()}")
+    check = "--check" in sys.argv
+    only = None
+    if "--only" in sys.argv:
+        only = set(sys.argv[sys.argv.index("--only") + 1].split(","))
+    report = {}
+    for i, (name, gen) in enumerate(fixtures().items()):
+        if only is not None and name not in only:
+            continue
+        np.random.seed(777000 + i)       # numpy's global RNG: Env.reset() (e.g. cartpole_env.py:103) draws from it
+        torch.manual_seed(888000 + i)
+        arrays = gen()
+        emit(name, arrays, check, report)
+        if "len" in arrays:
+            ln = np.asarray(arrays["len"]).reshape(-1)
+            print(f"  {name}: lens min/mean/max = {ln.min():.0f}/{ln.mean():.1f}/{ln.max():.0f}")
+        elif "done" in arrays:
+            print(f"  {name}: {len(arrays['reward'])} rows, done={int(arrays['done'].sum())}")
+    if check and any(report.values()):
+        raise SystemExit("fixtures do not regenerate bit-identically: " + str({k: v for k, v in report.items() if v}))
 
 
 if __name__ == "__main__":

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/trajopt_grpo.h but not exported"
     assert sorted(L.EXPORTS) == syms            # the ctypes table binds exactly the header
-    assert lib.tg_abi_version() == 1
+    assert lib.tg_abi_version() == 2
 
 
 def test_host_side_queries_need_no_device():

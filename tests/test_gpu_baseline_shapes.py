@@ -1,0 +1,292 @@
+"""Round-2 parity fixtures: the BASELINE.json policy shapes and the depths / activations round 1 left
+unpinned, all produced by the UNMODIFIED reference (oracle/make_golden.py):
+
+  cartpole_cfg1        cfg 1 at full size: 10 x 10 x 500, 5-128^4-1, shipped weights (FP32-pipe deep-net kernels)
+  quadpole2d_w128      cfg 3 policy shape 10-128-128-2   (tensor-core kernels: rollout_tc2, update_tcw)
+  quadpole_w256        cfg 4 policy shape 20-256-256-4   (tensor-core kernels: rollout_tc256, update_tcw)
+  pendulum_h1 / cartpole_h3 / pendulum_h0       1 / 3 / 0 hidden layers, odd widths
+  cartpole_tanh / pendulum_mixed_act            Tanh; per-layer activation list ["Tanh", "ReLU"]
+  ppo_*_ragged_quadpole2d                       ragged full-batch PPO (MC and GAE)
+  ppo_mc_quadpole2d_shipped / ppo_gae_cartpole_shipped   shipped 3-hidden-layer 128-wide actor + critic
+
+Every kernel-level check runs in both arithmetic modes the shape supports (FP32 pipe, 3xTF32 tensor cores).
+Gradient tolerances: 3e-4 of max|g| against the reference's fp32 autograd (its own rounding is ~1e-4), and the
+tighter per-width bound GRAD_TOL_F64 against the float64 oracle evaluated on the same reference trajectories.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import restate as R
+
+pytestmark = pytest.mark.gpu
+
+NEW_ROLLOUTS = ["cartpole_cfg1", "quadpole2d_w128", "quadpole_w256", "pendulum_h1", "cartpole_h3", "pendulum_h0",
+                "cartpole_tanh", "pendulum_mixed_act"]
+# max |g_kernel - g_float64| / max |g_float64| per widest hidden layer (measured on B200: see profiles/README_r2.md)
+GRAD_TOL_F64 = {0: 2e-5, 24: 2e-5, 32: 2e-5, 48: 2e-5, 64: 3e-5, 128: 5e-5, 256: 1e-4}
+
+
+def load(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name), allow_pickle=False))
+
+
+def dev(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+@pytest.fixture(scope="module")
+def E():
+    from trajopt_grpo_b200 import engine
+    return engine
+
+
+def _weights(g, prefix=""):
+    Ws, bs, i = [], [], 0
+    while f"{prefix}W{i}" in g:
+        Ws.append(g[f"{prefix}W{i}"]); bs.append(g[f"{prefix}b{i}"]); i += 1
+    return Ws, bs
+
+
+def _flat(Ws, bs):
+    return np.concatenate([np.concatenate([w.reshape(-1), b.reshape(-1)]) for w, b in zip(Ws, bs)]).astype(np.float32)
+
+
+def _dims(Ws):
+    return [Ws[0].shape[1]] + [w.shape[0] for w in Ws]
+
+
+def _act_names(g):
+    """the engine-side activation argument: a torch.nn class name or the per-layer list."""
+    if "activation" not in g:
+        return "ReLU"
+    names = str(g["activation"]).split(",")
+    return names[0] if len(names) == 1 else names
+
+
+def _modes(dims):
+    hid = dims[1:-1]
+    tc = len(hid) == 2 and hid[0] == hid[1] and hid[0] in (64, 128, 256)
+    return ("fp32", "3xtf32") if tc else ("fp32",)
+
+
+def _soa(g):
+    G, Eps, T = int(g["G"]), int(g["E"]), int(g["T"])
+    N = G * Eps
+    obs = dev(g["obs"].reshape(N, T, -1).transpose(1, 2, 0))
+    act = dev(g["act"].reshape(N, T, -1).transpose(1, 2, 0))
+    rew = dev(g["rew"].reshape(N, T).T)
+    ln = dev(g["len"].reshape(-1).astype(np.int32))
+    return G, Eps, T, N, obs, act, rew, ln
+
+
+def _to_ref_shape(x, G, Eps):
+    x = x.cpu().numpy()
+    if x.ndim == 3:
+        return x.transpose(2, 0, 1).reshape(G, Eps, x.shape[0], x.shape[1])
+    return x.T.reshape(G, Eps, x.shape[0])
+
+
+@pytest.mark.parametrize("name", NEW_ROLLOUTS)
+def test_rollout_float64_matches_reference(E, golden_dir, name):
+    g = load(golden_dir, f"rollout_grpo_{name}.npz")
+    kind, G, Eps, T = int(g["kind"]), int(g["G"]), int(g["E"]), int(g["T"])
+    Ws, bs = _weights(g)
+    dims = _dims(Ws)
+    cov = [float(g["cov"])] * R.ACT_DIM[kind]
+    nz = dev(g["noise"].transpose(0, 2, 1))
+    for mode in _modes(dims):
+        try:
+            E.set_math(mode)
+            out = E.rollout(kind, T, R.DEFAULT_DT[kind], dims, _act_names(g), dev(_flat(Ws, bs)), cov,
+                            dev(g["init"].T.copy(), torch.float64), noise=nz)
+            torch.cuda.synchronize()
+        finally:
+            E.set_math("auto")
+        ln = out["len"].cpu().numpy().reshape(G, Eps)
+        assert np.array_equal(ln, g["len"].astype(np.int32)), mode          # lengths bit-exact
+        mask = (np.arange(T)[None, None, :] < ln[:, :, None]).astype(np.float32)
+        assert np.array_equal(mask, g["mask"]), mode
+        np.testing.assert_allclose(_to_ref_shape(out["obs"], G, Eps), g["obs"], rtol=2e-4, atol=2e-4, err_msg=mode)
+        np.testing.assert_allclose(_to_ref_shape(out["act"], G, Eps), g["act"], rtol=2e-4, atol=2e-4, err_msg=mode)
+        np.testing.assert_allclose(_to_ref_shape(out["rew"], G, Eps), g["rew"], rtol=2e-4, atol=5e-4, err_msg=mode)
+        sel = g["mask"] > 0
+        np.testing.assert_allclose(_to_ref_shape(out["logp"], G, Eps)[sel], g["logp_valid"], rtol=1e-4, atol=1e-4,
+                                   err_msg=mode)
+        pad = ~sel
+        assert np.all(_to_ref_shape(out["obs"], G, Eps)[pad] == 0) and np.all(_to_ref_shape(out["rew"], G, Eps)[pad] == 0)
+
+
+@pytest.mark.parametrize("name", NEW_ROLLOUTS)
+def test_grpo_gradient_matches_reference_and_float64_oracle(E, golden_dir, name, record_property):
+    g = load(golden_dir, f"rollout_grpo_{name}.npz")
+    kind = int(g["kind"])
+    G, Eps, T, N, obs, act, rew, ln = _soa(g)
+    Ws, bs = _weights(g)
+    dims = _dims(Ws)
+    act_names = _act_names(g)
+    cov = [float(g["cov"])] * dims[-1]
+    params = dev(_flat(Ws, bs))
+    # float64 oracle on the reference's own trajectories and its advantages
+    _, adv_ref = R.grpo_advantage(g["rew"], g["mask"], float(g["gamma"]))
+    _, dW, db, _, _ = R.grpo_objective_and_grad(g["obs"], g["act"], adv_ref, g["mask"], Ws, bs, Ws, bs,
+                                                 np.asarray(cov, np.float32), float(g["eps_clip"]),
+                                                 act=R.acts_from_names(g["activation"]) if "activation" in g else 0,
+                                                 dtype="float64")
+    ref64 = np.concatenate([np.concatenate([w.reshape(-1), b]) for w, b in zip(dW, db)])
+    ref32 = np.concatenate([g[f"grpo_grad{i}"].reshape(-1) for i in range(2 * len(Ws))])
+    width = max(dims[1:-1], default=0)
+    for mode in _modes(dims):
+        try:
+            E.set_math(mode)
+            adv, _ = E.advantage(0, G, Eps, T, float(g["gamma"]), 0.0, rew, ln)
+            _, old_lp = E.policy_forward_traj(dims, act_names, params, obs, cov, act, ln)
+            grad, stats = E.policy_grad(dims, act_names, params, cov, obs, act, adv, old_lp, ln, float(g["eps_clip"]),
+                                        1.0 / G)
+            torch.cuda.synchronize()
+        finally:
+            E.set_math("auto")
+        got = grad.cpu().numpy()
+        assert int(stats[1].item()) == int(g["mask"].sum()), mode
+        # vs the unmodified reference (fp32 torch autograd through SGD(lr=1)), layer by layer
+        off = 0
+        for i in range(2 * len(Ws)):
+            r = g[f"grpo_grad{i}"]
+            part = got[off:off + r.size].reshape(r.shape)
+            off += r.size
+            assert np.abs(part - r).max() <= 3e-4 * max(np.abs(r).max(), 1e-6) + 1e-5, (mode, i)
+        e64 = float(np.abs(got - ref64).max() / np.abs(ref64).max())
+        e32 = float(np.abs(got - ref32).max() / np.abs(ref32).max())
+        record_property(f"grad_err_vs_f64_{mode}", e64)
+        print(f"[grad-parity] {name:22s} width {width:3d} {mode:7s} vs float64 oracle {e64:.2e}  vs reference fp32 {e32:.2e}")
+        assert e64 <= GRAD_TOL_F64[width], (mode, e64)
+
+
+@pytest.mark.parametrize("name", NEW_ROLLOUTS)
+def test_grpo_adam_updates_match_reference(E, golden_dir, name):
+    """updates_per_iter = 3, twice (old policy synced in between), Adam lr 3e-4, vs the unmodified GRPO.learn."""
+    g = load(golden_dir, f"rollout_grpo_{name}.npz")
+    G, Eps, T, N, obs, act, rew, ln = _soa(g)
+    Ws, bs = _weights(g)
+    dims = _dims(Ws)
+    act_names = _act_names(g)
+    cov = [float(g["cov"])] * dims[-1]
+    for mode in _modes(dims):
+        params = dev(_flat(Ws, bs))
+        m, v = torch.zeros_like(params), torch.zeros_like(params)
+        try:
+            E.set_math(mode)
+            adv, _ = E.advantage(0, G, Eps, T, float(g["gamma"]), 0.0, rew, ln)
+            step = 0
+            for key in ("grpo_adam3_p", "grpo_adam6_p"):
+                _, old_lp = E.policy_forward_traj(dims, act_names, params, obs, cov, act, ln)
+                for _ in range(3):
+                    step += 1
+                    grad, _ = E.policy_grad(dims, act_names, params, cov, obs, act, adv, old_lp, ln,
+                                            float(g["eps_clip"]), 1.0 / G)
+                    E.adam_step(params, grad, m, v, step, 3e-4)
+                got = params.cpu().numpy()
+                off = 0
+                for i in range(2 * len(Ws)):
+                    ref = g[f"{key}{i}"]
+                    np.testing.assert_allclose(got[off:off + ref.size].reshape(ref.shape), ref, rtol=2e-4, atol=3e-6,
+                                               err_msg=f"{mode} {key}{i}")
+                    off += ref.size
+        finally:
+            E.set_math("auto")
+
+
+# ----------------------------------------------------------------------------
+# host classes on the new fixtures (GRPO.learn / PPO.learn end to end)
+# ----------------------------------------------------------------------------
+def _load_actor(net, Ws, bs):
+    sd = {}
+    for i, (w, b) in enumerate(zip(Ws, bs)):
+        sd[f"network.{2 * i}.weight"] = torch.from_numpy(w)
+        sd[f"network.{2 * i}.bias"] = torch.from_numpy(b)
+    net.load_state_dict(sd)
+
+
+def _make_buffer(tg, g):
+    buf = tg.Rollout_Buffer.__new__(tg.Rollout_Buffer)
+    buf.avg_reward = []
+    buf.device_rollout = None
+    tg.Rollout_Buffer.store(buf, g["obs"], g["act"], g["rew"], g["len"], g["mask"])
+    return buf
+
+
+@pytest.mark.parametrize("name", NEW_ROLLOUTS)
+def test_grpo_learn_host_api_matches_reference(golden_dir, name):
+    import trajopt_grpo_b200 as tg
+    g = load(golden_dir, f"rollout_grpo_{name}.npz")
+    kind = int(g["kind"])
+    Ws, bs = _weights(g)
+    hidden = [int(h) for h in g["hidden"]]
+    O, A = R.OBS_DIM[kind], R.ACT_DIM[kind]
+    buf = _make_buffer(tg, g)
+    pol = tg.GaussianActor_NeuralNetwork(O, A, hidden, _act_names(g), float(g["cov"]))
+    _load_actor(pol.actor, Ws, bs)
+    opt = torch.optim.Adam(pol.parameters(), lr=3e-4)
+    algo = tg.GRPO(float(g["eps_clip"]), 0.0, float(g["gamma"]), pol, opt, None, updates_per_iter=3)
+    for key in ("grpo_adam3_p", "grpo_adam6_p"):
+        algo.learn(buf)
+        for i, p in enumerate(pol.parameters()):
+            np.testing.assert_allclose(p.detach().cpu().numpy(), g[f"{key}{i}"], rtol=2e-4, atol=3e-6)
+
+
+PPO_NEW = ["ppo_mc_ragged_quadpole2d", "ppo_gae_ragged_quadpole2d", "ppo_mc_quadpole2d_shipped",
+           "ppo_gae_cartpole_shipped"]
+
+
+@pytest.mark.parametrize("name", PPO_NEW)
+def test_ppo_learn_matches_reference(golden_dir, name):
+    import trajopt_grpo_b200 as tg
+    g = load(golden_dir, f"{name}.npz")
+    kind = int(g["kind"])
+    hidden = [int(h) for h in g["hidden"]]
+    O, A = R.OBS_DIM[kind], R.ACT_DIM[kind]
+    Ws, bs = _weights(g)
+    cWs, cbs = _weights(g, "c")
+    buf = _make_buffer(tg, g)
+    if "ragged" in name:
+        assert len(set(g["len"].reshape(-1).tolist())) > 1
+    kw = dict(c1=0.5, kl_coeff=0.5, gamma=float(g["gamma"]), lam=float(g["lam"]), entropy=0.01, batch_size=None,
+              monte_carlo=bool(g["monte_carlo"]))
+
+    def fresh():
+        pol = tg.GaussianActorCritic_NeuralNetwork(O, A, hidden, "ReLU", float(g["cov"]))
+        _load_actor(pol.actor, Ws, bs)
+        _load_actor(pol.critic, cWs, cbs)
+        return pol
+
+    pol = fresh()
+    before = [p.detach().clone() for p in pol.parameters()]
+    tg.PPO(float(g["eps_clip"]), pol, torch.optim.SGD(pol.parameters(), lr=1.0), None, 1, **kw).learn(buf)
+    for i, (b, p) in enumerate(zip(before, pol.parameters())):
+        ref = g[f"ppo_grad{i}"]
+        got = (b - p.detach()).cpu().numpy()
+        assert np.abs(got - ref).max() <= 5e-4 * max(np.abs(ref).max(), 1e-6) + 1e-6, (i, np.abs(got - ref).max())
+    pol = fresh()
+    tg.PPO(float(g["eps_clip"]), pol, torch.optim.Adam(pol.parameters(), lr=2e-4), None, 3, **kw).learn(buf)
+    for i, p in enumerate(pol.parameters()):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), g[f"ppo_adam3_p{i}"], rtol=5e-4, atol=5e-6)
+
+
+def test_per_layer_activation_list_rejected_by_tensor_core_mode(E):
+    """A per-layer activation list runs on the FP32-pipe kernels; forcing 3xTF32 for it is an error, not a
+    silent change of arithmetic."""
+    from trajopt_grpo_b200._lib import EngineError
+    dims = [3, 64, 64, 1]
+    params = torch.zeros(3 * 64 + 64 + 64 * 64 + 64 + 64 + 1, device="cuda")
+    s0 = torch.zeros(3, 8, device="cuda"); s0[1] = -1.0
+    out = E.rollout(1, 5, 0.05, dims, ["Tanh", "ReLU"], params, [0.5], s0)      # auto: FP32 pipe
+    assert int(out["len"].min()) >= 1
+    try:
+        E.set_math("3xtf32")
+        with pytest.raises(EngineError, match="not eligible"):
+            E.rollout(1, 5, 0.05, dims, ["Tanh", "ReLU"], params, [0.5], s0)
+    finally:
+        E.set_math("auto")

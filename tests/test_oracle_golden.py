@@ -70,7 +70,15 @@ def _weights(g, prefix=""):
     return Ws, bs
 
 
-ROLLOUTS = ["cartpole", "pendulum", "quadpole2d", "quadpole"]
+ROLLOUTS = ["cartpole", "pendulum", "quadpole2d", "quadpole",
+            # round 2: BASELINE shapes (cfg 1 at full size with the shipped weights, cfg 3 / cfg 4 policy widths),
+            # depth 0 / 1 / 3, Tanh and a per-layer activation list
+            "cartpole_cfg1", "quadpole2d_w128", "quadpole_w256", "pendulum_h1", "cartpole_h3", "pendulum_h0",
+            "cartpole_tanh", "pendulum_mixed_act"]
+
+
+def _act(g):
+    return R.acts_from_names(g["activation"]) if "activation" in g else R.ACT_RELU
 
 
 @pytest.mark.parametrize("name", ROLLOUTS)
@@ -80,7 +88,7 @@ def test_rollout_matches_reference(golden_dir, name):
     Ws, bs = _weights(g)
     cfg = R.EnvCfg.make(kind, T)
     cov = np.full(R.ACT_DIM[kind], g["cov"], np.float32)
-    obs, act, rew, logp, ln, mask = R.rollout(cfg, g["init"], Ws, bs, cov, g["noise"])
+    obs, act, rew, logp, ln, mask = R.rollout(cfg, g["init"], Ws, bs, cov, g["noise"], act=_act(g))
     sh = lambda x: x.reshape((G, E) + x.shape[1:])
     assert np.array_equal(sh(ln), g["len"].astype(np.int32))       # lengths bit-exact
     assert np.array_equal(sh(mask), g["mask"])
@@ -101,7 +109,7 @@ def test_grpo_gradient_matches_reference(golden_dir, name):
     cov = np.full(R.ACT_DIM[kind], g["cov"], np.float32)
     rtg, adv = R.grpo_advantage(g["rew"], g["mask"], float(g["gamma"]))
     J, dW, db, lp, old_lp = R.grpo_objective_and_grad(g["obs"], g["act"], adv, g["mask"], Ws, bs, Ws, bs,
-                                                       cov, float(g["eps_clip"]), dtype="float32")
+                                                       cov, float(g["eps_clip"]), act=_act(g), dtype="float32")
     for i in range(len(Ws)):
         gw, gb = g[f"grpo_grad{2 * i}"], g[f"grpo_grad{2 * i + 1}"]
         scale = max(np.abs(gw).max(), 1e-6)
@@ -127,7 +135,8 @@ def test_grpo_adam_updates_match_reference(golden_dir, name):
         for it in range(3):
             step += 1
             J, dW, db, _, _ = R.grpo_objective_and_grad(g["obs"], g["act"], adv, g["mask"], params[0::2], params[1::2],
-                                                       old[0::2], old[1::2], cov, float(g["eps_clip"]), dtype="float32")
+                                                       old[0::2], old[1::2], cov, float(g["eps_clip"]), act=_act(g),
+                                                       dtype="float32")
             grads = []
             for a, b in zip(dW, db):
                 grads += [a, b]

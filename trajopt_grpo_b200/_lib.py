@@ -17,6 +17,8 @@ LIB_PATH = os.path.join(HERE, "libtrajopt_grpo_b200.so")
 TG_MAX_LAYERS = 8
 ENV_CARTPOLE, ENV_PENDULUM, ENV_QUADPOLE2D, ENV_QUADPOLE = 0, 1, 2, 3
 ACT_IDS = {"ReLU": 0, "Tanh": 1, "Sigmoid": 2}
+ACT_PER_LAYER = -1
+ABI_VERSION = 2
 PREC_F32, PREC_F64 = 0, 1
 ADV_GRPO, ADV_PPO_MC, ADV_PPO_GAE = 0, 1, 2
 
@@ -27,7 +29,8 @@ class EnvCfg(C.Structure):
 
 
 class MlpCfg(C.Structure):
-    _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * (TG_MAX_LAYERS + 1)), ("activation", C.c_int32)]
+    _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * (TG_MAX_LAYERS + 1)), ("activation", C.c_int32),
+                ("layer_activation", C.c_int32 * TG_MAX_LAYERS)]
 
 
 class EngineError(RuntimeError):
@@ -91,6 +94,9 @@ def load():
                 fn = getattr(lib, name)
                 fn.restype = res
                 fn.argtypes = args
+            if lib.tg_abi_version() != ABI_VERSION:
+                raise EngineError(f"{LIB_PATH} has ABI version {lib.tg_abi_version()}, this package binds "
+                                  f"version {ABI_VERSION}: rebuild with `python -m trajopt_grpo_b200._build --force`")
             _lib = lib
     return _lib
 
@@ -129,13 +135,23 @@ def mlp_cfg(dims, activation="ReLU") -> MlpCfg:
     dims = [int(d) for d in dims]
     if len(dims) - 1 > TG_MAX_LAYERS or len(dims) < 2:
         raise EngineError(f"MLP with {len(dims) - 1} Linear layers is outside [1, {TG_MAX_LAYERS}]")
-    if activation not in ACT_IDS:
-        raise EngineError(f"activation {activation!r} is not supported by the kernels ({sorted(ACT_IDS)})")
+    # models/neural_network.py:38-45: one torch.nn class name for every hidden layer, or a list with one per layer
+    names = list(activation) if isinstance(activation, (list, tuple)) else [activation] * max(len(dims) - 2, 1)
+    if isinstance(activation, (list, tuple)) and len(names) != len(dims) - 2:
+        raise EngineError("Number of activation functions must equal the number of hidden layers.")
+    for nm in names:
+        if nm not in ACT_IDS:
+            raise EngineError(f"activation {nm!r} is not supported by the kernels ({sorted(ACT_IDS)})")
     cfg = MlpCfg()
     cfg.n_layers = len(dims) - 1
     for i, d in enumerate(dims):
         cfg.dims[i] = d
-    cfg.activation = ACT_IDS[activation]
+    if len(set(names)) <= 1:
+        cfg.activation = ACT_IDS[names[0]] if names else 0
+    else:
+        cfg.activation = ACT_PER_LAYER          # FP32-pipe kernels; the tensor-core kernels take one activation
+        for i, nm in enumerate(names):
+            cfg.layer_activation[i] = ACT_IDS[nm]
     return cfg
 
 

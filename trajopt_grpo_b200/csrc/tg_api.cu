@@ -291,8 +291,13 @@ int tg_build_layout(const tg_mlp_cfg *mlp, bool with_backward, tg_mlp_layout *ou
     TG_REQUIRE(mlp != nullptr, TG_ERR_ARG, "mlp cfg is null");
     TG_REQUIRE(mlp->n_layers >= 1 && mlp->n_layers <= TG_MAX_LAYERS, TG_ERR_SHAPE, "n_layers %d not in [1,%d]",
                mlp->n_layers, TG_MAX_LAYERS);
-    TG_REQUIRE(mlp->activation >= 0 && mlp->activation <= 2, TG_ERR_ARG, "unknown activation %d", mlp->activation);
+    TG_REQUIRE(mlp->activation >= TG_ACT_PER_LAYER && mlp->activation <= 2, TG_ERR_ARG, "unknown activation %d",
+               mlp->activation);
     const int nl = mlp->n_layers;
+    if (mlp->activation == TG_ACT_PER_LAYER)
+        for (int l = 0; l < nl - 1; ++l)
+            TG_REQUIRE(mlp->layer_activation[l] >= 0 && mlp->layer_activation[l] <= 2, TG_ERR_ARG,
+                       "unknown activation %d after hidden layer %d", mlp->layer_activation[l], l);
     TG_REQUIRE(mlp->dims[0] >= 1 && mlp->dims[0] <= TG_MAX_WIDTH, TG_ERR_SHAPE, "input dim %d out of range", mlp->dims[0]);
     TG_REQUIRE(mlp->dims[nl] >= 1 && mlp->dims[nl] <= TG_MAX_ACT, TG_ERR_SHAPE, "output dim %d not in [1,%d]",
                mlp->dims[nl], TG_MAX_ACT);
@@ -306,6 +311,8 @@ int tg_build_layout(const tg_mlp_cfg *mlp, bool with_backward, tg_mlp_layout *ou
     memset(out, 0, sizeof(*out));
     out->n_layers = nl;
     out->act = mlp->activation;
+    for (int l = 0; l < TG_MAX_LAYERS; ++l)
+        out->acts[l] = mlp->activation == TG_ACT_PER_LAYER ? (l < nl - 1 ? mlp->layer_activation[l] : 0) : mlp->activation;
     out->cfg = maxh <= 64 ? 0 : (maxh <= 128 ? 1 : 2);
     out->O = mlp->dims[0];
     out->A = mlp->dims[nl];

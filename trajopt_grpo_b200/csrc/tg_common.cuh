@@ -16,8 +16,8 @@ void tg_set_error(const char *fmt, ...);
     do {                                                                           \
         cudaError_t _e = (expr);                                                   \
         if (_e != cudaSuccess) {                                                   \
-            tg_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
-            return (int)_e;                                                        \
+            tg_set_error("%s:%d %s -> cudaError %d (%s)", __FILE__, __LINE__, #expr, (int)_e, cudaGetErrorString(_e)); \
+            return TG_ERR_CUDA;                                                    \
         }                                                                          \
     } while (0)
 #define TG_REQUIRE(cond, code, ...)                                                \
@@ -79,6 +79,7 @@ struct tg_layer_layout {
 };
 struct tg_mlp_layout {
     int n_layers, act, cfg, NP, B, NT;
+    int acts[TG_MAX_LAYERS];  // activation after hidden Linear l (all equal to `act` unless TG_ACT_PER_LAYER)
     int O, A, kmax;  // kmax = max input width over layers (activation buffer rows)
     tg_layer_layout L[TG_MAX_LAYERS];
     int64_t total;   // floats in the staged buffer

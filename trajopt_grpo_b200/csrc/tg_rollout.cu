@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(TileCfg<CFG>::NT) rollout_kernel(const __grid_
         // 2. hidden layers (ping-pong Xa <-> Xb)
         float *xin = Xa, *xout = Xb;
         for (int l = 0; l < nl - 1; ++l) {
-            tile_layer<CFG, 0, WG>(W + a.lay.L[l].wt, W + a.lay.L[l].bias, xin, xout, a.lay.L[l].K, a.lay.act);
+            tile_layer<CFG, 0, WG>(W + a.lay.L[l].wt, W + a.lay.L[l].bias, xin, xout, a.lay.L[l].K, a.lay.acts[l]);
             __syncthreads();
             float *tmp = xin; xin = xout; xout = tmp;
         }
@@ -652,9 +652,10 @@ extern "C" int tg_rollout(tg_ctx *ctx, const tg_env_cfg *env, const tg_mlp_cfg *
     if (rc) return rc;
     int O, A;
     tg_env_dims(env->kind, &O, &A);
-    TG_REQUIRE(mlp->n_layers >= 1 && mlp->dims[0] == O && mlp->dims[mlp->n_layers] == A, TG_ERR_SHAPE,
-               "policy dims (%d -> %d) do not match env obs/act dims (%d/%d)", mlp->dims[0],
-               mlp->dims[mlp->n_layers > 0 ? mlp->n_layers : 0], O, A);
+    TG_REQUIRE(mlp->n_layers >= 1 && mlp->n_layers <= TG_MAX_LAYERS, TG_ERR_SHAPE, "n_layers %d not in [1,%d]",
+               mlp->n_layers, TG_MAX_LAYERS);
+    TG_REQUIRE(mlp->dims[0] == O && mlp->dims[mlp->n_layers] == A, TG_ERR_SHAPE,
+               "policy dims (%d -> %d) do not match env obs/act dims (%d/%d)", mlp->dims[0], mlp->dims[mlp->n_layers], O, A);
     cudaStream_t st = (cudaStream_t)stream;
     TG_CUDA(cudaSetDevice(ctx->device));
     // ---- tensor-core paths (3xTF32 tcgen05) for eligible policies

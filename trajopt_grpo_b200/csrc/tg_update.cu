@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(TileCfg<CFG>::NT) update_kernel(const __grid_c
         // ---- 2. forward, keeping H_1..H_nh
         for (int l = 0; l < nh; ++l) {
             tile_layer<CFG, 0, WG>(W + a.lay.L[l].wt, W + a.lay.L[l].bias, l == 0 ? X0 : H + (size_t)(l - 1) * NP * LDX,
-                                   H + (size_t)l * NP * LDX, a.lay.L[l].K, a.lay.act);
+                                   H + (size_t)l * NP * LDX, a.lay.L[l].K, a.lay.acts[l]);
             __syncthreads();
         }
         const float *Hlast = nh > 0 ? H + (size_t)(nh - 1) * NP * LDX : X0;
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(TileCfg<CFG>::NT) update_kernel(const __grid_c
                 if (k < K) {
 #pragma unroll
                     for (int j = 0; j < A; ++j) s = fmaf(ldw1<WG>(Wo + j * K + k), D[j * LDX + b], s);
-                    s *= act_bwd_from_out(Hl[k * LDX + b], a.lay.act);
+                    s *= act_bwd_from_out(Hl[k * LDX + b], a.lay.acts[nh - 1]);
                 }
                 Hl[k * LDX + b] = s;
             }
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(TileCfg<CFG>::NT) update_kernel(const __grid_c
                 tile_dw<CFG>(dZ, L.N, Hin, L.K, gp + L.flat_w, gp + L.flat_w + (int64_t)L.N * L.K);
                 __syncthreads();
                 if (l > 0) {
-                    tile_layer<CFG, 1, WG>(W + L.wn, nullptr, dZ, Hin, L.N, a.lay.act);
+                    tile_layer<CFG, 1, WG>(W + L.wn, nullptr, dZ, Hin, L.N, a.lay.acts[l - 1]);
                     __syncthreads();
                 }
             }

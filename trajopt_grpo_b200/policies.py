@@ -44,20 +44,21 @@ class NeuralNetwork(torch.nn.Module):
                 activations = activation
             else:
                 raise TypeError("activation must be either a string or a list of strings.")
-            if len(set(activations)) != 1:
-                raise L.EngineError("the kernels take one activation for all hidden layers")
             layers = []
             dims = [input_dim] + list(hidden_dims)
             for i in range(len(hidden_dims)):
                 layers.append(torch.nn.Linear(dims[i], dims[i + 1]))
                 layers.append(getattr(torch.nn, activations[i])())
             layers.append(torch.nn.Linear(hidden_dims[-1], output_dim))
-            self.activation_name = activations[0]
+            # what the kernels are told: one name, or the per-layer list (FP32-pipe kernels)
+            self.activation_name = activations[0] if len(set(activations)) == 1 else list(activations)
         else:
             layers = [torch.nn.Linear(input_dim, output_dim)]
+            activations = []
             self.activation_name = "ReLU"
-        if self.activation_name not in L.ACT_IDS:
-            raise L.EngineError(f"activation {self.activation_name!r} is not supported by the kernels")
+        for nm in activations:
+            if nm not in L.ACT_IDS:
+                raise L.EngineError(f"activation {nm!r} is not supported by the kernels ({sorted(L.ACT_IDS)})")
         self.network = torch.nn.Sequential(*layers)
         self.dims = [input_dim] + list(hidden_dims) + [output_dim]
         self._flat = None
