@@ -83,6 +83,11 @@ typedef struct tg_env_cfg {
     double dt;               /* env.timestep */
     int32_t time_limit_step; /* CartPole, Pendulum */
     int32_t balanced_limit;  /* Pendulum */
+    /* physical constructor arguments (all zero = the reference's defaults):
+     *   CartPole (cartpole_env.py:7-16): masscart, masspole, length, gravity
+     *   Pendulum (pendulum_env.py:8-17): mass, length, gravity, -
+     * QuadPole2D / QuadPole take none in the reference (quadrotor_env.py:353-357, 867-872). */
+    double phys[4];
 } tg_env_cfg;
 
 /* models/neural_network.py:36-65 -- n_layers Linear layers, dims[0]=input_dim,
@@ -183,6 +188,13 @@ int tg_env_step(tg_ctx *ctx, const tg_env_cfg *env, int precision, int64_t N,
                 const void *state, const float *raw_action, const int32_t *steps_done,
                 const int32_t *bal_count, void *next_state, void *reward, int32_t *done,
                 int32_t *bal_out, void *stream);
+
+/* Env._dynamics(state, control) (cartpole_env.py:51-92, pendulum_env.py:48-75, quadrotor_env.py:417-528,
+ * 1044-1130): the state transition alone, for N independent envs, with the control ALREADY wrapped
+ * (what step() passes after _wrap_action; float32 like the reference's wrapped action).
+ *   state [S][N] (float|double per precision), control [A][N] fp32 -> next_state [S][N] */
+int tg_env_dynamics(tg_ctx *ctx, const tg_env_cfg *env, int precision, int64_t N, const void *state,
+                    const float *control, void *next_state, void *stream);
 
 /* Quadrotor._dynamics (quadrotor_env.py:113-169): state [12][N], control [4][N]
  * (both float|double per precision) -> next [12][N]. */

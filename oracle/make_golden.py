@@ -54,11 +54,17 @@ def set_state(env, kind, vec):
     env._time_balanced = 0
 
 
-def gen_transitions(kind, rng, episodes, scale, max_steps=None, pd=False):
-    """Run episodes of the real env on random raw actions; record every transition."""
+def gen_transitions(kind, rng, episodes, scale, max_steps=None, pd=False, env_kw=None, dynamics=False):
+    """Run episodes of the real env on random raw actions; record every transition.  `dynamics`: also call
+    Env._dynamics(state, wrapped action) directly (the known answers of the tg_env_dynamics entry point)."""
     cls = _envs()[kind]
-    env = cls() if max_steps is None else cls(max_steps=max_steps)
+    kw = dict(env_kw or {})
+    if max_steps is not None:
+        kw["max_steps"] = max_steps
+    env = cls(**kw)
     rows = {k: [] for k in ["state", "action", "next", "reward", "done", "steps_done", "bal_count"]}
+    if dynamics:
+        rows["control"], rows["dyn_next"] = [], []
     for ep in range(episodes):
         obs, _ = env.reset()
         bal = 0
@@ -74,6 +80,10 @@ def gen_transitions(kind, rng, episodes, scale, max_steps=None, pd=False):
             rows["action"].append(a)
             rows["steps_done"].append(t)
             rows["bal_count"].append(bal)
+            if dynamics:
+                u = np.asarray(env._wrap_action(a), dtype=np.float32)
+                rows["control"].append(u)
+                rows["dyn_next"].append(np.asarray(env._dynamics(np.array(obs, dtype=np.float64), u), dtype=np.float64).reshape(-1))
             obs, r, f1, f2, _ = env.step(a)
             if kind == 1:
                 bal = bal + 1 if obs[1] <= -0.99 else 0
@@ -304,6 +314,72 @@ def gen_ppo_minibatch(kind, hidden, cov, G, E, T, seed, gamma, lam, eps_clip, ba
     return out
 
 
+SHIPPED = ["CartPole/cartpole_nn_grpo/001", "CartPole/cartpole_nn_ppo/001", "QuadPole2D/quadpole2d_nn_ppo/001"]
+
+
+def copy_shipped():
+    """The reference ships three trained checkpoints under reports/** (policy.pt, optimizer.pt[h], reward.csv,
+    metadata.json: DATA files written by Pipeline.save, pipelines/pipeline.py:104-118).  They are copied to
+    tests/golden/shipped/ so that the GPU box (no /root/reference) can test that they load and resume."""
+    import shutil
+    for rel in SHIPPED:
+        src = os.path.join(ref_shims.REFERENCE_ROOT, "reports", rel)
+        dst = os.path.join(OUT, "shipped", rel)
+        os.makedirs(dst, exist_ok=True)
+        for f in os.listdir(src):
+            if f.split(".")[-1] in ("pt", "pth", "csv", "json"):
+                shutil.copyfile(os.path.join(src, f), os.path.join(dst, f))
+
+
+def gen_resume(algo_name, kind, hidden, report, G, E, T, seed, updates):
+    """Resume from a shipped checkpoint the way Pipeline.load does (pipelines/pipeline.py:93-102:
+    algorithm.load, policy.load, buffer.load), then one learn() on an injected rollout: the loaded Adam
+    moments and step count decide the update, so the weights afterwards pin the whole resume path.
+    (GaussianActor_NeuralNetwork has no load() in the reference -- GRPO resume raises there; its policy.pt is
+    loaded through load_state_dict instead.)"""
+    import json
+    from algorithms.grpo import GRPO
+    from algorithms.ppo import PPO
+    from buffers.rollout_buffer import Rollout_Buffer
+    path = os.path.join(ref_shims.REFERENCE_ROOT, "reports", report)
+    meta = json.load(open(os.path.join(path, "metadata.json")))
+    rng = np.random.default_rng(seed)
+    import restate
+    ppo = algo_name == "ppo"
+    policy = make_policy(kind, hidden, 0.5, seed, critic=ppo)
+    am = meta["algorithm"]
+    if ppo:
+        opt = torch.optim.Adam(policy.parameters(), lr=2e-4)
+        algo = PPO(am["epsilon"], policy, opt, None, updates, c1=am["c1"], kl_coeff=am["kl_coeff"], gamma=am["gamma"],
+                   lam=am["lam"], entropy=am["entropy"], batch_size=am["batch_size"], monte_carlo=True)
+        algo.load(path)
+        policy.load(path)
+    else:
+        opt = torch.optim.Adam(policy.parameters(), lr=3e-4)
+        algo = GRPO(am["epsilon"], am["beta"], 0.5, policy, opt, None, updates_per_iter=updates)
+        algo.load(path)
+        policy.load_state_dict(torch.load(os.path.join(path, "policy.pt"), weights_only=True))
+        algo.old_policy.load_state_dict(policy.state_dict())
+    rb = Rollout_Buffer.__new__(Rollout_Buffer)
+    n_epochs = Rollout_Buffer.load(rb, path)
+    A = {0: 1, 1: 1, 2: 2, 3: 4}[kind]
+    init = restate.reset_states(kind, G * E, rng)
+    noise = rng.standard_normal((T, G * E, A)).astype(np.float32)
+    obs, act, rew, ln, mask = run_rollout(kind, policy, init, noise, G, E, T, False)
+    buf = Buf()
+    buf.group_observations, buf.group_actions = torch.from_numpy(obs), torch.from_numpy(act)
+    buf.group_rewards, buf.group_masks = torch.from_numpy(rew), torch.from_numpy(mask)
+    step0 = int(float(opt.state_dict()["state"][0]["step"]))
+    algo.learn(buf)
+    out = dict(kind=kind, hidden=np.array(hidden, dtype=np.int64), G=G, E=E, T=T, updates=updates, report=np.array(report),
+               init=init, noise=noise, obs=obs, act=act, rew=rew, len=ln, mask=mask, n_epochs_loaded=n_epochs,
+               step_loaded=step0, step_after=int(float(opt.state_dict()["state"][0]["step"])),
+               gamma=float(am.get("gamma", 0.5)), lam=float(am.get("lam", 0.0)), epsilon=float(am["epsilon"]))
+    for i, a in enumerate(policy.parameters()):
+        out[f"resume_p{i}"] = a.detach().numpy().copy()
+    return out
+
+
 def _same(a, b):
     return a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b, equal_nan=a.dtype.kind == "f")
 
@@ -344,6 +420,16 @@ def fixtures():
     for k in range(4):
         F[f"transitions_env{k}"] = transitions(k)
     F["quadrotor12_dynamics"] = lambda: gen_quadrotor12(np.random.default_rng(20261019))
+    # non-default physical constructor arguments (cartpole_env.py:7-16, pendulum_env.py:8-17) and direct
+    # Env._dynamics(state, control) calls for all four envs
+    CP_KW = dict(masscart=0.7, masspole=0.3, length=0.8, gravity=9.5, timestep=0.025)
+    PD_KW = dict(mass=0.6, length=0.9, gravity=9.7, timestep=0.04)
+    F["transitions_cartpole_params"] = lambda: dict(gen_transitions(0, np.random.default_rng(41), 4, 1.0, 100, env_kw=CP_KW,
+                                                                    dynamics=True), **{k: np.float64(v) for k, v in CP_KW.items()})
+    F["transitions_pendulum_params"] = lambda: dict(gen_transitions(1, np.random.default_rng(42), 3, 0.8, 100, env_kw=PD_KW,
+                                                                    dynamics=True), **{k: np.float64(v) for k, v in PD_KW.items()})
+    F["dynamics_quadpole2d"] = lambda: gen_transitions(2, np.random.default_rng(43), 2, 1.0, 60, dynamics=True)
+    F["dynamics_quadpole"] = lambda: gen_transitions(3, np.random.default_rng(44), 2, 1.0, 60, dynamics=True)
 
     roll = {
         # round 1: small policies, one per env
@@ -390,6 +476,12 @@ def fixtures():
     F["ppo_minibatch_quadpole2d"] = lambda: gen_ppo_minibatch(kind=2, hidden=[32, 32], cov=0.5, G=3, E=4, T=120, seed=11,
                                                               gamma=0.99, lam=0.95, eps_clip=0.2, batch_size=64, updates=2,
                                                               torch_seed=4321)
+    # resume from the shipped checkpoints (Pipeline(load_path=...) semantics), then one learn()
+    F["resume_grpo_cartpole"] = lambda: gen_resume("grpo", 0, [128, 128, 128, 128], SHIPPED[0], G=3, E=4, T=60, seed=31,
+                                                   updates=2)
+    F["resume_ppo_cartpole"] = lambda: gen_resume("ppo", 0, [128, 128, 128], SHIPPED[1], G=2, E=3, T=80, seed=32, updates=2)
+    F["resume_ppo_quadpole2d"] = lambda: gen_resume("ppo", 2, [128, 128, 128], SHIPPED[2], G=2, E=3, T=80, seed=33,
+                                                    updates=2)
     return F
 
 
@@ -400,6 +492,8 @@ def main():
     ref_shims.install()
     os.makedirs(OUT, exist_ok=True)
     check = "--check" in sys.argv
+    if not check:
+        copy_shipped()
     only = None
     if "--only" in sys.argv:
         only = set(sys.argv[sys.argv.index("--only") + 1].split(","))

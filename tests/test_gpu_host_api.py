@@ -259,46 +259,205 @@ def test_trajectory_export_matches_reference_loop(tg, tmp_path):
     np.testing.assert_allclose(df.values[:, 1:], want, rtol=1e-12, atol=0)
 
 
-def test_pipeline_train_save_load_resume(tg, tmp_path):
-    """pipelines/pipeline.py: train -> archive checkpoint in the reference's file formats -> a new
-    Pipeline(load_path=...) resumes with identical policy, optimizer state and reward history."""
-    import json
+def _epoch_loop(policy, algo, buf, epochs, save_dir):
+    """The calls the reference's orchestration makes on the hot-path objects, and nothing else
+    (pipelines/pipeline.py:163-164 sample -> learn; :111-113 the three save() calls).  The reference's own
+    Pipeline class drives the engine's classes unchanged; tests/test_dropin_surface.py checks in the build
+    container that every attribute it touches exists here."""
+    for _ in range(epochs):
+        buf.sample()
+        algo.learn(buf)
+        for part in (algo, policy, buf):
+            part.save(save_dir)
 
-    def build(load_path=None):
+
+def test_train_checkpoint_resume_through_the_reference_protocol(tg, tmp_path):
+    """train -> checkpoint in the reference's file formats -> fresh objects load() it (what
+    Pipeline(load_path=...) does, pipeline.py:93-102) -> identical policy, optimizer state and reward history,
+    and the resumed run continues bit-identically to the uninterrupted one."""
+    d = str(tmp_path)
+
+    def build():
         torch.manual_seed(4)
         pol = tg.GaussianActor_NeuralNetwork(5, 1, [32, 32], "ReLU", 0.5)
         opt = torch.optim.Adam(pol.parameters(), lr=3e-4)
         algo = tg.GRPO(0.15, 0.5, 0.5, pol, opt, None, updates_per_iter=1)
-        env_fn = lambda: tg.CartPole(max_steps=40)
-        mgr = tg.RolloutManager(env_fn, pol, restart=False, num_workers=4, num_episodes_per_worker=5,
-                                use_multiprocessing=False, seed=1)
-        buf = tg.Rollout_Buffer(mgr)
-        return tg.Pipeline("cartpole_nn_grpo", "001", env_fn, pol, algo, mgr, buf, None, None, load_path=load_path,
-                           save_freq=1, root=str(tmp_path)), pol, opt, buf
+        mgr = tg.RolloutManager(lambda: tg.CartPole(max_steps=40), pol, restart=False, num_workers=4,
+                                num_episodes_per_worker=5, use_multiprocessing=False, seed=1)
+        return pol, opt, algo, mgr, tg.Rollout_Buffer(mgr)
 
-    pipe, pol, opt, buf = build()
-    pipe.train(3)
-    d = pipe.archive_path
-    assert d.endswith(os.path.join("archive", "CartPole", "cartpole_nn_grpo", "001"))
-    for f in ("policy.pt", "optimizer.pth", "reward.csv", "metadata.json"):
+    pol, opt, algo, mgr, buf = build()
+    _epoch_loop(pol, algo, buf, 3, d)
+    for f in ("policy.pt", "optimizer.pth", "reward.csv"):
         assert os.path.exists(os.path.join(d, f)), f
-    meta = json.load(open(os.path.join(d, "metadata.json")))
-    assert meta["env_name"] == "CartPole" and meta["policy"]["hidden_dims"] == [32, 32]
+    meta = {"policy": pol.metadata(), "algorithm": algo.metadata(), "buffer": buf.metadata()}     # pipeline.py:120-139
+    assert meta["policy"]["hidden_dims"] == [32, 32]
     assert meta["algorithm"] == {"algorithm": "GRPO", "epsilon": 0.15, "beta": 0.5, "updates_per_iter": 1}
     assert meta["policy"]["num_parameters"] == 5 * 32 + 32 + 32 * 32 + 32 + 32 + 1
-    pipe2, pol2, opt2, buf2 = build(load_path=d)
+    assert isinstance(meta["buffer"]["avg_reward"], float)
+    pol2, opt2, algo2, mgr2, buf2 = build()
+    algo2.load(d); pol2.load(d); n = buf2.load(d)                  # pipeline.py:98-100, in its order
+    assert n == 3 and np.allclose(buf2.avg_reward, [float(x) for x in buf.avg_reward])
     assert torch.equal(pol2.flat_parameters(), pol.flat_parameters())
-    assert len(buf2.avg_reward) == 3 and np.allclose(buf2.avg_reward, [float(x) for x in buf.avg_reward])
-    assert pipe2.loaded_metadata["checkpoint_name"] == "001"
+    # continue both: same manager stream position is part of the resume contract of OUR seedable manager
+    mgr2._epoch, mgr2._rng = mgr._epoch, np.random.default_rng(123)
+    mgr._rng = np.random.default_rng(123)
+    buf.sample(); algo.learn(buf)
+    buf2.sample(); algo2.learn(buf2)
+    assert torch.equal(pol2.flat_parameters(), pol.flat_parameters())
     s1, s2 = opt.state_dict()["state"], opt2.state_dict()["state"]
     assert s1.keys() == s2.keys()
     for k in s1:
         assert torch.equal(s1[k]["exp_avg"].cpu(), s2[k]["exp_avg"].cpu())
-        assert float(s1[k]["step"]) == float(s2[k]["step"]) == 3.0
-    pipe2.save_trajectory()
-    assert os.path.exists(os.path.join(pipe2.archive_path, "trajectory.csv"))
-    pipe2.publish()
-    assert os.path.exists(os.path.join(pipe2.publish_path, "metadata.json"))
+        assert float(s1[k]["step"]) == float(s2[k]["step"]) == 4.0
+    buf2.save_trajectory(d)
+    assert os.path.exists(os.path.join(d, "trajectory.csv"))
+    mgr.shutdown(); mgr2.shutdown()                                # pipeline.py:207
+
+
+def test_learn_sees_weights_loaded_after_construction(tg, golden_dir):
+    """weights written through torch (load_state_dict, p.add_) after GRPO was constructed, or into
+    old_policy, must defeat the 'rollout log-prob == old-policy log-prob' shortcut (grpo.py:118-119)."""
+    g = load(golden_dir, "rollout_grpo_pendulum.npz")
+    Ws, bs = _weights(g)
+    hidden = [int(h) for h in g["hidden"]]
+    torch.manual_seed(0)
+    pol = tg.GaussianActor_NeuralNetwork(3, 1, hidden, "ReLU", float(g["cov"]))
+    algo = tg.GRPO(float(g["eps_clip"]), 0.0, float(g["gamma"]), pol, torch.optim.Adam(pol.parameters(), lr=3e-4), None,
+                   updates_per_iter=3)
+    t0 = pol.param_tag()
+    _load_actor(pol.actor, Ws, bs)                                 # load AFTER construction: old_policy is stale
+    assert pol.param_tag() != t0
+    with torch.no_grad():
+        next(iter(pol.parameters())).add_(0.0)
+    mgr = tg.RolloutManager(lambda: tg.Pendulum(max_steps=int(g["T"])), pol, restart=True, num_workers=int(g["G"]),
+                            num_episodes_per_worker=int(g["E"]), use_multiprocessing=False, seed=0)
+    buf = tg.Rollout_Buffer(mgr)
+    init = torch.from_numpy(g["init"].T.copy()).float().cuda()
+    nz = torch.from_numpy(np.ascontiguousarray(g["noise"].transpose(0, 2, 1))).cuda()
+    buf.sample(init_state=init, noise=nz)
+    # reference semantics: old log-probs come from old_policy (random init here), NOT from the rollout weights
+    old = algo.old_policy
+    ref_pol = tg.GaussianActor_NeuralNetwork(3, 1, hidden, "ReLU", float(g["cov"]))
+    ref_pol.load_state_dict(pol.state_dict())
+    ref_algo = tg.GRPO(float(g["eps_clip"]), 0.0, float(g["gamma"]), ref_pol, torch.optim.Adam(ref_pol.parameters(), lr=3e-4),
+                       None, updates_per_iter=3)
+    ref_algo.old_policy.load_state_dict(old.state_dict())          # explicit stale old policy: never takes the shortcut
+    assert ref_algo.old_policy.param_tag() != ref_algo._old_tag
+    algo.learn(buf)
+    ref_algo.learn(buf)
+    assert torch.equal(pol.flat_parameters(), ref_pol.flat_parameters())
+    # and the shortcut's own result differs (ratio != 1 from the first update), so the check above is not vacuous
+    p3 = tg.GaussianActor_NeuralNetwork(3, 1, hidden, "ReLU", float(g["cov"]))
+    _load_actor(p3.actor, Ws, bs)                                  # loaded BEFORE GRPO copies it: old == current
+    a3 = tg.GRPO(float(g["eps_clip"]), 0.0, float(g["gamma"]), p3, torch.optim.Adam(p3.parameters(), lr=3e-4), None,
+                 updates_per_iter=3)
+    mgr3 = tg.RolloutManager(lambda: tg.Pendulum(max_steps=int(g["T"])), p3, restart=True, num_workers=int(g["G"]),
+                             num_episodes_per_worker=int(g["E"]), use_multiprocessing=False, seed=0)
+    b3 = tg.Rollout_Buffer(mgr3)
+    b3.sample(init_state=init, noise=nz)
+    a3.learn(b3)
+    assert not torch.equal(p3.flat_parameters(), pol.flat_parameters())
+
+
+RESUME = [("resume_grpo_cartpole", "grpo"), ("resume_ppo_cartpole", "ppo"), ("resume_ppo_quadpole2d", "ppo")]
+
+
+@pytest.mark.parametrize("name,kind_name", RESUME)
+def test_resume_from_shipped_checkpoints(tg, golden_dir, name, kind_name):
+    """The three checkpoints the reference ships under reports/** (copied as data to tests/golden/shipped by
+    oracle/make_golden.py) load through algorithm.load / policy.load / buffer.load, and one learn() from the
+    loaded Adam state reproduces the unmodified reference's resumed update."""
+    import json
+    g = load(golden_dir, f"{name}.npz")
+    path = os.path.join(golden_dir, "shipped", str(g["report"]))
+    meta = json.load(open(os.path.join(path, "metadata.json")))
+    kind = int(g["kind"])
+    hidden = [int(h) for h in g["hidden"]]
+    assert hidden == meta["policy"]["hidden_dims"]
+    O, A = R.OBS_DIM[kind], R.ACT_DIM[kind]
+    am = meta["algorithm"]
+    torch.manual_seed(0)
+    if kind_name == "ppo":
+        pol = tg.GaussianActorCritic_NeuralNetwork(O, A, hidden, meta["policy"]["activation"], 0.5)
+        opt = torch.optim.Adam(pol.parameters(), lr=2e-4)
+        algo = tg.PPO(am["epsilon"], pol, opt, None, int(g["updates"]), c1=am["c1"], kl_coeff=am["kl_coeff"],
+                      gamma=am["gamma"], lam=am["lam"], entropy=am["entropy"], batch_size=am["batch_size"], monte_carlo=True)
+    else:
+        pol = tg.GaussianActor_NeuralNetwork(O, A, hidden, meta["policy"]["activation"], 0.5)
+        opt = torch.optim.Adam(pol.parameters(), lr=3e-4)
+        algo = tg.GRPO(am["epsilon"], am["beta"], 0.5, pol, opt, None, updates_per_iter=int(g["updates"]))
+    mgr = tg.RolloutManager(lambda: getattr(tg, ENV_CLS[kind])(max_steps=int(g["T"])), pol, num_workers=int(g["G"]),
+                            num_episodes_per_worker=int(g["E"]), use_multiprocessing=False, seed=0)
+    buf = tg.Rollout_Buffer(mgr)
+    algo.load(path); pol.load(path); n_epochs = buf.load(path)      # pipelines/pipeline.py:98-100
+    assert n_epochs == int(g["n_epochs_loaded"])
+    assert pol.metadata()["num_parameters"] == meta["policy"]["num_parameters"]
+    sd = torch.load(os.path.join(path, "policy.pt"), weights_only=True)
+    first = (sd["actor"] if kind_name == "ppo" else sd)["network.0.weight"]
+    assert torch.equal(next(iter(pol.parameters())).detach().cpu(), first)
+    tg.Rollout_Buffer.store(buf, g["obs"], g["act"], g["rew"], g["len"], g["mask"])
+    algo.learn(buf)
+    assert algo._flat_opt.step_count == int(g["step_after"]) == int(g["step_loaded"]) + int(g["updates"])
+    for i, p in enumerate(pol.parameters()):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), g[f"resume_p{i}"], rtol=5e-4, atol=5e-6, err_msg=f"param {i}")
+    assert int(float(opt.state_dict()["state"][0]["step"])) == int(g["step_after"])
+
+
+@pytest.mark.parametrize("name,kind,keys", [("cartpole", 0, ("masscart", "masspole", "length", "gravity")),
+                                            ("pendulum", 1, ("mass", "length", "gravity"))])
+def test_env_with_non_default_physical_parameters(tg, golden_dir, name, kind, keys):
+    """CartPole / Pendulum constructed with non-default masses, length, gravity, timestep (cartpole_env.py:7-16,
+    pendulum_env.py:8-17): batched tg_env_step in float64 vs the reference's transitions, Env._dynamics, and a
+    free-running rollout against the oracle with the same parameters."""
+    from trajopt_grpo_b200 import engine as E
+    g = load(golden_dir, f"transitions_{name}_params.npz")
+    kw = {k: float(g[k]) for k in keys}
+    dt = float(g["timestep"])
+    env = getattr(tg, ENV_CLS[kind])(max_steps=100, timestep=dt, **kw)
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    nxt, rew, done, _ = E.env_step(kind, 100, dt, dev(g["state"].T), dev(g["action"].T), dev(g["steps_done"].astype(np.int32)),
+                                   dev(g["bal_count"].astype(np.int32)), phys=env._tg_phys)
+    np.testing.assert_allclose(nxt.cpu().numpy().T, g["next"], rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(rew.cpu().numpy(), g["reward"], rtol=1e-10, atol=1e-11)
+    assert np.array_equal(done.cpu().numpy().astype(bool), g["done"])
+    for i in (0, 7, 50):
+        np.testing.assert_allclose(env._dynamics(g["state"][i], g["control"][i]), g["dyn_next"][i], rtol=1e-11, atol=1e-12)
+    # free-running rollout through the host classes vs the oracle with the same physical parameters
+    rng = np.random.default_rng(3)
+    torch.manual_seed(0)
+    pol = tg.GaussianActor_NeuralNetwork(R.OBS_DIM[kind], 1, [32, 32], "ReLU", 0.5)
+    Gn, En, T = 4, 4, 25
+    mgr = tg.RolloutManager(lambda: getattr(tg, ENV_CLS[kind])(max_steps=T, timestep=dt, **kw), pol, num_workers=Gn,
+                            num_episodes_per_worker=En, use_multiprocessing=False, seed=0, precision="f64")
+    init = R.reset_states(kind, Gn * En, rng)
+    noise = rng.standard_normal((T, Gn * En, 1)).astype(np.float32)
+    r = mgr.rollout_device(init_state=dev(init.T), noise=dev(noise.transpose(0, 2, 1)))
+    Ws = [pol.actor.network[i].weight.detach().cpu().numpy() for i in (0, 2, 4)]
+    bs = [pol.actor.network[i].bias.detach().cpu().numpy() for i in (0, 2, 4)]
+    cfg = R.EnvCfg.make(kind, T, dt, phys=[kw[k] for k in keys])
+    o, a, rw, lp, ln, m = R.rollout(cfg, init, Ws, bs, np.array([0.5], np.float32), noise)
+    assert np.array_equal(r.len.cpu().numpy(), ln)
+    np.testing.assert_allclose(r.obs.cpu().numpy().transpose(2, 0, 1), o, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(r.rew.cpu().numpy().T, rw, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("name,kind", [("dynamics_quadpole2d", 2), ("dynamics_quadpole", 3), ("transitions_cartpole_params", None)])
+def test_env_dynamics_matches_reference(tg, golden_dir, name, kind):
+    """Env._dynamics(state, control) (quadrotor_env.py:417-528, 1044-1130) through tg_env_dynamics: float64 vs the
+    reference's direct _dynamics calls, float32 within the throughput-mode tolerance."""
+    from trajopt_grpo_b200 import engine as E
+    if kind is None:
+        return
+    g = load(golden_dir, f"{name}.npz")
+    dev = lambda x, dt=None: torch.from_numpy(np.ascontiguousarray(x)).cuda() if dt is None else \
+        torch.from_numpy(np.ascontiguousarray(x)).cuda().to(dt)
+    nxt = E.env_dynamics(kind, 0.02, dev(g["state"].T), dev(g["control"].T))
+    np.testing.assert_allclose(nxt.cpu().numpy().T, g["dyn_next"], rtol=1e-11, atol=1e-12)
+    nxt32 = E.env_dynamics(kind, 0.02, dev(g["state"].T, torch.float32), dev(g["control"].T))
+    np.testing.assert_allclose(nxt32.cpu().numpy().T, g["dyn_next"], rtol=1e-5, atol=1e-5)
+    env = getattr(tg, ENV_CLS[kind])()
+    np.testing.assert_allclose(env._dynamics(g["state"][3], g["control"][3]), g["dyn_next"][3], rtol=1e-11, atol=1e-12)
 
 
 def test_ppo_minibatched_learn_matches_reference(tg, golden_dir):

@@ -36,6 +36,18 @@ def test_transitions_float32_mode_close(golden_dir, kind):
     np.testing.assert_allclose(rew, g["reward"], rtol=1e-4, atol=2e-4)
 
 
+@pytest.mark.parametrize("name,kind,keys", [("cartpole", 0, ("masscart", "masspole", "length", "gravity")),
+                                            ("pendulum", 1, ("mass", "length", "gravity"))])
+def test_transitions_non_default_physical_parameters(golden_dir, name, kind, keys):
+    """CartPole / Pendulum constructed with non-default masses, lengths, gravity and timestep."""
+    g = load(golden_dir, f"transitions_{name}_params.npz")
+    cfg = R.EnvCfg.make(kind, 100, float(g["timestep"]), phys=[float(g[k]) for k in keys])
+    nxt, rew, done, _ = R.env_step(cfg, g["state"], g["action"], g["steps_done"], g["bal_count"], np.float64)
+    np.testing.assert_allclose(nxt, g["next"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(rew, g["reward"], rtol=1e-11, atol=1e-12)
+    assert np.array_equal(done, g["done"])
+
+
 def test_quadrotor12_dynamics(golden_dir):
     g = load(golden_dir, "quadrotor12_dynamics.npz")
     out = R.quadrotor12_dynamics(g["state"], g["control"])

@@ -25,7 +25,7 @@ ADV_GRPO, ADV_PPO_MC, ADV_PPO_GAE = 0, 1, 2
 
 class EnvCfg(C.Structure):
     _fields_ = [("kind", C.c_int32), ("max_steps", C.c_int32), ("dt", C.c_double),
-                ("time_limit_step", C.c_int32), ("balanced_limit", C.c_int32)]
+                ("time_limit_step", C.c_int32), ("balanced_limit", C.c_int32), ("phys", C.c_double * 4)]
 
 
 class MlpCfg(C.Structure):
@@ -58,6 +58,7 @@ _SIGS = {
                              _u64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tg_noise_fill": (C.c_int, [_vp, _u64, _i64, _i64, _i32, _i32, _vp, _vp]),
     "tg_env_step": (C.c_int, [_vp, C.POINTER(EnvCfg), _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tg_env_dynamics": (C.c_int, [_vp, C.POINTER(EnvCfg), _i32, _i64, _vp, _vp, _vp, _vp]),
     "tg_quadrotor12_dynamics": (C.c_int, [_vp, _i32, _i64, _d, _vp, _vp, _vp, _vp]),
     "tg_policy_forward": (C.c_int, [_vp, C.POINTER(MlpCfg), _i64, _vp, _vp, C.POINTER(_f), _vp, _vp, _vp, _vp]),
     "tg_policy_forward_traj": (C.c_int, [_vp, C.POINTER(MlpCfg), _i64, _i32, _vp, _vp, _vp, _vp, C.POINTER(_f), _vp,
@@ -180,9 +181,13 @@ def balanced_limit_count(dt: float, limit: float = 5.0) -> int:
             raise EngineError("timestep too small for the balanced-time threshold")
 
 
-def env_cfg(kind: int, max_steps: int, dt: float) -> EnvCfg:
+def env_cfg(kind: int, max_steps: int, dt: float, phys=None) -> EnvCfg:
+    """`phys`: the env's physical constructor arguments (CartPole: masscart, masspole, length, gravity;
+    Pendulum: mass, length, gravity); None = the reference's defaults."""
     cfg = EnvCfg()
     cfg.kind, cfg.max_steps, cfg.dt = int(kind), int(max_steps), float(dt)
+    for i, v in enumerate(phys or ()):
+        cfg.phys[i] = float(v)
     cfg.time_limit_step = time_limit_step(float(dt), int(max_steps)) if kind in (ENV_CARTPOLE, ENV_PENDULUM) else 0
     cfg.balanced_limit = balanced_limit_count(float(dt)) if kind == ENV_PENDULUM else 0
     return cfg

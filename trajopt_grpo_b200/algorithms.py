@@ -53,37 +53,49 @@ class _FlatOptimizer:
     torch.optim.Adam with default flags (what every reference pipeline builds,
     pipelines/cartpole_pipeline_grpo.py:65) runs as ONE tg_adam_step launch whose
     moment buffers are aliased into `optimizer.state`, so `optimizer.state_dict()`
-    checkpoints (grpo.py:150-160, ppo.py:207-225) keep working.  Any other
-    optimizer gets `p.grad` views of the flat gradient and its own `step()`.
+    checkpoints (grpo.py:150-160, ppo.py:207-225) keep working and
+    `optimizer.load_state_dict()` (a resumed run) is picked up: state tensors that are
+    not our aliases were put there by torch, so their moments are copied in and their
+    step count is taken verbatim.  Any other optimizer gets `p.grad` views of the flat
+    gradient and its own `step()`.
     """
 
     def __init__(self, optimizer, policy):
         self.opt, self.policy = optimizer, policy
         self.m = self.v = None
         self.step_count = 0
-
-    def _params_match_flat(self, flat):
-        groups = self.opt.param_groups
-        if len(groups) != 1:
-            return False
-        off, base = 0, flat.data_ptr()
-        for p in groups[0]["params"]:
-            if p.data_ptr() != base + 4 * off:
-                return False
-            off += p.numel()
-        return off == flat.numel()
+        self._steps = {}          # id(param) -> its own CPU step tensor (torch's Adam keeps one per parameter)
+        self._ok_key = None
+        self._ok = False
 
     def _fused_adam_ok(self, flat):
-        if type(self.opt) is not torch.optim.Adam or not self._params_match_flat(flat):
-            return False
-        g = self.opt.param_groups[0]
-        return not g.get("amsgrad", False) and not g.get("maximize", False) and g.get("weight_decay", 0) == 0 \
+        groups = self.opt.param_groups
+        g = groups[0] if groups else {}
+        key = (type(self.opt), len(groups), id(g.get("params")), len(g.get("params", ())), flat.data_ptr(),
+               flat.numel(), g.get("amsgrad"), g.get("maximize"), g.get("weight_decay"), g.get("capturable"),
+               g.get("differentiable"))
+        if key == self._ok_key:
+            return self._ok
+        ok = type(self.opt) is torch.optim.Adam and len(groups) == 1
+        if ok:
+            off, base = 0, flat.data_ptr()
+            for p in g["params"]:                                     # parameters alias the flat vector, in order
+                if p.data_ptr() != base + 4 * off:
+                    ok = False
+                    break
+                off += p.numel()
+            ok = ok and off == flat.numel()
+        ok = ok and not g.get("amsgrad", False) and not g.get("maximize", False) and g.get("weight_decay", 0) == 0 \
             and not g.get("capturable", False) and not g.get("differentiable", False)
+        self._ok_key, self._ok = key, ok
+        return ok
 
     def _sync_adam_state(self, flat):
         if self.m is None or self.m.numel() != flat.numel() or self.m.device != flat.device:
             self.m, self.v = torch.zeros_like(flat), torch.zeros_like(flat)
+            self._steps = {}
         off = 0
+        loaded_step = None
         for p in self.opt.param_groups[0]["params"]:
             n = p.numel()
             st = self.opt.state[p]
@@ -93,9 +105,18 @@ class _FlatOptimizer:
                 if cur is not None and cur.data_ptr() != view.data_ptr():
                     view.copy_(cur.to(view.device, torch.float32))      # state came from load_state_dict()
                 st[key] = view
-            if "step" in st:
-                self.step_count = max(self.step_count, int(float(st["step"])))
+            mine = self._steps.get(id(p))
+            cur = st.get("step")
+            if cur is not None and cur is not mine:                     # replaced by load_state_dict(): verbatim
+                loaded_step = int(float(cur))
+            if mine is None:
+                mine = self._steps[id(p)] = torch.tensor(float(self.step_count))
+            st["step"] = mine
             off += n
+        if loaded_step is not None:
+            self.step_count = loaded_step
+            for t in self._steps.values():
+                t.fill_(float(loaded_step))
 
     def step(self, flat, grad):
         if self._fused_adam_ok(flat):
@@ -104,9 +125,8 @@ class _FlatOptimizer:
             self.step_count += 1
             engine.adam_step(flat, grad, self.m, self.v, self.step_count, g["lr"], g["betas"][0], g["betas"][1],
                              g["eps"])
-            stamp = torch.tensor(float(self.step_count))
-            for p in g["params"]:
-                self.opt.state[p]["step"] = stamp
+            for t in self._steps.values():
+                t.fill_(float(self.step_count))
             return
         off = 0
         params = [p for grp in self.opt.param_groups for p in grp["params"]]
@@ -152,7 +172,8 @@ class GRPO(Algorithm):
             # grpo.py:129-132 cannot run in the reference either; no oracle for a KL term
             raise L.EngineError("ref_model is not supported: the reference's KL branch is broken (every config passes None)")
         self.old_policy = copy.deepcopy(self.policy)                 # grpo.py:48
-        self._synced_tag = policy.param_tag()                        # old_policy == policy at this tag
+        self._synced_tag = policy.param_tag()                        # old_policy == policy at this tag ...
+        self._old_tag = self.old_policy.param_tag()                  # ... while old_policy itself is untouched
         self._flat_opt = _FlatOptimizer(optimizer, policy)
         self.last_stats = None
 
@@ -169,7 +190,8 @@ class GRPO(Algorithm):
         # grpo.py:118-119: log-prob under the frozen old policy.  The rollout kernel already
         # evaluated it when the rollout was produced by weights identical to old_policy.
         cur_tag = pol.param_tag()
-        if r.logp is not None and r.policy_tag == cur_tag and self._synced_tag == cur_tag:
+        if r.logp is not None and r.policy_tag == cur_tag and self._synced_tag == cur_tag \
+                and self.old_policy.param_tag() == self._old_tag:
             old_logp = r.logp
         else:
             _, old_logp = engine.policy_forward_traj(dims, act_name, old_flat[:flat.numel()].contiguous(), r.obs, cov,
@@ -186,12 +208,14 @@ class GRPO(Algorithm):
             self.last_stats = stats
         self.old_policy.load_state_dict(self.policy.state_dict())   # grpo.py:148
         self._synced_tag = pol.param_tag()
+        self._old_tag = self.old_policy.param_tag()
 
     def save(self, path: str) -> None:
         torch.save(self.optimizer.state_dict(), os.path.join(path, "optimizer.pth"))
 
     def load(self, path: str) -> None:
-        self.optimizer.load_state_dict(torch.load(os.path.join(path, "optimizer.pth")))
+        """grpo.py:156-160."""
+        self.optimizer.load_state_dict(torch.load(os.path.join(path, "optimizer.pth"), weights_only=True))
 
     def metadata(self):
         return {"algorithm": "GRPO", "epsilon": self.epsilon, "beta": self.beta,
@@ -294,4 +318,6 @@ class PPO(Algorithm):
         torch.save(self.optimizer.state_dict(), os.path.join(path, "optimizer.pt"))
 
     def load(self, path: str) -> None:
+        """ppo.py:217-225."""
         self.optimizer.load_state_dict(torch.load(os.path.join(path, "optimizer.pt"), weights_only=True))
+        self.old_policy.load_state_dict(self.policy.state_dict())

@@ -17,6 +17,15 @@ from . import _lib as L
 from .rollout import DeviceRollout
 
 
+def _global_mean(x: torch.Tensor) -> float:
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        s = torch.stack([x.sum(dtype=torch.float64), torch.tensor(float(x.numel()), dtype=torch.float64, device=x.device)])
+        dist.all_reduce(s)
+        return float((s[0] / s[1]).item())
+    return float(x.mean().item())
+
+
 class Buffer:
     """buffers/buffer.py:3-8."""
 
@@ -57,17 +66,20 @@ class Rollout_Buffer(Buffer):
         self.avg_reward = np.atleast_1d(np.loadtxt(os.path.join(path, "reward.csv"), delimiter=",")).tolist()
         return len(self.avg_reward)
 
-    def sample(self):
-        """rollout_buffer.py:45-53 through the fused kernel."""
-        r = self.rollout_manager.rollout_device()
+    def sample(self, init_state=None, noise=None):
+        """rollout_buffer.py:45-53 through the fused kernel.  `init_state` ([S, local envs] CUDA tensor) and
+        `noise` ([T, A, local envs]) are optional injection hooks (tests, benchmarks with host-provided
+        initial states); by default the manager draws the reset distribution and the Philox stream."""
+        r = self.rollout_manager.rollout_device(init_state=init_state, noise=noise)
         self.device_rollout = r
         self.group_observations = r.group_observations()
         self.group_actions = r.group_actions()
         self.group_rewards = r.group_rewards()
         self.group_lengths = r.group_lengths()
         self._group_masks = None
-        # rollout_buffer.py:70: rewards.sum(2).mean() == mean episodic return (one scalar D2H)
-        self.avg_reward.append(np.float32(r.ret.mean().item()))
+        # rollout_buffer.py:70: rewards.sum(2).mean() == mean episodic return (one scalar D2H); over ALL ranks'
+        # groups when the rollout is sharded, so every rank logs (and rank 0 saves) the same history
+        self.avg_reward.append(np.float32(_global_mean(r.ret)))
 
     def store(self, group_observations, group_actions, group_rewards, group_lengths, group_masks):
         """rollout_buffer.py:55-70 for externally produced [G,E,T,.] tensors: they are

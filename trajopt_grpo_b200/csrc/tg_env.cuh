@@ -6,8 +6,9 @@
 //
 // Each Env<KIND> provides
 //   S, A                     state/obs and action dims
-//   step(s, raw_a, p, steps_done, bal, reward) -> done
-// where `s` is advanced in place, `bal` is the Pendulum balanced-step counter.
+//   step<R, WRAPPED>(s, a, p, steps_done, bal, reward) -> done
+// where `s` is advanced in place, `bal` is the Pendulum balanced-step counter; WRAPPED = the action is
+// already the wrapped control (Env._dynamics' argument) instead of the raw policy sample.
 #pragma once
 #include "tg_common.cuh"
 
@@ -16,6 +17,11 @@ struct EnvParams {
     int max_steps;
     int time_limit_step;
     int balanced_limit;
+    // derived from the physical constructor arguments on the host, in Python-float (double) arithmetic and the
+    // reference's operation order:
+    //   CartPole: k[0] = masscart + masspole, k[1] = masspole * length, k[2] = length, k[3] = gravity, k[4] = masspole
+    //   Pendulum: k[0] = 1 / (mass * length**2), k[1] = mass * gravity * length
+    double k[5];
 };
 
 template <typename R> struct Mth;
@@ -48,18 +54,18 @@ template <int KIND> struct Env;
 // ---------------------------------------------------------------------------
 template <> struct Env<TG_ENV_CARTPOLE> {
     static constexpr int S = 5, A = 1;
-    template <typename R>
+    template <typename R, bool WRAPPED = false>
     static TG_D bool step(R *s, const float *a, const EnvParams &p, int steps_done, int &bal, R &reward) {
-        const float u32 = 5.0f * clip1(a[0]);                    // :48-49, float32
+        const float u32 = WRAPPED ? a[0] : 5.0f * clip1(a[0]);   // :48-49, float32
         R x = s[0], xd = s[1], sn = s[2], cs = s[3], thd = s[4];
         thd = clipr<R>(thd, (R)-10, (R)10);                      // :58
         const R u = (R)u32;
-        const R mc = 1, mp = 1, l = (R)0.5, g = (R)TG_G, dt = (R)p.dt;
+        const R M = (R)p.k[0], mpl = (R)p.k[1], l = (R)p.k[2], g = (R)p.k[3], mp = (R)p.k[4], dt = (R)p.dt;
         R theta = Mth<R>::atan2(sn, cs);                         // :68
         const R thd2 = thd * thd;
-        const R alpha = (g * sn + cs * ((-u - (mp * l) * thd2 * sn) / (mc + mp))) /
-                        (l * ((R)(4.0 / 3.0) - (mp * (cs * cs)) / (mc + mp)));   // :71-73
-        const R acc = (u + (mp * l) * (thd2 * sn - alpha * cs)) / (mc + mp);    // :76
+        const R alpha = (g * sn + cs * ((-u - mpl * thd2 * sn) / M)) /
+                        (l * ((R)(4.0 / 3.0) - (mp * (cs * cs)) / M));   // :71-73
+        const R acc = (u + mpl * (thd2 * sn - alpha * cs)) / M;  // :76
         xd = xd + acc * dt;                                      // :79
         x = x + xd * dt;                                         // :80
         thd = thd + alpha * dt;                                  // :82
@@ -86,16 +92,16 @@ template <> struct Env<TG_ENV_CARTPOLE> {
 // ---------------------------------------------------------------------------
 template <> struct Env<TG_ENV_PENDULUM> {
     static constexpr int S = 3, A = 1;
-    template <typename R>
+    template <typename R, bool WRAPPED = false>
     static TG_D bool step(R *s, const float *a, const EnvParams &p, int steps_done, int &bal, R &reward) {
-        const float u32 = clip1(a[0]);                           // :45-46
+        const float u32 = WRAPPED ? a[0] : clip1(a[0]);          // :45-46
         R sn = s[0], cs = s[1], thd = s[2];
         const R dt = (R)p.dt;
         thd = clipr<R>(thd, (R)-10, (R)10);                      // :57
         R theta = Mth<R>::atan2(sn, cs);                         // :59
         R s0, c0;
         Mth<R>::sincos(theta, &s0, &c0);                         // np.sin(theta) (:61)
-        const R alpha = (R)(1.0 / (1.0 * 0.5 * 0.5)) * ((R)u32 - (R)(1.0 * TG_G * 0.5) * s0);
+        const R alpha = (R)p.k[0] * ((R)u32 - (R)p.k[1] * s0);   // :61
         thd = thd + alpha * dt;                                  // :63
         theta = theta + thd * dt;                                // :64
         Mth<R>::sincos(theta, &sn, &cs);
@@ -114,11 +120,11 @@ template <> struct Env<TG_ENV_PENDULUM> {
 // ---------------------------------------------------------------------------
 template <> struct Env<TG_ENV_QUADPOLE2D> {
     static constexpr int S = 10, A = 2;
-    template <typename R>
+    template <typename R, bool WRAPPED = false>
     static TG_D bool step(R *s, const float *a, const EnvParams &p, int steps_done, int &bal, R &reward) {
         const float hov = (float)((1.5 + 0.5) * TG_G / 2);       // :895
-        const float u1 = wrap_hover(hov, a[0]);                  // :928 (float32 mul then add, unfused)
-        const float u2 = wrap_hover(hov, a[1]);
+        const float u1 = WRAPPED ? a[0] : wrap_hover(hov, a[0]);   // :928 (float32 mul then add, unfused)
+        const float u2 = WRAPPED ? a[1] : wrap_hover(hov, a[1]);
         R x = s[0], z = s[1], vx = s[2], vz = s[3], sth = s[4], cth = s[5], thd = s[6];
         R sph = s[7], cph = s[8], phd = s[9];
         const R mq = (R)1.5, mp = (R)0.5, Lp = (R)0.75, g = (R)TG_G, dt = (R)p.dt;
@@ -171,11 +177,11 @@ template <typename R> TG_D Q4<R> qmul(const Q4<R> &q, const Q4<R> &r) {   // :19
 
 template <> struct Env<TG_ENV_QUADPOLE> {
     static constexpr int S = 20, A = 4;
-    template <typename R>
+    template <typename R, bool WRAPPED = false>
     static TG_D bool step(R *s, const float *a, const EnvParams &p, int steps_done, int &bal, R &reward) {
         const float hov = (float)((1.5 + 0.5) * TG_G / 4);       // :376
-        const float u1 = wrap_hover(hov, a[0]), u2 = wrap_hover(hov, a[1]);   // :409-413
-        const float u3 = wrap_hover(hov, a[2]), u4 = wrap_hover(hov, a[3]);
+        const float u1 = WRAPPED ? a[0] : wrap_hover(hov, a[0]), u2 = WRAPPED ? a[1] : wrap_hover(hov, a[1]);   // :409-413
+        const float u3 = WRAPPED ? a[2] : wrap_hover(hov, a[2]), u4 = WRAPPED ? a[3] : wrap_hover(hov, a[3]);
         const R ut = (R)(((u1 + u2) + u3) + u4);                 // :442 float32 adds
         const R m0 = (R)1.5, mp = (R)0.5, L = (R)0.5, arm = (R)0.5;
         const R Ixx = (R)0.4, Iyy = (R)0.4, Izz = (R)0.25, g = (R)TG_G, dt = (R)p.dt;

@@ -627,7 +627,7 @@ static int launch_rollout_tc(int precision, const RolloutTcArgs &a, cudaStream_t
     return TG_OK;
 }
 
-static int fill_env_params(const tg_env_cfg *env, EnvParams *p) {
+int tg_fill_env_params(const tg_env_cfg *env, EnvParams *p) {
     TG_REQUIRE(env != nullptr, TG_ERR_ARG, "env cfg is null");
     TG_REQUIRE(env->kind >= 0 && env->kind <= 3, TG_ERR_ARG, "unknown env kind %d", env->kind);
     TG_REQUIRE(env->max_steps > 0 && env->dt > 0, TG_ERR_SHAPE, "max_steps and dt must be positive");
@@ -635,8 +635,23 @@ static int fill_env_params(const tg_env_cfg *env, EnvParams *p) {
     p->max_steps = env->max_steps;
     p->time_limit_step = env->time_limit_step;
     p->balanced_limit = env->balanced_limit;
+    for (int i = 0; i < 5; ++i) p->k[i] = 0.0;
+    const bool dflt = env->phys[0] == 0.0 && env->phys[1] == 0.0 && env->phys[2] == 0.0 && env->phys[3] == 0.0;
+    if (env->kind == TG_ENV_CARTPOLE) {                 // cartpole_env.py:7-16
+        const double mc = dflt ? 1.0 : env->phys[0], mp = dflt ? 1.0 : env->phys[1], l = dflt ? 0.5 : env->phys[2];
+        const double g = dflt ? TG_G : env->phys[3];
+        TG_REQUIRE(mc + mp > 0 && l > 0, TG_ERR_ARG, "CartPole masses and length must be positive");
+        p->k[0] = mc + mp; p->k[1] = mp * l; p->k[2] = l; p->k[3] = g; p->k[4] = mp;
+    } else if (env->kind == TG_ENV_PENDULUM) {          // pendulum_env.py:8-17
+        const double m = dflt ? 1.0 : env->phys[0], l = dflt ? 0.5 : env->phys[1], g = dflt ? TG_G : env->phys[2];
+        TG_REQUIRE(m > 0 && l > 0, TG_ERR_ARG, "Pendulum mass and length must be positive");
+        p->k[0] = 1.0 / (m * (l * l)); p->k[1] = m * g * l;
+    } else {
+        TG_REQUIRE(dflt, TG_ERR_UNSUPPORTED, "the quadrotor envs take no physical constructor arguments in the reference");
+    }
     return TG_OK;
 }
+static int fill_env_params(const tg_env_cfg *env, EnvParams *p) { return tg_fill_env_params(env, p); }
 
 extern "C" int tg_rollout(tg_ctx *ctx, const tg_env_cfg *env, const tg_mlp_cfg *mlp, int precision, int64_t N,
                           const void *init_state, const float *params, const float *cov_diag, const float *noise,

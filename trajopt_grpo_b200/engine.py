@@ -67,7 +67,7 @@ def _workspace(key, nbytes: int, device) -> torch.Tensor:
 
 
 def rollout(kind, max_steps, dt, dims, activation, params, cov_diag, init_state, noise=None, seed=0,
-            want_logp=True, out=None, env_offset=0):
+            want_logp=True, out=None, env_offset=0, phys=None):
     """tg_rollout.  init_state [S,N] float32 (throughput) or float64 (parity).
     Returns dict(obs [T,O,N], act [T,A,N], rew [T,N], logp [T,N], len [N] i32, ret [N])."""
     lib = L.load()
@@ -92,7 +92,7 @@ def rollout(kind, max_steps, dt, dims, activation, params, cov_diag, init_state,
             "len": torch.empty((N,), dtype=torch.int32, device=dev),
             "ret": torch.empty((N,), dtype=torch.float32, device=dev),
         }
-    ecfg = L.env_cfg(kind, T, dt)
+    ecfg = L.env_cfg(kind, T, dt, phys)
     mcfg = L.mlp_cfg(dims, activation)
     prec = L.PREC_F64 if init_state.dtype == torch.float64 else L.PREC_F32
     with torch.cuda.device(dev):
@@ -118,7 +118,7 @@ def noise_fill(seed, N, T, A, device=None, env_offset=0):
     return out
 
 
-def env_step(kind, max_steps, dt, state, raw_action, steps_done=None, bal_count=None):
+def env_step(kind, max_steps, dt, state, raw_action, steps_done=None, bal_count=None, phys=None):
     """tg_env_step.  state [S,N] f32|f64, raw_action [A,N] f32 -> (next, reward, done i32, bal i32)."""
     lib = L.load()
     O, A = OBS_DIM[kind], ACT_DIM[kind]
@@ -134,7 +134,7 @@ def env_step(kind, max_steps, dt, state, raw_action, steps_done=None, bal_count=
     rew = torch.empty((N,), dtype=state.dtype, device=dev)
     done = torch.empty((N,), dtype=torch.int32, device=dev)
     bal = torch.empty((N,), dtype=torch.int32, device=dev)
-    ecfg = L.env_cfg(kind, max_steps, dt)
+    ecfg = L.env_cfg(kind, max_steps, dt, phys)
     prec = L.PREC_F64 if state.dtype == torch.float64 else L.PREC_F32
     with torch.cuda.device(dev):
         rc = lib.tg_env_step(L.ctx(dev), C.byref(ecfg), prec, N, L.ptr(state), L.ptr(raw_action), L.ptr(steps_done),
@@ -142,6 +142,27 @@ def env_step(kind, max_steps, dt, state, raw_action, steps_done=None, bal_count=
     L.check(rc, "tg_env_step")
     _count(1)
     return nxt, rew, done, bal
+
+
+def env_dynamics(kind, dt, state, control, phys=None):
+    """tg_env_dynamics: Env._dynamics for N envs.  state [S,N] f32|f64, control [A,N] f32 (already wrapped)
+    -> next state [S,N]."""
+    lib = L.load()
+    O, A = OBS_DIM[kind], ACT_DIM[kind]
+    _need(state, state.dtype, "state")
+    if state.dtype not in (torch.float32, torch.float64) or state.shape[0] != O:
+        raise L.EngineError(f"state must be [S={O}, N] float32 or float64")
+    N = state.shape[1]
+    _need(control, torch.float32, "control", (A, N))
+    nxt = torch.empty_like(state)
+    ecfg = L.env_cfg(kind, 1, dt, phys)
+    prec = L.PREC_F64 if state.dtype == torch.float64 else L.PREC_F32
+    with torch.cuda.device(state.device):
+        rc = lib.tg_env_dynamics(L.ctx(state.device), C.byref(ecfg), prec, N, L.ptr(state), L.ptr(control), L.ptr(nxt),
+                                 L.stream_ptr())
+    L.check(rc, "tg_env_dynamics")
+    _count(1)
+    return nxt
 
 
 def quadrotor12_dynamics(state, control, dt=0.05):

@@ -44,6 +44,7 @@ class Env(abc.ABC):
     """environments/env.py:10-68 (gym.Env + `restart`)."""
 
     _tg_kind: int = -1
+    _tg_phys = None          # physical constructor arguments for the kernels (None = reference defaults)
     _state_keys: tuple = ()
     _state_split: tuple = ()
 
@@ -91,7 +92,8 @@ class Env(abc.ABC):
         a = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(-1, 1)).cuda()
         steps = torch.tensor([self._steps], dtype=torch.int32, device="cuda")
         bal = torch.tensor([self._bal_count], dtype=torch.int32, device="cuda")
-        nxt, rew, done, bal_out = engine.env_step(self._tg_kind, self.max_steps, self.timestep, s, a, steps, bal)
+        nxt, rew, done, bal_out = engine.env_step(self._tg_kind, self.max_steps, self.timestep, s, a, steps, bal,
+                                                  phys=self._tg_phys)
         return nxt.cpu().numpy()[:, 0], float(rew.item()), bool(done.item()), int(bal_out.item())
 
     def step(self, action):
@@ -108,7 +110,12 @@ class Env(abc.ABC):
         return False, done            # the quadrotor envs and CartPole only ever truncate
 
     def _dynamics(self, state, control):
-        raise NotImplementedError("dynamics run inside the fused kernels; use step() or engine.env_step")
+        """Env._dynamics(state, control) (cartpole_env.py:51-92, pendulum_env.py:48-75, quadrotor_env.py:417-528,
+        1044-1130): one transition from `state` under the ALREADY WRAPPED `control` (float32, as step() passes
+        it), through tg_env_dynamics in float64."""
+        s = torch.from_numpy(np.asarray(state, np.float64).reshape(-1, 1).copy()).cuda()
+        u = torch.from_numpy(np.asarray(control, np.float32).reshape(-1, 1).copy()).cuda()
+        return engine.env_dynamics(self._tg_kind, self.timestep, s, u, phys=self._tg_phys).cpu().numpy()[:, 0]
 
     def render(self, *a, **k):
         raise NotImplementedError("rendering is outside the hot path (SURVEY.md section 2)")
@@ -132,9 +139,8 @@ class CartPole(Env):
     def __init__(self, env_name: str = "CartPole", masscart: float = 1.0, masspole: float = 1.0, length: float = 0.5,
                  gravity: float = 9.80665, timestep: float = 0.02, max_steps: int = 500):
         super().__init__(env_name)
-        if (masscart, masspole, length, gravity) != (1.0, 1.0, 0.5, 9.80665):
-            raise L.EngineError("the CartPole kernel is specialised for the reference's default physical parameters")
         self.masscart, self.masspole, self.length, self.gravity = masscart, masspole, length, gravity
+        self._tg_phys = (masscart, masspole, length, gravity)
         self.timestep, self.max_steps = timestep, max_steps
         self.max_time = max_steps * timestep
         self._initial_state = None
@@ -162,9 +168,8 @@ class Pendulum(Env):
     def __init__(self, env_name: str = "Pendulum", swingup: bool = False, mass: float = 1.0, length: float = 0.5,
                  gravity: float = 9.80665, timestep: float = 0.05, max_steps: int = 200):
         super().__init__(env_name)
-        if (mass, length, gravity) != (1.0, 0.5, 9.80665):
-            raise L.EngineError("the Pendulum kernel is specialised for the reference's default physical parameters")
         self.swingup, self.mass, self.length, self.gravity = swingup, mass, length, gravity
+        self._tg_phys = (mass, length, gravity)
         self.timestep, self.max_steps = timestep, max_steps
         self.max_time = max_steps * timestep
         self._initial_state = None

@@ -150,11 +150,13 @@ class _GaussianBase(ActorCritic):
         return [float(c) for c in torch.diagonal(self.cov)]
 
     def param_tag(self):
-        """Identity of the current parameter VALUES without a device sync: torch's
-        version counter sees every torch-side in-place write (load_state_dict, copy_),
-        `_param_epoch` counts the raw-pointer writes of tg_adam_step."""
+        """Identity of the current parameter VALUES without a device sync.  The Parameters are re-homed
+        views of the flat buffer (`p.data = view`), so each has its OWN version counter: the sum of the
+        parameters' `_version` sees every torch-side in-place write (load_state_dict, copy_, add_, a torch
+        optimizer's step), `_param_epoch` counts the raw-pointer writes of tg_adam_step and every load /
+        re-bind.  Writes that bypass both (`p.data.add_()`) are invisible to torch itself."""
         flat = self.flat_parameters()
-        return (flat.data_ptr(), flat._version, getattr(self, "_param_epoch", 0))
+        return (flat.data_ptr(), sum(p._version for p in self.parameters()), getattr(self, "_param_epoch", 0))
 
     def bump_param_epoch(self):
         self._param_epoch = getattr(self, "_param_epoch", 0) + 1
@@ -232,6 +234,7 @@ class GaussianActor_NeuralNetwork(_GaussianBase):
 
     def load_state_dict(self, state_dict):
         self.actor.load_state_dict(state_dict)
+        self.bump_param_epoch()
 
     def flat_parameters(self) -> torch.Tensor:
         self.actor.flat_params()
@@ -243,7 +246,7 @@ class GaussianActor_NeuralNetwork(_GaussianBase):
     def load(self, path):
         """Missing in the reference (GRPO resume raises); added so
         checkpoints written by save() round-trip."""
-        self.actor.load_state_dict(torch.load(os.path.join(path, "policy.pt"), weights_only=True))
+        self.load_state_dict(torch.load(os.path.join(path, "policy.pt"), weights_only=True))
 
 
 class GaussianActorCritic_NeuralNetwork(_GaussianBase):
@@ -276,8 +279,10 @@ class GaussianActorCritic_NeuralNetwork(_GaussianBase):
     def load_state_dict(self, state_dict):
         self.actor.load_state_dict(state_dict["actor"])
         self.critic.load_state_dict(state_dict["critic"])
+        self.bump_param_epoch()
 
     def load(self, path):
+        """actor_critic.py:340-346."""
         sd = torch.load(os.path.join(path, "policy.pt"), weights_only=True)
         self.load_state_dict(sd)
 

@@ -97,7 +97,8 @@ def _device_rollout(env, policy, G, E, restart, rng, seed, precision="f32", init
         host = torch.from_numpy(np.ascontiguousarray(s0.T)).to(dtype).pin_memory()
         init_state = host.to(dev, non_blocking=True)
     out = engine.rollout(kind, env.max_steps, env.timestep, policy.actor.dims, policy.actor.activation_name, flat,
-                         policy.cov_diag, init_state, noise=noise, seed=seed, env_offset=env_offset)
+                         policy.cov_diag, init_state, noise=noise, seed=seed, env_offset=env_offset,
+                         phys=getattr(env, "_tg_phys", None))
     tag = policy.param_tag() if hasattr(policy, "param_tag") else None
     return DeviceRollout(out["obs"], out["act"], out["rew"], out["logp"], out["len"], out["ret"], G, E,
                          int(env.max_steps), tag)
@@ -143,16 +144,33 @@ class RolloutManager:
         self.obs_dim = self.env.observation_space.shape[0]
         self.act_dim = self.env.action_space.shape[0]
         self.max_steps = self.env.max_steps
-        self.episodes_completed = [0 for _ in range(num_workers)]
+        self.episodes_completed = [0] * num_workers      # no workers to poll: stays zero (rollout_manager.py:52)
         self.precision = precision
         # multi-GPU: this rank owns a contiguous block of whole groups
         self.rank, self.world_size = rank, world_size
         self.local_workers, self.env_offset = plan_shard(num_workers, num_episodes_per_worker, rank, world_size)
-        self._seed = int(np.random.SeedSequence(seed).generate_state(1, np.uint64)[0]) if seed is not None \
-            else int(np.random.SeedSequence().generate_state(1, np.uint64)[0])
+        self._seed = self._resolve_seed(seed, world_size)
         self._rng = np.random.default_rng(self._seed)
         self._epoch = 0
         self.last: DeviceRollout | None = None
+
+    @staticmethod
+    def _resolve_seed(seed, world_size: int) -> int:
+        """One 64-bit seed for the initial-state generator and the Philox stream.  Sharded runs rely on every
+        rank drawing the SAME global initial states and noise stream (shard_initial_states), so with
+        seed=None rank 0's OS-entropy seed is broadcast; without a process group that cannot work."""
+        if seed is not None:
+            return int(np.random.SeedSequence(seed).generate_state(1, np.uint64)[0])
+        own = int(np.random.SeedSequence().generate_state(1, np.uint64)[0])
+        if world_size == 1:
+            return own
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise L.EngineError("RolloutManager(world_size > 1, seed=None) needs an initialised torch.distributed "
+                                "process group to share rank 0's seed; pass an explicit seed otherwise")
+        box = [own]
+        dist.broadcast_object_list(box, src=0)
+        return int(box[0])
 
     def print_progress(self):  # rollout_manager.py:63-83: nothing to poll, a rollout is one launch
         pass
@@ -165,13 +183,12 @@ class RolloutManager:
             blk = shard_initial_states(self.env, self.num_workers, E, self.restart, self._rng, self.rank,
                                        self.world_size)
             dtype = torch.float64 if self.precision == "f64" else torch.float32
-            init_state = torch.from_numpy(np.ascontiguousarray(blk.T)).to(dtype).pin_memory().cuda(non_blocking=True)
+            dev = self.policy.actor.flat_params().device                 # the policy's device, not the current one
+            init_state = torch.from_numpy(np.ascontiguousarray(blk.T)).to(dtype).pin_memory().to(dev, non_blocking=True)
         seed = (self._seed + 0x9E3779B97F4A7C15 * (self._epoch + 1)) & (2 ** 64 - 1)
         self._epoch += 1
         self.last = _device_rollout(self.env, self.policy, G, E, self.restart, self._rng, seed, self.precision,
                                     init_state=init_state, noise=noise, env_offset=self.env_offset)
-        for i in range(self.num_workers):
-            self.episodes_completed[i] = 0
         return self.last
 
     def rollout(self):
