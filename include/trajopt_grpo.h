@@ -275,6 +275,13 @@ int tg_policy_grad(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T,
                    float eps_clip, float scale, float kl_coef,
                    float *out_grad, float *out_stats, void *workspace, void *stream);
 
+/* HBM scratch traffic of one tg_policy_grad call beyond the algorithmic trajectory reads (host-side arithmetic,
+ * no device work): the streamed 128 / 256-wide tensor-core path hands H1, dZ2, dZ1 and [x, 1] from its
+ * forward/backward kernel to its weight-gradient kernel through an HBM scratch.  n_tiles = number of live
+ * 128-sample tiles (sum over steps of ceil(live envs / 128)).  Both outputs are 0 for the fused paths. */
+int tg_policy_grad_scratch_bytes(const tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t n_tiles,
+                                 int64_t *bytes_written, int64_t *bytes_read);
+
 /* Critic regression gradient (ppo.py:168-169: MSELoss(V(obs), rtg_norm)):
  *   target [T][N]; scale = c1 / n_valid  -> out_grad [n_params(critic)], out_stats[0] = sum sq err */
 int tg_value_grad(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T,

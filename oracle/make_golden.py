@@ -204,8 +204,66 @@ class Buf:
     pass
 
 
-def gen_rollout_and_learn(kind, hidden, cov, G, E, T, restart, seed, gamma, eps_clip, noise_scale=1.0,
-                          activation="ReLU", weights=None):
+KINK_MARGIN = 2e-6
+
+
+def kink_margin_over_updates(out, act_ids, lr=3e-4, updates=6):
+    """min ReLU-kink margin (restate.kink_margin) over the valid samples of a fixture, at its initial weights and
+    after each of the Adam updates the fixture records (replayed with the oracle)."""
+    import restate as R
+    Ws, bs, i = [], [], 0
+    while f"W{i}" in out:
+        Ws.append(out[f"W{i}"]); bs.append(out[f"b{i}"]); i += 1
+    cov = np.full(out["act"].shape[-1], out["cov"], np.float32)
+    x = out["obs"][out["mask"] > 0]
+    _, adv = R.grpo_advantage(out["rew"], out["mask"], float(out["gamma"]))
+    params = []
+    for w, b in zip(Ws, bs):
+        params += [w.copy(), b.copy()]
+    m, v = [np.zeros_like(p) for p in params], [np.zeros_like(p) for p in params]
+    old = [p.copy() for p in params]
+    margin0 = margin = R.kink_margin(x, params[0::2], params[1::2], act_ids)
+    if margin0 < KINK_MARGIN:
+        return margin0, margin0
+    for step in range(1, updates + 1):
+        _, dW, db, _, _ = R.grpo_objective_and_grad(out["obs"], out["act"], adv, out["mask"], params[0::2], params[1::2],
+                                                    old[0::2], old[1::2], cov, float(out["eps_clip"]), act=act_ids,
+                                                    dtype="float32")
+        grads = []
+        for a, b in zip(dW, db):
+            grads += [a, b]
+        params = R.adam_step(params, grads, m, v, step, lr)
+        if step % 3 == 0:
+            old = [p.copy() for p in params]
+        margin = min(margin, R.kink_margin(x, params[0::2], params[1::2], act_ids))
+    return margin0, margin
+
+
+def gen_rollout_and_learn(screen=True, **kw):
+    """_gen_rollout_and_learn with the numpy seed screened: a fixture whose samples come within KINK_MARGIN of a
+    ReLU kink is regenerated with seed + 1000 -- there the fp32 answer depends on the summation order
+    (tie-breaking), which is not what these fixtures pin.  Screened: the initial weights always (gradient tests);
+    the weights after each recorded Adam update too for widths <= 64 (at 128 / 256 the ~3 million pre-activations
+    of the six updates cannot all clear the margin; `kink_margin` is recorded and the Adam tests use the
+    kink-tolerant criterion when it is small)."""
+    import restate as R
+    act = kw.get("activation", "ReLU")
+    act_ids = R.acts_from_names(act if isinstance(act, str) else ",".join(act))
+    wide = max(kw["hidden"], default=0) > 64
+    for attempt in range(200):
+        out = _gen_rollout_and_learn(**kw)
+        m0, margin = kink_margin_over_updates(out, act_ids)
+        out["kink_margin0"], out["kink_margin"] = np.float64(m0), np.float64(margin)
+        if not screen or (m0 >= KINK_MARGIN and (wide or margin >= KINK_MARGIN)):
+            out["seed_used"] = np.int64(kw["seed"])
+            return out
+        print(f"    seed {kw['seed']}: kink margin {m0:.1e} / {margin:.1e} < {KINK_MARGIN:.0e}, trying seed {kw['seed'] + 1000}")
+        kw = dict(kw, seed=kw["seed"] + 1000)
+    raise RuntimeError("no seed with a clear kink margin")
+
+
+def _gen_rollout_and_learn(kind, hidden, cov, G, E, T, restart, seed, gamma, eps_clip, noise_scale=1.0,
+                           activation="ReLU", weights=None):
     rng = np.random.default_rng(seed)
     sys.path.insert(0, HERE)
     import restate
@@ -441,7 +499,8 @@ def fixtures():
         # (pipelines/cartpole_pipeline_grpo.py:54-76: 10 workers x 10 episodes x 500 steps, 5-128^4-1, cov 0.5,
         # eps 0.15, gamma 0.5, restart=False)
         "cartpole_cfg1": dict(kind=0, hidden=[128, 128, 128, 128], cov=0.5, G=10, E=10, T=500, restart=False, seed=21,
-                              gamma=0.5, eps_clip=0.15, weights=CP_GRPO),
+                              gamma=0.5, eps_clip=0.15, weights=CP_GRPO, screen=False),   # 4,370 samples x 512 units:
+        # not screenable; the margin is recorded and the GPU test falls back to kink-tolerant bounds when it is small
         # cfg 3 / cfg 4 policy shapes (tensor-core kernels) at small N
         "quadpole2d_w128": dict(kind=2, hidden=[128, 128], cov=0.5, G=3, E=4, T=60, restart=True, seed=22, gamma=0.99,
                                 eps_clip=0.2),

@@ -25,8 +25,25 @@ pytestmark = pytest.mark.gpu
 
 NEW_ROLLOUTS = ["cartpole_cfg1", "quadpole2d_w128", "quadpole_w256", "pendulum_h1", "cartpole_h3", "pendulum_h0",
                 "cartpole_tanh", "pendulum_mixed_act"]
-# max |g_kernel - g_float64| / max |g_float64| per widest hidden layer (measured on B200: see profiles/README_r2.md)
-GRAD_TOL_F64 = {0: 2e-5, 24: 2e-5, 32: 2e-5, 48: 2e-5, 64: 3e-5, 128: 5e-5, 256: 1e-4}
+# max |g_kernel - g_float64| / max |g_float64|: measured on B200 2.1e-7 .. 8.6e-7 for every width and both
+# arithmetic modes (gpurun_out/r2a_pytest_gpu.log, profiles/README_r2.md); bound with a 6x margin
+GRAD_TOL_F64 = 5e-6
+KINK = 2e-6        # oracle/make_golden.py KINK_MARGIN
+
+
+def _adam_close(got, ref, margin, lr, n_updates, what):
+    """Post-Adam weights vs the reference.  Strict (rtol 2e-4, atol 3e-6) when no sample of the fixture comes
+    within KINK of a ReLU kink along the update path.  Otherwise a unit whose pre-activation is within fp32
+    summation noise of 0 may legitimately switch sides, which perturbs the gradient by ~1e-3 of its max; Adam
+    normalises every element's step to ~lr, so elements whose gradient is smaller than that perturbation can move
+    the other way: all elements within 2*lr per update, and >= 90 % of them within the strict tolerance."""
+    if margin >= KINK:
+        np.testing.assert_allclose(got, ref, rtol=2e-4, atol=3e-6, err_msg=what)
+        return
+    d = np.abs(got - ref)
+    strict = d <= 3e-6 + 2e-4 * np.abs(ref)
+    assert strict.mean() >= 0.90, (what, float(strict.mean()))
+    assert d.max() <= 2.0 * lr * n_updates + 3e-6, (what, float(d.max()))
 
 
 def load(golden_dir, name):
@@ -138,6 +155,23 @@ def test_grpo_gradient_matches_reference_and_float64_oracle(E, golden_dir, name,
                                                  dtype="float64")
     ref64 = np.concatenate([np.concatenate([w.reshape(-1), b]) for w, b in zip(dW, db)])
     ref32 = np.concatenate([g[f"grpo_grad{i}"].reshape(-1) for i in range(2 * len(Ws))])
+    # kink variants (only fixtures that could not be screened, i.e. cfg 1 at full size): every ReLU decision within
+    # KINK of 0 may fall either way in fp32; the kernel must match ONE of the 2^k float64 gradients
+    act_ids = R.acts_from_names(g["activation"]) if "activation" in g else 0
+    variants = [ref64]
+    if float(g["kink_margin0"]) < KINK:
+        import itertools
+        nk = R.near_kinks(g["obs"][g["mask"] > 0], Ws, bs, act_ids, KINK)
+        assert 0 < len(nk) <= 8, len(nk)
+        for r_ in range(1, len(nk) + 1):
+            for combo in itertools.combinations(nk, r_):
+                fl = {}
+                for (layer, row, unit) in combo:
+                    fl.setdefault(layer, []).append((row, unit))
+                _, dWv, dbv, _, _ = R.grpo_objective_and_grad(g["obs"], g["act"], adv_ref, g["mask"], Ws, bs, Ws, bs,
+                                                               np.asarray(cov, np.float32), float(g["eps_clip"]),
+                                                               act=act_ids, dtype="float64", flips=fl)
+                variants.append(np.concatenate([np.concatenate([w.reshape(-1), b]) for w, b in zip(dWv, dbv)]))
     width = max(dims[1:-1], default=0)
     for mode in _modes(dims):
         try:
@@ -151,18 +185,19 @@ def test_grpo_gradient_matches_reference_and_float64_oracle(E, golden_dir, name,
             E.set_math("auto")
         got = grad.cpu().numpy()
         assert int(stats[1].item()) == int(g["mask"].sum()), mode
-        # vs the unmodified reference (fp32 torch autograd through SGD(lr=1)), layer by layer
-        off = 0
-        for i in range(2 * len(Ws)):
-            r = g[f"grpo_grad{i}"]
-            part = got[off:off + r.size].reshape(r.shape)
-            off += r.size
-            assert np.abs(part - r).max() <= 3e-4 * max(np.abs(r).max(), 1e-6) + 1e-5, (mode, i)
-        e64 = float(np.abs(got - ref64).max() / np.abs(ref64).max())
+        e64 = float(min(np.abs(got - v).max() for v in variants) / np.abs(ref64).max())
         e32 = float(np.abs(got - ref32).max() / np.abs(ref32).max())
+        if len(variants) == 1 or e64 == float(np.abs(got - ref64).max() / np.abs(ref64).max()):
+            # vs the unmodified reference (fp32 torch autograd through SGD(lr=1)), layer by layer
+            off = 0
+            for i in range(2 * len(Ws)):
+                r = g[f"grpo_grad{i}"]
+                part = got[off:off + r.size].reshape(r.shape)
+                off += r.size
+                assert np.abs(part - r).max() <= 3e-4 * max(np.abs(r).max(), 1e-6) + 1e-5, (mode, i)
         record_property(f"grad_err_vs_f64_{mode}", e64)
         print(f"[grad-parity] {name:22s} width {width:3d} {mode:7s} vs float64 oracle {e64:.2e}  vs reference fp32 {e32:.2e}")
-        assert e64 <= GRAD_TOL_F64[width], (mode, e64)
+        assert e64 <= GRAD_TOL_F64, (mode, e64)
 
 
 @pytest.mark.parametrize("name", NEW_ROLLOUTS)
@@ -192,8 +227,8 @@ def test_grpo_adam_updates_match_reference(E, golden_dir, name):
                 off = 0
                 for i in range(2 * len(Ws)):
                     ref = g[f"{key}{i}"]
-                    np.testing.assert_allclose(got[off:off + ref.size].reshape(ref.shape), ref, rtol=2e-4, atol=3e-6,
-                                               err_msg=f"{mode} {key}{i}")
+                    _adam_close(got[off:off + ref.size].reshape(ref.shape), ref, float(g["kink_margin"]), 3e-4, step,
+                                f"{mode} {key}{i}")
                     off += ref.size
         finally:
             E.set_math("auto")
@@ -231,10 +266,10 @@ def test_grpo_learn_host_api_matches_reference(golden_dir, name):
     _load_actor(pol.actor, Ws, bs)
     opt = torch.optim.Adam(pol.parameters(), lr=3e-4)
     algo = tg.GRPO(float(g["eps_clip"]), 0.0, float(g["gamma"]), pol, opt, None, updates_per_iter=3)
-    for key in ("grpo_adam3_p", "grpo_adam6_p"):
+    for n_upd, key in ((3, "grpo_adam3_p"), (6, "grpo_adam6_p")):
         algo.learn(buf)
         for i, p in enumerate(pol.parameters()):
-            np.testing.assert_allclose(p.detach().cpu().numpy(), g[f"{key}{i}"], rtol=2e-4, atol=3e-6)
+            _adam_close(p.detach().cpu().numpy(), g[f"{key}{i}"], float(g["kink_margin"]), 3e-4, n_upd, f"{key}{i}")
 
 
 PPO_NEW = ["ppo_mc_ragged_quadpole2d", "ppo_gae_ragged_quadpole2d", "ppo_mc_quadpole2d_shipped",

@@ -484,3 +484,42 @@ def test_ppo_minibatched_learn_matches_reference(tg, golden_dir):
     assert algo._flat_opt.step_count == n_steps                   # one optimizer step per minibatch
     for i, p in enumerate(pol.parameters()):
         np.testing.assert_allclose(p.detach().cpu().numpy(), g[f"ppo_mb_adam_p{i}"], rtol=1e-3, atol=2e-5)
+
+
+@pytest.mark.parametrize("updates", [1, 3])
+def test_streamed_epoch_equals_sample_plus_learn(tg, updates):
+    """GRPO.learn_streamed (BASELINE configs[4]: more envs per GPU than trajectories fit in HBM) keeps only the
+    initial states and the Philox seed and rematerialises the rollout chunk by chunk (whole groups) in every
+    update; it must train the same weights as sample() + learn() on the same seed.  The only difference is the
+    fp32 order in which the per-chunk gradients are summed."""
+    def build():
+        torch.manual_seed(5)
+        pol = tg.GaussianActor_NeuralNetwork(20, 4, [256, 256], "ReLU", 0.3)
+        opt = torch.optim.Adam(pol.parameters(), lr=3e-4)
+        algo = tg.GRPO(0.2, 0.01, 0.999, pol, opt, None, updates_per_iter=updates)
+        mgr = tg.RolloutManager(lambda: tg.QuadPole(max_steps=60), pol, restart=True, num_workers=12,
+                                num_episodes_per_worker=16, use_multiprocessing=False, seed=11)
+        return pol, algo, mgr
+
+    rng = np.random.default_rng(2)
+    env = tg.QuadPole(max_steps=60)
+    s0 = np.repeat(env.sample_initial_states(12, rng), 16, axis=0)
+    init = torch.from_numpy(np.ascontiguousarray(s0.T)).float().cuda()
+    pol_a, algo_a, mgr_a = build()
+    buf = tg.Rollout_Buffer(mgr_a)
+    buf.sample(init_state=init)
+    n_ref = int(buf.device_rollout.len.sum())
+    algo_a.learn(buf)
+    pol_b, algo_b, mgr_b = build()
+    n_valid = algo_b.learn_streamed(mgr_b, init_state=init, chunk_groups=5)      # chunks of 5, 5 and 2 groups
+    assert int(n_valid) == n_ref
+    assert abs(float(algo_b.last_mean_return) - float(buf.avg_reward[-1])) < 1e-3 * max(1.0, abs(float(buf.avg_reward[-1])))
+    a, b = pol_a.flat_parameters(), pol_b.flat_parameters()
+    # Adam's first steps move every element by ~lr; a summation-order difference of 1e-7 relative in the gradient
+    # cannot flip a step except for elements whose gradient is ~0: bound by 2 lr per update, 99.9 % within 1e-6
+    d = (a - b).abs()
+    assert float(d.max()) <= 2 * 3e-4 * updates + 1e-7
+    assert float((d <= 1e-6).float().mean()) >= 0.999
+    # second epoch through the streamed path continues from synchronised old-policy weights
+    algo_b.learn_streamed(mgr_b, init_state=init, chunk_groups=12)
+    assert bool(torch.isfinite(pol_b.flat_parameters()).all())

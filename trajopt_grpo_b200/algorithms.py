@@ -174,12 +174,14 @@ class GRPO(Algorithm):
         self.old_policy = copy.deepcopy(self.policy)                 # grpo.py:48
         self._synced_tag = policy.param_tag()                        # old_policy == policy at this tag ...
         self._old_tag = self.old_policy.param_tag()                  # ... while old_policy itself is untouched
+        self._seen_loads = getattr(policy, "checkpoint_loads", 0)
         self._flat_opt = _FlatOptimizer(optimizer, policy)
         self.last_stats = None
 
     def learn(self, buffer) -> None:
         r = _rollout_of(buffer)
         pol = self.policy
+        self._resync_after_checkpoint_load()
         flat = pol.flat_parameters()
         old_flat = self.old_policy.flat_parameters()
         dims, act_name, cov = pol.actor.dims, pol.actor.activation_name, pol.cov_diag
@@ -209,6 +211,89 @@ class GRPO(Algorithm):
         self.old_policy.load_state_dict(self.policy.state_dict())   # grpo.py:148
         self._synced_tag = pol.param_tag()
         self._old_tag = self.old_policy.param_tag()
+
+    def learn_streamed(self, manager, init_state=None, chunk_groups: int = 8192):
+        """One whole epoch -- rollout AND learn (pipelines/pipeline.py:163-164) -- for more envs than trajectories fit
+        in HBM (BASELINE configs[4]: up to 4M envs per GPU x 1000 steps x 104 B = 416 GB).
+
+        The reference stores every trajectory (rollout_worker.py:64-68) because its GRPO.learn revisits them in
+        every update (grpo.py:106-145).  Here only the initial states and the Philox seed are kept; the rollout is
+        REMATERIALISED chunk by chunk (whole GRPO groups, so the group statistics of grpo.py:108-115 stay exact):
+
+            for each update:  for each chunk of `chunk_groups` groups:
+                K1 rollout of the chunk under the FROZEN old policy (deterministic: same seed, same global env
+                   index -> the identical trajectories, log-probs included, in every update)
+                K2 advantages of the chunk         K3 gradient of the chunk under the current weights, accumulated
+            [gradient allreduce]  Adam
+
+        One trajectory buffer of chunk size is reused.  With updates_per_iter == 1 no work is repeated.
+        Equal to sample() + learn() on the same seed up to the fp32 summation order of the per-chunk gradients.
+        Returns the number of valid env-steps of this rank's rollout as a 0-dim CUDA tensor (no host sync)."""
+        from .rollout import shard_initial_states
+        import numpy as np
+        pol = self.policy
+        self._resync_after_checkpoint_load()
+        flat = pol.flat_parameters()
+        if self.old_policy.param_tag() != self._old_tag or self._synced_tag != pol.param_tag():
+            self.old_policy.load_state_dict(pol.state_dict())      # start of an epoch: old == current (grpo.py:148)
+        old_flat = self.old_policy.actor.flat_params()
+        dims, act_name, cov = pol.actor.dims, pol.actor.activation_name, pol.cov_diag
+        env, E = manager.env, manager.num_episodes_per_worker
+        G_loc = manager.local_workers
+        world = _dist_world()
+        dev = flat.device
+        if init_state is None:
+            blk = shard_initial_states(env, manager.num_workers, E, manager.restart, manager._rng, manager.rank,
+                                       manager.world_size)
+            init_state = torch.from_numpy(np.ascontiguousarray(blk.T)).to(torch.float32).pin_memory().to(dev, non_blocking=True)
+        seed = (manager._seed + 0x9E3779B97F4A7C15 * (manager._epoch + 1)) & (2 ** 64 - 1)
+        manager._epoch += 1
+        scale = (-1.0 if self.maximize else 1.0) / (G_loc * world)
+        n_valid = torch.zeros((), dtype=torch.int64, device=dev)
+        ret_sum = torch.zeros((), dtype=torch.float64, device=dev)
+        out = getattr(self, "_stream_out", None)
+        grad_total, grad_part = torch.empty_like(flat), torch.empty_like(flat)
+        for u in range(self.updates_per_iter):
+            grad_total.zero_()
+            for g0 in range(0, G_loc, chunk_groups):
+                g1 = min(G_loc, g0 + chunk_groups)
+                n0, n1 = g0 * E, g1 * E
+                s0 = init_state[:, n0:n1].contiguous()
+                out = engine.rollout(env._tg_kind, env.max_steps, env.timestep, dims, act_name, old_flat, cov, s0,
+                                     seed=seed, env_offset=manager.env_offset + n0, phys=getattr(env, "_tg_phys", None),
+                                     out=out)
+                adv, _ = engine.advantage(L.ADV_GRPO, g1 - g0, E, env.max_steps, self.gamma, 0.0, out["rew"], out["len"])
+                _, stats = engine.policy_grad(dims, act_name, flat, cov, out["obs"], out["act"], adv, out["logp"],
+                                              out["len"], self.epsilon, scale, out_grad=grad_part)
+                grad_total.add_(grad_part)
+                if u == 0:
+                    n_valid.add_(out["len"].sum())
+                    ret_sum.add_(out["ret"].sum(dtype=torch.float64))
+                self.last_stats = stats
+            if world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(grad_total)
+            self._flat_opt.step(flat, grad_total)
+            pol.bump_param_epoch()
+        self._stream_out = out
+        self.old_policy.load_state_dict(self.policy.state_dict())   # grpo.py:148
+        self._synced_tag = pol.param_tag()
+        self._old_tag = self.old_policy.param_tag()
+        self.last_mean_return = ret_sum / (G_loc * E)
+        return n_valid
+
+    def _resync_after_checkpoint_load(self):
+        """policy.load(path) (an engine extension: the reference's GaussianActor has no load(), so its GRPO runs
+        cannot resume at all) restores the weights a checkpoint holds -- the state right after a learn(), where
+        old_policy had just been synchronised (grpo.py:148).  The resumed run continues like the uninterrupted one
+        only if old_policy is restored with them.  Plain load_state_dict() calls keep the reference's semantics
+        (old_policy untouched)."""
+        loads = getattr(self.policy, "checkpoint_loads", 0)
+        if loads != self._seen_loads:
+            self._seen_loads = loads
+            self.old_policy.load_state_dict(self.policy.state_dict())
+            self._synced_tag = self.policy.param_tag()
+            self._old_tag = self.old_policy.param_tag()
 
     def save(self, path: str) -> None:
         torch.save(self.optimizer.state_dict(), os.path.join(path, "optimizer.pth"))

@@ -66,10 +66,12 @@ class Rollout_Buffer(Buffer):
         self.avg_reward = np.atleast_1d(np.loadtxt(os.path.join(path, "reward.csv"), delimiter=",")).tolist()
         return len(self.avg_reward)
 
-    def sample(self, init_state=None, noise=None):
+    def sample(self, init_state=None, noise=None, sync_metrics: bool = True):
         """rollout_buffer.py:45-53 through the fused kernel.  `init_state` ([S, local envs] CUDA tensor) and
         `noise` ([T, A, local envs]) are optional injection hooks (tests, benchmarks with host-provided
-        initial states); by default the manager draws the reset distribution and the Philox stream."""
+        initial states); by default the manager draws the reset distribution and the Philox stream.
+        sync_metrics=False keeps the epoch free of host synchronisation: the mean return is appended as a
+        0-dim CUDA tensor and converted when `avg_reward` is read through metadata() / save()."""
         r = self.rollout_manager.rollout_device(init_state=init_state, noise=noise)
         self.device_rollout = r
         self.group_observations = r.group_observations()
@@ -79,7 +81,7 @@ class Rollout_Buffer(Buffer):
         self._group_masks = None
         # rollout_buffer.py:70: rewards.sum(2).mean() == mean episodic return (one scalar D2H); over ALL ranks'
         # groups when the rollout is sharded, so every rank logs (and rank 0 saves) the same history
-        self.avg_reward.append(np.float32(_global_mean(r.ret)))
+        self.avg_reward.append(np.float32(_global_mean(r.ret)) if sync_metrics else r.ret.mean())
 
     def store(self, group_observations, group_actions, group_rewards, group_lengths, group_masks):
         """rollout_buffer.py:55-70 for externally produced [G,E,T,.] tensors: they are
@@ -140,11 +142,19 @@ class Rollout_Buffer(Buffer):
         return {"observations": obs.cpu().numpy(), "actions": act.cpu().numpy(), "rewards": rew.cpu().numpy(),
                 "lengths": ln.cpu().numpy().astype(int)}
 
+    def _resolve_rewards(self):
+        """deferred (sync_metrics=False) entries -> floats."""
+        for i, v in enumerate(self.avg_reward):
+            if isinstance(v, torch.Tensor):
+                self.avg_reward[i] = np.float32(v.item())
+
     def metadata(self):
+        self._resolve_rewards()
         return {"avg_reward": float(self.avg_reward[-1]) if len(self.avg_reward) > 0 else None}
 
     def save(self, path: str):
         """rollout_buffer.py:115-126."""
+        self._resolve_rewards()
         with open(os.path.join(path, "reward.csv"), "w") as f:
             for reward in self.avg_reward:
                 f.write(f"{reward}\n")

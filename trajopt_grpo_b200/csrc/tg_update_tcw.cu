@@ -71,6 +71,8 @@ struct TcwArgs {
     float *out_mu, *out_logp;
 };
 
+bool tg_update_tcw_shape_built(const tg_mlp_cfg *mlp);
+
 bool tg_update_tcw_eligible(const tg_mlp_cfg *mlp) {
     if (!mlp || mlp->n_layers != 3) return false;
     const int W = mlp->dims[1];
@@ -1029,6 +1031,22 @@ int tg_policy_grad_tcw(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, con
 #undef TCW_CASE
     tg_set_error("no wide tensor-core update kernel instance for obs %d / act %d", O, A);
     return TG_ERR_UNSUPPORTED;
+}
+
+extern "C" int tg_policy_grad_scratch_bytes(const tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t n_tiles,
+                                            int64_t *bytes_written, int64_t *bytes_read) {
+    TG_REQUIRE(ctx && mlp && bytes_written && bytes_read, TG_ERR_ARG, "tg_policy_grad_scratch_bytes: null argument");
+    *bytes_written = *bytes_read = 0;
+    if (!tg_update_tcw_shape_built(mlp) || ctx->math_mode == TG_MATH_FP32) return TG_OK;
+    TcwLayout L;
+    build_tcw_layout(mlp, &L);
+    const int64_t arr = (int64_t)16 * (L.W / 32) * 1024, xb = (int64_t)16 * L.OKP * 32;
+    *bytes_written = n_tiles * (3 * arr + 2 * xb);                       // kernel A: H1, dZ2, dZ1 (fp32) + [x,1] hi/lo
+    // kernel B, one launch per 128-row half of the outputs: its half of dZ2 and dZ1, all of H1, [x,1] hi/lo
+    const int64_t halves = L.W / 128;
+    *bytes_read = n_tiles * halves * (2 * (arr / halves) + arr + 2 * xb);
+    if (halves == 2) *bytes_read += n_tiles * arr;                       // kernel A: K-half-1 threads reload H1 / dZ2 halves
+    return TG_OK;
 }
 
 bool tg_update_tcw_shape_built(const tg_mlp_cfg *mlp) {

@@ -83,6 +83,8 @@ def rollout(kind, max_steps, dt, dims, activation, params, cov_diag, init_state,
     _need(params, torch.float32, "params")
     if noise is not None:
         _need(noise, torch.float32, "noise", (T, A, N))
+    if out is not None and (tuple(out["obs"].shape) != (T, O, N) or out["obs"].device != dev):
+        out = None
     if out is None:
         out = {
             "obs": torch.empty((T, O, N), dtype=torch.float32, device=dev),
@@ -307,6 +309,23 @@ def policy_grad(dims, activation, params, cov_diag, obs, act, adv, old_logp, len
     L.check(rc, "tg_policy_grad")
     _count(5)                                      # pack, order_keys, order_count, update, grad_reduce
     return grad, stats
+
+
+def policy_grad_traffic_bytes(dims, n_valid: int, length, activation="ReLU"):
+    """HBM bytes one tg_policy_grad launch moves for a rollout with episode lengths `length` [N] i32:
+    algorithmic trajectory reads (obs + act + adv + old log-prob of every valid step) plus the scratch the
+    streamed wide tensor-core path writes and reads back (tg_policy_grad_scratch_bytes)."""
+    lib = L.load()
+    T_max = int(length.max().item())
+    live = (length.view(1, -1) > torch.arange(T_max, device=length.device).view(-1, 1)).sum(1)      # envs alive per step
+    n_tiles = int(((live + 127) // 128).sum().item())
+    w, r = C.c_int64(), C.c_int64()
+    mcfg = L.mlp_cfg(dims, activation)
+    L.check(lib.tg_policy_grad_scratch_bytes(L.ctx(length.device), C.byref(mcfg), n_tiles, C.byref(w), C.byref(r)),
+            "tg_policy_grad_scratch_bytes")
+    alg = 4 * (dims[0] + dims[-1] + 2) * int(n_valid)
+    return {"algorithmic_read": alg, "scratch_written": int(w.value), "scratch_read": int(r.value),
+            "total": alg + int(w.value) + int(r.value), "live_tiles": n_tiles}
 
 
 def policy_grad_batch(dims, activation, params, cov_diag, obs, act, adv, old_logp, sample_ids, eps_clip, scale,

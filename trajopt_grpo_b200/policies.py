@@ -245,8 +245,11 @@ class GaussianActor_NeuralNetwork(_GaussianBase):
 
     def load(self, path):
         """Missing in the reference (GRPO resume raises); added so
-        checkpoints written by save() round-trip."""
+        checkpoints written by save() round-trip.  `checkpoint_loads` lets GRPO re-synchronise its
+        old_policy with the restored weights (a checkpoint is written right after a learn(), where
+        old_policy == policy, grpo.py:148)."""
         self.load_state_dict(torch.load(os.path.join(path, "policy.pt"), weights_only=True))
+        self.checkpoint_loads = getattr(self, "checkpoint_loads", 0) + 1
 
 
 class GaussianActorCritic_NeuralNetwork(_GaussianBase):

@@ -77,7 +77,7 @@ class RolloutWorker:
 
 
 def _device_rollout(env, policy, G, E, restart, rng, seed, precision="f32", init_state=None, noise=None,
-                    env_offset=0, device=None) -> DeviceRollout:
+                    env_offset=0, device=None, out=None) -> DeviceRollout:
     kind = getattr(env, "_tg_kind", -1)
     if kind < 0:
         raise L.EngineError(f"{type(env).__name__} has no fused kernel (supported: CartPole, Pendulum, "
@@ -98,7 +98,7 @@ def _device_rollout(env, policy, G, E, restart, rng, seed, precision="f32", init
         init_state = host.to(dev, non_blocking=True)
     out = engine.rollout(kind, env.max_steps, env.timestep, policy.actor.dims, policy.actor.activation_name, flat,
                          policy.cov_diag, init_state, noise=noise, seed=seed, env_offset=env_offset,
-                         phys=getattr(env, "_tg_phys", None))
+                         phys=getattr(env, "_tg_phys", None), out=out)
     tag = policy.param_tag() if hasattr(policy, "param_tag") else None
     return DeviceRollout(out["obs"], out["act"], out["rew"], out["logp"], out["len"], out["ret"], G, E,
                          int(env.max_steps), tag)
@@ -133,7 +133,7 @@ class RolloutManager:
 
     def __init__(self, env_fn: callable, policy, worker_class=RolloutWorker, restart=False, num_workers: int = 4,
                  num_episodes_per_worker: int = 5, use_multiprocessing: bool = True, *, seed: int = None,
-                 precision: str = "f32", rank: int = 0, world_size: int = 1):
+                 precision: str = "f32", rank: int = 0, world_size: int = 1, reuse_buffers: bool = False):
         self.env_fn, self.worker_class, self.policy = env_fn, worker_class, policy
         self.restart = restart
         self.num_workers = num_workers
@@ -153,6 +153,10 @@ class RolloutManager:
         self._rng = np.random.default_rng(self._seed)
         self._epoch = 0
         self.last: DeviceRollout | None = None
+        # reuse_buffers: every rollout overwrites ONE set of trajectory buffers instead of allocating a fresh
+        # one (a cfg-4 shard is 57 GB); tensors returned by an earlier rollout()/sample() then alias the new data
+        self.reuse_buffers = reuse_buffers
+        self._out = None
 
     @staticmethod
     def _resolve_seed(seed, world_size: int) -> int:
@@ -188,7 +192,11 @@ class RolloutManager:
         seed = (self._seed + 0x9E3779B97F4A7C15 * (self._epoch + 1)) & (2 ** 64 - 1)
         self._epoch += 1
         self.last = _device_rollout(self.env, self.policy, G, E, self.restart, self._rng, seed, self.precision,
-                                    init_state=init_state, noise=noise, env_offset=self.env_offset)
+                                    init_state=init_state, noise=noise, env_offset=self.env_offset,
+                                    out=self._out if self.reuse_buffers else None)
+        if self.reuse_buffers:
+            r = self.last
+            self._out = {"obs": r.obs, "act": r.act, "rew": r.rew, "logp": r.logp, "len": r.len, "ret": r.ret}
         return self.last
 
     def rollout(self):
