@@ -270,7 +270,13 @@ def measure(D, w, steps, warmup, full, args):
         algo = tg.PPO(w["eps"], policy, opt, None, w["updates"], c1=0.5, kl_coeff=0.5, gamma=w["gamma"], lam=0.95,
                       entropy=0.01, batch_size=None, monte_carlo=True)
     else:
-        algo = tg.GRPO(w["eps"], 0.01, w["gamma"], policy, opt, None, updates_per_iter=w["updates"])
+        # maximize=True: the reference's `J.backward(); optimizer.step()` DESCENDS on the surrogate (its own
+        # comment says ascent was meant).  Measured here (profiles/README_r2.md): descent destroys the stabilising start
+        # policy within 6 epochs (valid fraction 1.0 -> 0.06), so the work per epoch is not stationary.  The benchmark
+        # therefore ascends -- the same kernels, the gradient scaled by -1 on the host; the class default stays the
+        # reference's sign.
+        algo = tg.GRPO(w["eps"], 0.01, w["gamma"], policy, opt, None, updates_per_iter=w["updates"],
+                       maximize=w.get("start") == "lqr")
     env_cls = getattr(tg, w["cls"])
     mgr = tg.RolloutManager(lambda: env_cls(max_steps=T), policy, restart=w.get("restart", True), num_workers=G * world,
                             num_episodes_per_worker=E, use_multiprocessing=False, seed=7, rank=rank, world_size=world,
@@ -359,8 +365,6 @@ def measure(D, w, steps, warmup, full, args):
         return out, None, None
 
     # ---------------- per-kernel timing, each alone, CUDA events on its stream -------------
-    r = buf.device_rollout
-    adv, _ = engine.advantage(0, r.G, r.E, r.T, w["gamma"], 0.0, r.rew, r.len)
     aflat = policy.actor.flat_params()
 
     def timeit(fn, warm, reps):
@@ -376,6 +380,10 @@ def measure(D, w, steps, warmup, full, args):
         return float(np.mean(ts))
 
     big = slots_per_step > 5e7
+    # K1 first: with reuse_buffers the rollout it leaves behind is the one K2 / K3 are then timed on
+    k1_ms = timeit(lambda: mgr.rollout_device(init_state=inits[0]), 1 if big else 2, 2 if big else 3)
+    r = mgr.last
+    adv, _ = engine.advantage(0, r.G, r.E, r.T, w["gamma"], 0.0, r.rew, r.len)
     k3_ms = timeit(lambda: engine.policy_grad(dims, "ReLU", aflat, policy.cov_diag, r.obs, r.act, adv, r.logp, r.len,
                                               w["eps"], 1.0 / G), 1 if big else 3, 2 if big else 5)
     k2_ms = timeit(lambda: engine.advantage(0, r.G, r.E, r.T, w["gamma"], 0.0, r.rew, r.len), 2, 3)
@@ -384,7 +392,6 @@ def measure(D, w, steps, warmup, full, args):
     tile_max = torch.nn.functional.pad(ln_t, (0, (-ln_t.numel()) % 128)).view(-1, 128).max(dim=1).values
     k1_exec_steps = float(tile_max.sum().item()) * 128.0
     valid_k = float(ln_t.sum().item())            # valid steps of the rollout the kernels are timed on
-    k1_ms = timeit(lambda: mgr.rollout_device(init_state=inits[0]), 1 if big else 2, 2 if big else 3)
     kern = {"k1_ms": k1_ms, "k2_ms": k2_ms, "k3_ms": k3_ms, "valid_k": valid_k, "k1_exec_steps": k1_exec_steps,
             "P": P, "dims": dims, "N": N, "T": T, "O": O, "A": A,
             "k3_traffic": engine.policy_grad_traffic_bytes(dims, int(valid_k), r.len)}

@@ -34,42 +34,57 @@ adv_grpo_kernel(int64_t G, int E, int T, int GC, float gamma, const float *__res
     float *gmean = reinterpret_cast<float *>(syy + envs);  // [GC]
     float *gstd = gmean + GC;                              // [GC]
 
+    // Both passes walk the time axis WARP-UNIFORMLY: every lane of a warp visits the same step t (from the warp's
+    // longest episode down to 0), so each reward / advantage row access is one coalesced 128-byte segment even
+    // when the episode lengths inside the warp are ragged; a lane whose episode has already ended (t >= L) keeps
+    // rtg = 0 and contributes nothing.  (Starting every lane at its own L-1 made ragged warps touch 32 different
+    // rows per load: 428 GB/s at the QuadPole2D shape, profiles/README_r2.md.)
     // pass 1: per-env scan + statistics
-    for (int i = threadIdx.x; i < envs; i += ADV_THREADS) {
-        const int64_t n = n0 + i;
-        const int L = len[n];
+    for (int i0 = (threadIdx.x & ~31); i0 < envs; i0 += ADV_THREADS) {
+        const int i = i0 + (threadIdx.x & 31);
+        const bool live = i < envs;
+        const int64_t n = n0 + (live ? i : 0);
+        const int L = live ? len[n] : 0;
+        const int Lw = __reduce_max_sync(0xffffffffu, L);
         // shift K = first scanned value of the group's first env: the one-pass variance of
         // (y - K) is exactly 0 for a constant group (std 0 -> NaN/inf like torch)
         // and well conditioned otherwise
-        const int64_t e0 = n0 + (int64_t)(i / E) * E;
-        const int L0 = len[e0];
-        const double K = L0 > 0 ? (double)__fadd_rn(rew[(int64_t)(L0 - 1) * N + e0], 1e-8f) : 0.0;
+        double K = 0.0;
+        if (live) {
+            const int64_t e0 = n0 + (int64_t)(i / E) * E;
+            const int L0 = len[e0];
+            K = L0 > 0 ? (double)__fadd_rn(rew[(int64_t)(L0 - 1) * N + e0], 1e-8f) : 0.0;
+        }
         float rtg = 0.0f;
         double ax = 0.0, ay = 0.0, ayy = 0.0;
         // the recurrence is serial per env (bit-exact torch rounding forbids re-association), so the memory
         // parallelism comes from loading ADV_UNROLL reward rows ahead of the dependent chain
-        int t = L - 1;
+        int t = Lw - 1;
         for (; t >= ADV_UNROLL - 1; t -= ADV_UNROLL) {
             float r[ADV_UNROLL];
 #pragma unroll
-            for (int j = 0; j < ADV_UNROLL; ++j) r[j] = rew[(int64_t)(t - j) * N + n];
+            for (int j = 0; j < ADV_UNROLL; ++j) r[j] = (t - j) < L ? rew[(int64_t)(t - j) * N + n] : 0.0f;
 #pragma unroll
             for (int j = 0; j < ADV_UNROLL; ++j) {
-                rtg = rtg_step(r[j], gamma, rtg);
+                if ((t - j) < L) {
+                    rtg = rtg_step(r[j], gamma, rtg);
+                    const double y = (double)__fadd_rn(rtg, 1e-8f) - K;
+                    ax += (double)rtg;
+                    ay += y;
+                    ayy += y * y;
+                }
+            }
+        }
+        for (; t >= 0; --t) {
+            if (t < L) {
+                rtg = rtg_step(rew[(int64_t)t * N + n], gamma, rtg);
                 const double y = (double)__fadd_rn(rtg, 1e-8f) - K;
                 ax += (double)rtg;
                 ay += y;
                 ayy += y * y;
             }
         }
-        for (; t >= 0; --t) {
-            rtg = rtg_step(rew[(int64_t)t * N + n], gamma, rtg);
-            const double y = (double)__fadd_rn(rtg, 1e-8f) - K;
-            ax += (double)rtg;
-            ay += y;
-            ayy += y * y;
-        }
-        sx[i] = ax; sy[i] = ay; syy[i] = ayy;
+        if (live) { sx[i] = ax; sy[i] = ay; syy[i] = ayy; }
     }
     __syncthreads();
     if (threadIdx.x < ng) {
@@ -88,31 +103,42 @@ adv_grpo_kernel(int64_t G, int E, int T, int GC, float gamma, const float *__res
     }
     __syncthreads();
     // pass 2: rescan and normalise; zero the padding
-    for (int i = threadIdx.x; i < envs; i += ADV_THREADS) {
-        const int64_t n = n0 + i;
-        const int L = len[n];
-        const float mean = gmean[i / E], sd = gstd[i / E];
-        for (int t = T - 1; t >= L; --t) {
-            adv[(int64_t)t * N + n] = 0.0f;
-            if (rtg_out) rtg_out[(int64_t)t * N + n] = 0.0f;
+    for (int i0 = (threadIdx.x & ~31); i0 < envs; i0 += ADV_THREADS) {
+        const int i = i0 + (threadIdx.x & 31);
+        const bool live = i < envs;
+        const int64_t n = n0 + (live ? i : 0);
+        const int L = live ? len[n] : 0;
+        const int Lw = __reduce_max_sync(0xffffffffu, L);
+        const float mean = live ? gmean[i / E] : 0.0f, sd = live ? gstd[i / E] : 1.0f;
+        if (live) {
+            for (int t = T - 1; t >= Lw; --t) {
+                adv[(int64_t)t * N + n] = 0.0f;
+                if (rtg_out) rtg_out[(int64_t)t * N + n] = 0.0f;
+            }
         }
         float rtg = 0.0f;
-        int t = L - 1;
+        int t = Lw - 1;
         for (; t >= ADV_UNROLL - 1; t -= ADV_UNROLL) {
             float r[ADV_UNROLL];
 #pragma unroll
-            for (int j = 0; j < ADV_UNROLL; ++j) r[j] = rew[(int64_t)(t - j) * N + n];
+            for (int j = 0; j < ADV_UNROLL; ++j) r[j] = (t - j) < L ? rew[(int64_t)(t - j) * N + n] : 0.0f;
 #pragma unroll
             for (int j = 0; j < ADV_UNROLL; ++j) {
-                rtg = rtg_step(r[j], gamma, rtg);
-                adv[(int64_t)(t - j) * N + n] = __fdiv_rn(__fsub_rn(rtg, mean), sd);
-                if (rtg_out) rtg_out[(int64_t)(t - j) * N + n] = rtg;
+                const bool in = (t - j) < L;
+                if (in) rtg = rtg_step(r[j], gamma, rtg);
+                if (live) {
+                    adv[(int64_t)(t - j) * N + n] = in ? __fdiv_rn(__fsub_rn(rtg, mean), sd) : 0.0f;
+                    if (rtg_out) rtg_out[(int64_t)(t - j) * N + n] = in ? rtg : 0.0f;
+                }
             }
         }
         for (; t >= 0; --t) {
-            rtg = rtg_step(rew[(int64_t)t * N + n], gamma, rtg);
-            adv[(int64_t)t * N + n] = __fdiv_rn(__fsub_rn(rtg, mean), sd);
-            if (rtg_out) rtg_out[(int64_t)t * N + n] = rtg;
+            const bool in = t < L;
+            if (in) rtg = rtg_step(rew[(int64_t)t * N + n], gamma, rtg);
+            if (live) {
+                adv[(int64_t)t * N + n] = in ? __fdiv_rn(__fsub_rn(rtg, mean), sd) : 0.0f;
+                if (rtg_out) rtg_out[(int64_t)t * N + n] = in ? rtg : 0.0f;
+            }
         }
     }
 }
@@ -132,47 +158,55 @@ adv_ppo_scan_kernel(int64_t N, int T, int gae, float gamma, float gamlam, const 
     __shared__ double red[5][ADV_THREADS];
     const int64_t n = (int64_t)blockIdx.x * ADV_THREADS + threadIdx.x;
     double sa = 0, saa = 0, sr = 0, srr = 0, cnt = 0;
-    if (n < N) {
-        const int L = len[n];
-        for (int t = T - 1; t >= L; --t) {
-            adv[(int64_t)t * N + n] = 0.0f;
-            rtg_out[(int64_t)t * N + n] = 0.0f;
+    {
+        // warp-uniform time axis (see adv_grpo_kernel): lanes past the end of their episode idle on the same row
+        const bool live = n < N;
+        const int64_t nn = live ? n : 0;
+        const int L = live ? len[nn] : 0;
+        const int Lw = __reduce_max_sync(0xffffffffu, L);
+        if (live) {
+            for (int t = T - 1; t >= Lw; --t) {
+                adv[(int64_t)t * N + nn] = 0.0f;
+                rtg_out[(int64_t)t * N + nn] = 0.0f;
+            }
         }
         float rtg = 0.0f, a_next = 0.0f, v_next = 0.0f;
         constexpr int PU = 8;                 // rows loaded ahead of the serial recurrence
-        float rb[PU], vb[PU];
-        for (int t = L - 1; t >= 0; --t) {
-            const int slot = (L - 1 - t) % PU;
-            if (slot == 0) {
+        for (int t0 = Lw - 1; t0 >= 0; t0 -= PU) {
+            float rb[PU], vb[PU];
 #pragma unroll
-                for (int j = 0; j < PU; ++j) {
-                    const int tt = t - j;
-                    rb[j] = tt >= 0 ? rew[(int64_t)tt * N + n] : 0.0f;
-                    vb[j] = tt >= 0 ? val[(int64_t)tt * N + n] : 0.0f;
+            for (int j = 0; j < PU; ++j) {
+                const int tt = t0 - j;
+                const bool in = tt >= 0 && tt < L;
+                rb[j] = in ? rew[(int64_t)tt * N + nn] : 0.0f;
+                vb[j] = in ? val[(int64_t)tt * N + nn] : 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < PU; ++j) {
+                const int t = t0 - j;
+                if (t < 0) break;
+                if (t >= L) {
+                    if (live) { adv[(int64_t)t * N + nn] = 0.0f; rtg_out[(int64_t)t * N + nn] = 0.0f; }
+                    continue;
                 }
+                const float r = rb[j], v = vb[j];
+                float a, ret;
+                if (!gae) {
+                    rtg = rtg_step(r, gamma, rtg);            // ppo.py:103-108
+                    ret = rtg;
+                    a = __fsub_rn(rtg, v);                    // :111
+                } else {
+                    // :114-123 (masks are prefix masks: next value/advantage are 0 past the end)
+                    const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(gamma, v_next)), v);
+                    a = (t == T - 1) ? __fsub_rn(r, v) : __fadd_rn(delta, __fmul_rn(gamlam, a_next));
+                    ret = __fadd_rn(v, a);                    // :124
+                    a_next = a;
+                    v_next = v;
+                }
+                adv[(int64_t)t * N + nn] = a;
+                rtg_out[(int64_t)t * N + nn] = ret;
+                sa += a; saa += (double)a * a; sr += ret; srr += (double)ret * ret;
             }
-            float r = rb[0], v = vb[0];
-#pragma unroll
-            for (int j = 1; j < PU; ++j) {
-                r = slot == j ? rb[j] : r;
-                v = slot == j ? vb[j] : v;
-            }
-            float a, ret;
-            if (!gae) {
-                rtg = rtg_step(r, gamma, rtg);            // ppo.py:103-108
-                ret = rtg;
-                a = __fsub_rn(rtg, v);                    // :111
-            } else {
-                // :114-123 (masks are prefix masks: next value/advantage are 0 past the end)
-                const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(gamma, v_next)), v);
-                a = (t == T - 1) ? __fsub_rn(r, v) : __fadd_rn(delta, __fmul_rn(gamlam, a_next));
-                ret = __fadd_rn(v, a);                    // :124
-                a_next = a;
-                v_next = v;
-            }
-            adv[(int64_t)t * N + n] = a;
-            rtg_out[(int64_t)t * N + n] = ret;
-            sa += a; saa += (double)a * a; sr += ret; srr += (double)ret * ret;
         }
         cnt = (double)L;
     }
