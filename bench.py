@@ -538,6 +538,9 @@ def run_ours(args, w):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "envs_per_gpu": N, "horizon": T, "group_size": w["E"],
                    "mlp": [O] + w["hidden"] + [A], "updates_per_iter": w["updates"], "cov": w["cov"], "lr": w["lr"],
+                   "objective_sign": ("ascent (GRPO(maximize=True)); the reference's literal sign descends on J and destroys "
+                                      "the start policy within 6 epochs (measured), see bench.py") if w.get("start") == "lqr"
+                   else "reference (descent on J, grpo.py:140-145)",
                    "start_policy": {"lqr": "stabilising linear feedback embedded in the ReLU net "
                                            "(bench_assets/quadpole_lqr_gain.json), other weights torch default init",
                                     "hover": "torch default init, output layer zeroed"}.get(w.get("start"), "torch default init"),
