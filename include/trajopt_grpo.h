@@ -275,6 +275,14 @@ int tg_policy_grad(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T,
                    float eps_clip, float scale, float kl_coef,
                    float *out_grad, float *out_stats, void *workspace, void *stream);
 
+/* The update kernels walk a ragged rollout in LENGTH ORDER (env indices sorted by episode length, live envs per
+ * step), built from `len` at the start of every tg_policy_grad / tg_value_grad / tg_policy_forward_traj call.
+ * The lengths do not change between the updates of one learn() (grpo.py:106, ppo.py:147): tg_len_order_hold
+ * builds the order once and later calls with the same (len pointer, N, T) reuse it until tg_len_order_release.
+ * The caller must not modify `len` while it is held. */
+int tg_len_order_hold(tg_ctx *ctx, int64_t N, int T, const int32_t *len, void *stream);
+int tg_len_order_release(tg_ctx *ctx);
+
 /* HBM scratch traffic of one tg_policy_grad call beyond the algorithmic trajectory reads (host-side arithmetic,
  * no device work): the streamed 128 / 256-wide tensor-core path hands H1, dZ2, dZ1 and [x, 1] from its
  * forward/backward kernel to its weight-gradient kernel through an HBM scratch.  n_tiles = number of live

@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 print(l)
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in srcs]
     if jobs or force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -69,6 +69,8 @@ _SIGS = {
     "tg_advantage_ppo_normalize": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "tg_export_trajectory": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tg_policy_grad_workspace_bytes": (_i64, [_vp, C.POINTER(MlpCfg)]),
+    "tg_len_order_hold": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "tg_len_order_release": (C.c_int, [_vp]),
     "tg_policy_grad_scratch_bytes": (C.c_int, [_vp, C.POINTER(MlpCfg), _i64, C.POINTER(_i64), C.POINTER(_i64)]),
     "tg_policy_grad": (C.c_int, [_vp, C.POINTER(MlpCfg), _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_f),
                                  _f, _f, _f, _vp, _vp, _vp, _vp]),

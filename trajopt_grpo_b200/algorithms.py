@@ -199,15 +199,16 @@ class GRPO(Algorithm):
             _, old_logp = engine.policy_forward_traj(dims, act_name, old_flat[:flat.numel()].contiguous(), r.obs, cov,
                                                      r.act, r.len)
         scale = (-1.0 if self.maximize else 1.0) / G_global         # grpo.py:140 (J /= group_size)
-        for _ in range(self.updates_per_iter):                      # grpo.py:106
-            grad, stats = engine.policy_grad(dims, act_name, flat, cov, r.obs, r.act, adv, old_logp, r.len,
-                                             self.epsilon, scale)
-            if world > 1:
-                import torch.distributed as dist
-                dist.all_reduce(grad)                                # the path's only collective
-            self._flat_opt.step(flat, grad)                         # grpo.py:143-145
-            pol.bump_param_epoch()
-            self.last_stats = stats
+        with engine.length_order(r.len, r.T):                       # lengths are fixed for all updates of this learn()
+            for _ in range(self.updates_per_iter):                  # grpo.py:106
+                grad, stats = engine.policy_grad(dims, act_name, flat, cov, r.obs, r.act, adv, old_logp, r.len,
+                                                 self.epsilon, scale)
+                if world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(grad)                            # the path's only collective
+                self._flat_opt.step(flat, grad)                     # grpo.py:143-145
+                pol.bump_param_epoch()
+                self.last_stats = stats
         self.old_policy.load_state_dict(self.policy.state_dict())   # grpo.py:148
         self._synced_tag = pol.param_tag()
         self._old_tag = self.old_policy.param_tag()
@@ -355,18 +356,19 @@ class PPO(Algorithm):
             self._learn_minibatched(r, flat, grad, na, a_dims, c_dims, act_name, cov, adv, rtg, old_logp, n_valid)
             self.old_policy.load_state_dict(self.policy.state_dict())   # ppo.py:186
             return
-        for _ in range(self.updates_per_iter):                      # ppo.py:147 (full batch; the order of a
-            # permutation does not change a mean)
-            _, stats = engine.policy_grad(a_dims, act_name, a_flat, cov, r.obs, r.act, adv, old_logp, r.len,
-                                          self.epsilon, -1.0 / n_valid, self.kl_coeff / n_valid,
-                                          out_grad=grad[:na])        # :160-166, 175-176
-            engine.value_grad(c_dims, act_name, c_flat, r.obs, rtg, r.len, self.c1 / n_valid, out_grad=grad[na:])
-            if world > 1:
-                import torch.distributed as dist
-                dist.all_reduce(grad)                                # actor + critic gradients in one message
-            self._flat_opt.step(flat, grad)                         # :181-183 (entropy term has zero gradient)
-            pol.bump_param_epoch()
-            self.last_stats = stats
+        with engine.length_order(r.len, r.T):
+            for _ in range(self.updates_per_iter):                      # ppo.py:147 (full batch; the order of a
+                # permutation does not change a mean)
+                _, stats = engine.policy_grad(a_dims, act_name, a_flat, cov, r.obs, r.act, adv, old_logp, r.len,
+                                              self.epsilon, -1.0 / n_valid, self.kl_coeff / n_valid,
+                                              out_grad=grad[:na])        # :160-166, 175-176
+                engine.value_grad(c_dims, act_name, c_flat, r.obs, rtg, r.len, self.c1 / n_valid, out_grad=grad[na:])
+                if world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(grad)                                # actor + critic gradients in one message
+                self._flat_opt.step(flat, grad)                         # :181-183 (entropy term has zero gradient)
+                pol.bump_param_epoch()
+                self.last_stats = stats
         self.old_policy.load_state_dict(self.policy.state_dict())   # ppo.py:186
 
     def _learn_minibatched(self, r, flat, grad, na, a_dims, c_dims, act_name, cov, adv, rtg, old_logp, n_valid):

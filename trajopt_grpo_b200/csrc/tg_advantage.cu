@@ -261,6 +261,7 @@ extern "C" int64_t tg_advantage_workspace_bytes(int64_t N, int G) {
 extern "C" int tg_advantage(tg_ctx *ctx, int mode, int64_t G, int E, int T, double gamma, double lam, const float *rew,
                             const int32_t *len, const float *values, float *out_adv, float *out_rtg, void *workspace,
                             void *stream) {
+    TgRange nvtx_range("tg_advantage (K2: reward-to-go + advantages)");
     TG_REQUIRE(ctx && rew && len && out_adv, TG_ERR_ARG, "tg_advantage: null argument");
     TG_REQUIRE(G > 0 && E > 0 && T > 0, TG_ERR_SHAPE, "tg_advantage: G, E, T must be positive");
     TG_CUDA(cudaSetDevice(ctx->device));
@@ -290,6 +291,7 @@ extern "C" int tg_advantage(tg_ctx *ctx, int mode, int64_t G, int E, int T, doub
 extern "C" int tg_advantage_ppo_raw(tg_ctx *ctx, int mode, int64_t G, int E, int T, double gamma, double lam,
                                     const float *rew, const int32_t *len, const float *values, float *out_adv,
                                     float *out_rtg, double *out_sums, void *workspace, void *stream) {
+    TgRange nvtx_range("tg_advantage_ppo_raw (K2)");
     TG_REQUIRE(ctx && rew && len && values && out_adv && out_rtg && out_sums && workspace, TG_ERR_ARG,
                "tg_advantage_ppo_raw: null argument");
     TG_REQUIRE(mode == TG_ADV_PPO_MC || mode == TG_ADV_PPO_GAE, TG_ERR_ARG, "unknown PPO advantage mode %d", mode);
@@ -309,6 +311,7 @@ extern "C" int tg_advantage_ppo_raw(tg_ctx *ctx, int mode, int64_t G, int E, int
 
 extern "C" int tg_advantage_ppo_normalize(tg_ctx *ctx, int64_t N, int T, const int32_t *len, const double *sums,
                                           float *adv, float *rtg, void *stream) {
+    TgRange nvtx_range("tg_advantage_ppo_normalize (K2)");
     TG_REQUIRE(ctx && len && sums && adv && rtg, TG_ERR_ARG, "tg_advantage_ppo_normalize: null argument");
     TG_REQUIRE(N > 0 && T > 0, TG_ERR_SHAPE, "tg_advantage_ppo_normalize: N, T must be positive");
     TG_CUDA(cudaSetDevice(ctx->device));

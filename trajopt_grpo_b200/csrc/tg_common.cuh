@@ -28,6 +28,19 @@ void tg_set_error(const char *fmt, ...);
         }                                                                          \
     } while (0)
 
+// NVTX range over the host side of an entry point (nsys attributes the kernels launched inside it to the range):
+// K1 = tg_rollout, K2 = tg_advantage*, K3 = tg_policy_grad / tg_value_grad.  Header-only nvtx3: a no-op unless a
+// profiler injects itself.
+#ifndef TG_NO_NVTX
+#include <nvtx3/nvToolsExt.h>
+struct TgRange {
+    explicit TgRange(const char *name) { nvtxRangePushA(name); }
+    ~TgRange() { nvtxRangePop(); }
+};
+#else
+struct TgRange { explicit TgRange(const char *) {} };
+#endif
+
 struct tg_ctx {
     int device;
     int sm_count;
@@ -45,6 +58,11 @@ struct tg_ctx {
     void *order_buf;
     size_t order_cap;
     int32_t *perm, *cnt;
+    // tg_len_order_hold: the order built for (held_len, held_N, held_T) stays valid until tg_len_order_release --
+    // the episode lengths do not change between the updates of one learn() (grpo.py:106, ppo.py:147)
+    const int32_t *held_len;
+    int64_t held_N;
+    int held_T;
 };
 // fills ctx->perm [N] and ctx->cnt [T] for `len` (asynchronous on `st`)
 int tg_len_order(tg_ctx *ctx, int64_t N, int T, const int32_t *len, cudaStream_t st);

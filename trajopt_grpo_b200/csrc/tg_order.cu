@@ -48,8 +48,25 @@ static int reserve(void **p, size_t *cap, size_t bytes) {
     return TG_OK;
 }
 
+extern "C" int tg_len_order_hold(tg_ctx *ctx, int64_t N, int T, const int32_t *len, void *stream) {
+    TG_REQUIRE(ctx && len, TG_ERR_ARG, "tg_len_order_hold: null argument");
+    TG_CUDA(cudaSetDevice(ctx->device));
+    ctx->held_len = nullptr;
+    int rc = tg_len_order(ctx, N, T, len, (cudaStream_t)stream);
+    if (rc) return rc;
+    ctx->held_len = len; ctx->held_N = N; ctx->held_T = T;
+    return TG_OK;
+}
+
+extern "C" int tg_len_order_release(tg_ctx *ctx) {
+    TG_REQUIRE(ctx != nullptr, TG_ERR_ARG, "tg_len_order_release: ctx is null");
+    ctx->held_len = nullptr;
+    return TG_OK;
+}
+
 int tg_len_order(tg_ctx *ctx, int64_t N, int T, const int32_t *len, cudaStream_t st) {
     TG_REQUIRE(N > 0 && N < (int64_t)1 << 31 && T > 0, TG_ERR_SHAPE, "tg_len_order: bad shape");
+    if (ctx->held_len != nullptr && ctx->held_len == len && ctx->held_N == N && ctx->held_T == T) return TG_OK;
     int bits = 1;
     while ((1 << bits) <= T) ++bits;             // keys are in [0, T]
     size_t temp = 0;

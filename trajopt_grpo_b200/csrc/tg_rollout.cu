@@ -657,6 +657,7 @@ extern "C" int tg_rollout(tg_ctx *ctx, const tg_env_cfg *env, const tg_mlp_cfg *
                           const void *init_state, const float *params, const float *cov_diag, const float *noise,
                           uint64_t seed, int64_t env_offset, float *out_obs, float *out_act, float *out_rew, float *out_logp,
                           int32_t *out_len, float *out_ret, void *stream) {
+    TgRange nvtx_range("tg_rollout (K1: fused policy-in-the-loop rollout)");
     TG_REQUIRE(ctx && env && mlp && init_state && params && cov_diag && out_obs && out_act && out_rew && out_len,
                TG_ERR_ARG, "tg_rollout: null argument");
     TG_REQUIRE(N > 0, TG_ERR_SHAPE, "tg_rollout: N must be positive");

@@ -420,6 +420,7 @@ extern "C" int tg_policy_grad(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int
                               const float *adv, const float *old_logp, const int32_t *len, const float *params,
                               const float *cov_diag, float eps_clip, float scale, float kl_coef, float *out_grad,
                               float *out_stats, void *workspace, void *stream) {
+    TgRange nvtx_range("tg_policy_grad (K3: clipped surrogate + MLP backward)");
     TG_REQUIRE(ctx && mlp && obs && act && adv && old_logp && len && params && cov_diag && out_grad && workspace,
                TG_ERR_ARG, "tg_policy_grad: null argument");
     TG_REQUIRE(N > 0 && T > 0, TG_ERR_SHAPE, "tg_policy_grad: N and T must be positive");
@@ -516,6 +517,7 @@ extern "C" int tg_value_grad_batch(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N
 extern "C" int tg_value_grad(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, const float *obs,
                              const float *target, const int32_t *len, const float *params, float scale,
                              float *out_grad, float *out_stats, void *workspace, void *stream) {
+    TgRange nvtx_range("tg_value_grad (K3: critic regression gradient)");
     TG_REQUIRE(ctx && mlp && obs && target && len && params && out_grad && workspace, TG_ERR_ARG,
                "tg_value_grad: null argument");
     TG_REQUIRE(N > 0 && T > 0, TG_ERR_SHAPE, "tg_value_grad: N and T must be positive");
@@ -578,6 +580,7 @@ extern "C" int tg_policy_forward(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t M, 
 extern "C" int tg_policy_forward_traj(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, const float *obs,
                                       const float *act, const int32_t *len, const float *params,
                                       const float *cov_diag, float *out_mu, float *out_logp, void *stream) {
+    TgRange nvtx_range("tg_policy_forward_traj (old log-probs / critic values)");
     TG_REQUIRE(ctx && mlp && obs && params, TG_ERR_ARG, "tg_policy_forward_traj: null argument");
     TG_REQUIRE(out_mu || out_logp, TG_ERR_ARG, "tg_policy_forward_traj: no output requested");
     TG_REQUIRE(!out_logp || (act && cov_diag), TG_ERR_ARG, "log-prob needs act and cov_diag");
@@ -634,6 +637,7 @@ __global__ void adam_kernel(int64_t n, float *__restrict__ p, const float *__res
 extern "C" int tg_adam_step(tg_ctx *ctx, int64_t n, float *params, const float *grad, float *exp_avg,
                             float *exp_avg_sq, int64_t step, double lr, double beta1, double beta2, double eps,
                             void *stream) {
+    TgRange nvtx_range("tg_adam_step");
     TG_REQUIRE(ctx && params && grad && exp_avg && exp_avg_sq, TG_ERR_ARG, "tg_adam_step: null argument");
     TG_REQUIRE(n > 0 && step >= 1, TG_ERR_SHAPE, "tg_adam_step: n>0 and step>=1 required");
     TG_CUDA(cudaSetDevice(ctx->device));

@@ -307,8 +307,33 @@ def policy_grad(dims, activation, params, cov_diag, obs, act, adv, old_logp, len
                                 L.ptr(length), L.ptr(params), L.cov_array(cov_diag), float(eps_clip), float(scale),
                                 float(kl_scale), L.ptr(grad), L.ptr(stats), L.ptr(ws), L.stream_ptr())
     L.check(rc, "tg_policy_grad")
-    _count(5)                                      # pack, order_keys, order_count, update, grad_reduce
+    _count(3 if length_order.held else 5)          # pack, [order_keys, order_count,] update, grad_reduce
     return grad, stats
+
+
+class length_order:
+    """with engine.length_order(r.len, T): the length order of the rollout is built once (tg_len_order_hold) and
+    reused by every policy_grad / value_grad / policy_forward_traj call inside the block."""
+    held = False
+
+    def __init__(self, length, T):
+        self.length, self.T = length, int(T)
+
+    def __enter__(self):
+        lib = L.load()
+        _need(self.length, torch.int32, "len")
+        dev = self.length.device
+        with torch.cuda.device(dev):
+            L.check(lib.tg_len_order_hold(L.ctx(dev), self.length.numel(), self.T, L.ptr(self.length), L.stream_ptr()),
+                    "tg_len_order_hold")
+        _count(2)
+        length_order.held = True
+        return self
+
+    def __exit__(self, *exc):
+        length_order.held = False
+        L.check(L.load().tg_len_order_release(L.ctx(self.length.device)), "tg_len_order_release")
+        return False
 
 
 def policy_grad_traffic_bytes(dims, n_valid: int, length, activation="ReLU"):
