@@ -316,6 +316,32 @@ int tg_adam_step(tg_ctx *ctx, int64_t n, float *params, const float *grad, float
                  float *exp_avg_sq, int64_t step, double lr, double beta1, double beta2, double eps,
                  void *stream);
 
+/* ---- gradient allreduce fused with Adam over NVLink peer memory -----------------
+ * Replaces, for a rollout sharded over several GPUs (one process per GPU, whole GRPO groups per GPU), the
+ * `torch.distributed.all_reduce(grad)` + `optimizer.step()` pair of every update (grpo.py:143-145, ppo.py:181-183
+ * on the summed gradient): each rank owns a cudaMalloc'ed window that its peers map through CUDA IPC; one kernel
+ * waits until every rank has published its gradient, sums the ranks' gradients with peer loads in rank order
+ * (bit-identical on every rank) and applies Adam in the same pass.  No NCCL call, no separate Adam launch.
+ *
+ *   tg_comm_create   allocates this rank's window for gradients of up to n_floats and writes its IPC handle
+ *                    (tg_comm_handle_bytes() bytes, host) to handle_out; the host exchanges the handles
+ *                    (e.g. torch.distributed.all_gather_object) ...
+ *   tg_comm_connect  ... and passes all `world` handles, rank-major; maps every peer window
+ *   tg_comm_grad_slot  device pointer where the NEXT step's local gradient has to be written: pass it as
+ *                    tg_policy_grad's out_grad (no copy)
+ *   tg_allreduce_adam_step  params -= Adam(sum over ranks of the gradient slots); `step` as tg_adam_step;
+ *                    out_grad_sum (may be NULL) receives the summed gradient
+ * All ranks must call tg_allreduce_adam_step the same number of times (it is a collective). */
+typedef struct tg_comm tg_comm;
+int tg_comm_handle_bytes(void);
+int tg_comm_create(tg_ctx *ctx, int rank, int world, int64_t n_floats, tg_comm **out, void *handle_out);
+int tg_comm_connect(tg_comm *comm, const void *all_handles);
+int tg_comm_destroy(tg_comm *comm);
+int tg_comm_grad_slot(tg_comm *comm, float **out);
+int tg_allreduce_adam_step(tg_ctx *ctx, tg_comm *comm, int64_t n, float *params, float *exp_avg, float *exp_avg_sq,
+                           int64_t step, double lr, double beta1, double beta2, double eps, float *out_grad_sum,
+                           void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,7 @@ def run_case(rank: int, world: int) -> dict:
     buf.device_rollout = mgr.rollout_device()
     algo.learn(buf)
     out["grpo"] = pol.flat_parameters().detach().cpu().numpy().copy()
+    out["_peer"] = algo._flat_opt._comm is not None
     # ---- PPO (GAE), QuadPole2D, 32x32 actor + critic (FP32-pipe kernels), full batch
     torch.manual_seed(1)
     pol2 = tg.GaussianActorCritic_NeuralNetwork(10, 2, [32, 32], "ReLU", 0.05)
@@ -42,6 +43,11 @@ def run_case(rank: int, world: int) -> dict:
     return out
 
 
+def tg_failure():
+    from trajopt_grpo_b200 import engine
+    return engine.PeerComm.last_failure
+
+
 def main():
     import torch.distributed as dist
     ref_path = sys.argv[1]
@@ -50,6 +56,9 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     got = run_case(rank, world)
     ref = np.load(ref_path)
+    if rank == 0:
+        print("peer-memory allreduce:", got.pop("_peer"), "(", tg_failure(), ")")
+    got.pop("_peer", None)
     for k, v in got.items():
         # identical on every rank (same allreduced gradient, same Adam)
         t = torch.from_numpy(v).cuda()

@@ -80,6 +80,12 @@ _SIGS = {
     "tg_value_grad_batch": (C.c_int, [_vp, C.POINTER(MlpCfg), _i64, _i32, _vp, _vp, _vp, _i64, _vp, _f, _vp, _vp, _vp,
                                       _vp]),
     "tg_adam_step": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _vp]),
+    "tg_comm_handle_bytes": (C.c_int, []),
+    "tg_comm_create": (C.c_int, [_vp, _i32, _i32, _i64, C.POINTER(_vp), _vp]),
+    "tg_comm_connect": (C.c_int, [_vp, _vp]),
+    "tg_comm_destroy": (C.c_int, [_vp]),
+    "tg_comm_grad_slot": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "tg_allreduce_adam_step": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)
 

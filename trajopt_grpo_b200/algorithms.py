@@ -67,6 +67,8 @@ class _FlatOptimizer:
         self._steps = {}          # id(param) -> its own CPU step tensor (torch's Adam keeps one per parameter)
         self._ok_key = None
         self._ok = False
+        self._comm = None         # engine.PeerComm: gradient allreduce + Adam over NVLink peer memory (world > 1)
+        self._comm_tried = False
 
     def _fused_adam_ok(self, flat):
         groups = self.opt.param_groups
@@ -117,6 +119,26 @@ class _FlatOptimizer:
             self.step_count = loaded_step
             for t in self._steps.values():
                 t.fill_(float(loaded_step))
+
+    def peer_comm(self, flat):
+        """The peer-memory gradient window of a sharded run (built on first use, collectively), or None: world
+        size 1, an optimizer the fused Adam kernel does not cover, TG_PEER_ALLREDUCE=0, or the windows could
+        not be mapped on every rank (the NCCL allreduce + tg_adam_step path is then used)."""
+        if self._comm_tried:
+            return self._comm if (self._comm is None or self._comm.n >= flat.numel()) else None
+        self._comm_tried = True
+        if _dist_world() > 1 and self._fused_adam_ok(flat) and os.environ.get("TG_PEER_ALLREDUCE", "1") != "0":
+            self._comm = engine.PeerComm.try_create(flat.numel(), flat.device)
+        return self._comm
+
+    def step_allreduced(self, flat, comm):
+        """Adam on the sum over ranks of the gradients the ranks wrote into their comm slots (one fused launch)."""
+        self._sync_adam_state(flat)
+        g = self.opt.param_groups[0]
+        self.step_count += 1
+        comm.allreduce_adam_step(flat, self.m, self.v, self.step_count, g["lr"], g["betas"][0], g["betas"][1], g["eps"])
+        for t in self._steps.values():
+            t.fill_(float(self.step_count))
 
     def step(self, flat, grad):
         if self._fused_adam_ok(flat):
@@ -199,14 +221,22 @@ class GRPO(Algorithm):
             _, old_logp = engine.policy_forward_traj(dims, act_name, old_flat[:flat.numel()].contiguous(), r.obs, cov,
                                                      r.act, r.len)
         scale = (-1.0 if self.maximize else 1.0) / G_global         # grpo.py:140 (J /= group_size)
+        comm = self._flat_opt.peer_comm(flat) if world > 1 else None
         with engine.length_order(r.len, r.T):                       # lengths are fixed for all updates of this learn()
             for _ in range(self.updates_per_iter):                  # grpo.py:106
+                # the path's only collective: the gradient summed over ranks.  With the peer-memory window the kernel
+                # writes its gradient into this rank's slot and ONE launch does allreduce + Adam (tg_comm.cu);
+                # otherwise NCCL allreduce + tg_adam_step
+                slot = comm.grad_slot()[:flat.numel()] if comm is not None else None
                 grad, stats = engine.policy_grad(dims, act_name, flat, cov, r.obs, r.act, adv, old_logp, r.len,
-                                                 self.epsilon, scale)
-                if world > 1:
-                    import torch.distributed as dist
-                    dist.all_reduce(grad)                            # the path's only collective
-                self._flat_opt.step(flat, grad)                     # grpo.py:143-145
+                                                 self.epsilon, scale, out_grad=slot)
+                if comm is not None:
+                    self._flat_opt.step_allreduced(flat, comm)      # grpo.py:143-145 on the summed gradient
+                else:
+                    if world > 1:
+                        import torch.distributed as dist
+                        dist.all_reduce(grad)
+                    self._flat_opt.step(flat, grad)                 # grpo.py:143-145
                 pol.bump_param_epoch()
                 self.last_stats = stats
         self.old_policy.load_state_dict(self.policy.state_dict())   # grpo.py:148
@@ -253,8 +283,10 @@ class GRPO(Algorithm):
         n_valid = torch.zeros((), dtype=torch.int64, device=dev)
         ret_sum = torch.zeros((), dtype=torch.float64, device=dev)
         out = getattr(self, "_stream_out", None)
-        grad_total, grad_part = torch.empty_like(flat), torch.empty_like(flat)
+        grad_own, grad_part = torch.empty_like(flat), torch.empty_like(flat)
+        comm = self._flat_opt.peer_comm(flat) if world > 1 else None
         for u in range(self.updates_per_iter):
+            grad_total = comm.grad_slot()[:flat.numel()] if comm is not None else grad_own
             grad_total.zero_()
             for g0 in range(0, G_loc, chunk_groups):
                 g1 = min(G_loc, g0 + chunk_groups)
@@ -271,10 +303,13 @@ class GRPO(Algorithm):
                     n_valid.add_(out["len"].sum())
                     ret_sum.add_(out["ret"].sum(dtype=torch.float64))
                 self.last_stats = stats
-            if world > 1:
-                import torch.distributed as dist
-                dist.all_reduce(grad_total)
-            self._flat_opt.step(flat, grad_total)
+            if comm is not None:
+                self._flat_opt.step_allreduced(flat, comm)
+            else:
+                if world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(grad_total)
+                self._flat_opt.step(flat, grad_total)
             pol.bump_param_epoch()
         self._stream_out = out
         self.old_policy.load_state_dict(self.policy.state_dict())   # grpo.py:148
@@ -352,6 +387,7 @@ class PPO(Algorithm):
         _, old_logp = engine.policy_forward_traj(a_dims, act_name, a_flat, r.obs, cov, r.act, r.len)
         n_valid = int(round(float(sums[4].item())))                 # global valid-step count (the .mean()s)
         grad = torch.empty_like(flat)
+        comm = self._flat_opt.peer_comm(flat) if (world > 1 and self.batch_size is None) else None
         if self.batch_size is not None:
             self._learn_minibatched(r, flat, grad, na, a_dims, c_dims, act_name, cov, adv, rtg, old_logp, n_valid)
             self.old_policy.load_state_dict(self.policy.state_dict())   # ppo.py:186
@@ -359,14 +395,19 @@ class PPO(Algorithm):
         with engine.length_order(r.len, r.T):
             for _ in range(self.updates_per_iter):                      # ppo.py:147 (full batch; the order of a
                 # permutation does not change a mean)
+                if comm is not None:
+                    grad = comm.grad_slot()[:flat.numel()]               # this rank's slot of the peer-memory window
                 _, stats = engine.policy_grad(a_dims, act_name, a_flat, cov, r.obs, r.act, adv, old_logp, r.len,
                                               self.epsilon, -1.0 / n_valid, self.kl_coeff / n_valid,
                                               out_grad=grad[:na])        # :160-166, 175-176
                 engine.value_grad(c_dims, act_name, c_flat, r.obs, rtg, r.len, self.c1 / n_valid, out_grad=grad[na:])
-                if world > 1:
-                    import torch.distributed as dist
-                    dist.all_reduce(grad)                                # actor + critic gradients in one message
-                self._flat_opt.step(flat, grad)                         # :181-183 (entropy term has zero gradient)
+                if comm is not None:
+                    self._flat_opt.step_allreduced(flat, comm)          # actor + critic gradients, allreduce + Adam fused
+                else:
+                    if world > 1:
+                        import torch.distributed as dist
+                        dist.all_reduce(grad)                            # actor + critic gradients in one message
+                    self._flat_opt.step(flat, grad)                     # :181-183 (entropy term has zero gradient)
                 pol.bump_param_epoch()
                 self.last_stats = stats
         self.old_policy.load_state_dict(self.policy.state_dict())   # ppo.py:186

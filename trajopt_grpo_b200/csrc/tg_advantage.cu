@@ -19,6 +19,68 @@
 // rtg recurrence with torch's rounding (separate multiply and add, no FMA)
 TG_D float rtg_step(float r, float gamma, float next) { return __fadd_rn(r, __fmul_rn(gamma, next)); }
 
+// One env's reverse scan, statistics pass.  PRED = the warp's episode lengths differ: every lane walks the time axis
+// from the warp's longest episode (Lw) so that each row access is one coalesced segment, and a lane whose episode has
+// ended (t >= L) keeps rtg = 0 and contributes nothing.  PRED = false (all lanes have L == Lw): no predicates.
+template <bool PRED>
+TG_D void grpo_scan_stats(const float *__restrict__ rew, int64_t N, int64_t n, int L, int Lw, float gamma, double K,
+                          double &ax, double &ay, double &ayy) {
+    float rtg = 0.0f;
+    // the recurrence is serial per env (bit-exact torch rounding forbids re-association), so the memory
+    // parallelism comes from loading ADV_UNROLL reward rows ahead of the dependent chain
+    int t = Lw - 1;
+    for (; t >= ADV_UNROLL - 1; t -= ADV_UNROLL) {
+        float r[ADV_UNROLL];
+#pragma unroll
+        for (int j = 0; j < ADV_UNROLL; ++j) r[j] = (!PRED || (t - j) < L) ? rew[(int64_t)(t - j) * N + n] : 0.0f;
+#pragma unroll
+        for (int j = 0; j < ADV_UNROLL; ++j) {
+            if (!PRED || (t - j) < L) {
+                rtg = rtg_step(r[j], gamma, rtg);
+                const double y = (double)__fadd_rn(rtg, 1e-8f) - K;
+                ax += (double)rtg;
+                ay += y;
+                ayy += y * y;
+            }
+        }
+    }
+    for (; t >= 0; --t) {
+        if (!PRED || t < L) {
+            rtg = rtg_step(rew[(int64_t)t * N + n], gamma, rtg);
+            const double y = (double)__fadd_rn(rtg, 1e-8f) - K;
+            ax += (double)rtg;
+            ay += y;
+            ayy += y * y;
+        }
+    }
+}
+
+// normalise pass: rescan, write the advantages (zeros past the end of the episode)
+template <bool PRED>
+TG_D void grpo_scan_norm(const float *__restrict__ rew, int64_t N, int64_t n, int L, int Lw, float gamma, float mean,
+                         float sd, float *__restrict__ adv, float *__restrict__ rtg_out) {
+    float rtg = 0.0f;
+    int t = Lw - 1;
+    for (; t >= ADV_UNROLL - 1; t -= ADV_UNROLL) {
+        float r[ADV_UNROLL];
+#pragma unroll
+        for (int j = 0; j < ADV_UNROLL; ++j) r[j] = (!PRED || (t - j) < L) ? rew[(int64_t)(t - j) * N + n] : 0.0f;
+#pragma unroll
+        for (int j = 0; j < ADV_UNROLL; ++j) {
+            const bool in = !PRED || (t - j) < L;
+            if (in) rtg = rtg_step(r[j], gamma, rtg);
+            adv[(int64_t)(t - j) * N + n] = in ? __fdiv_rn(__fsub_rn(rtg, mean), sd) : 0.0f;
+            if (rtg_out) rtg_out[(int64_t)(t - j) * N + n] = in ? rtg : 0.0f;
+        }
+    }
+    for (; t >= 0; --t) {
+        const bool in = !PRED || t < L;
+        if (in) rtg = rtg_step(rew[(int64_t)t * N + n], gamma, rtg);
+        adv[(int64_t)t * N + n] = in ? __fdiv_rn(__fsub_rn(rtg, mean), sd) : 0.0f;
+        if (rtg_out) rtg_out[(int64_t)t * N + n] = in ? rtg : 0.0f;
+    }
+}
+
 __global__ void __launch_bounds__(ADV_THREADS)
 adv_grpo_kernel(int64_t G, int E, int T, int GC, float gamma, const float *__restrict__ rew,
                 const int32_t *__restrict__ len, float *__restrict__ adv, float *__restrict__ rtg_out) {
@@ -34,11 +96,8 @@ adv_grpo_kernel(int64_t G, int E, int T, int GC, float gamma, const float *__res
     float *gmean = reinterpret_cast<float *>(syy + envs);  // [GC]
     float *gstd = gmean + GC;                              // [GC]
 
-    // Both passes walk the time axis WARP-UNIFORMLY: every lane of a warp visits the same step t (from the warp's
-    // longest episode down to 0), so each reward / advantage row access is one coalesced 128-byte segment even
-    // when the episode lengths inside the warp are ragged; a lane whose episode has already ended (t >= L) keeps
-    // rtg = 0 and contributes nothing.  (Starting every lane at its own L-1 made ragged warps touch 32 different
-    // rows per load: 428 GB/s at the QuadPole2D shape, profiles/README_r2.md.)
+    // Both passes walk the time axis WARP-UNIFORMLY (see grpo_scan_stats): starting every lane at its own L-1 made
+    // ragged warps touch 32 different rows per load (428 GB/s at the QuadPole2D shape, profiles/README_r2.md).
     // pass 1: per-env scan + statistics
     for (int i0 = (threadIdx.x & ~31); i0 < envs; i0 += ADV_THREADS) {
         const int i = i0 + (threadIdx.x & 31);
@@ -46,45 +105,18 @@ adv_grpo_kernel(int64_t G, int E, int T, int GC, float gamma, const float *__res
         const int64_t n = n0 + (live ? i : 0);
         const int L = live ? len[n] : 0;
         const int Lw = __reduce_max_sync(0xffffffffu, L);
+        const bool ragged = __any_sync(0xffffffffu, live && L != Lw);
+        if (!live) continue;
         // shift K = first scanned value of the group's first env: the one-pass variance of
         // (y - K) is exactly 0 for a constant group (std 0 -> NaN/inf like torch)
         // and well conditioned otherwise
-        double K = 0.0;
-        if (live) {
-            const int64_t e0 = n0 + (int64_t)(i / E) * E;
-            const int L0 = len[e0];
-            K = L0 > 0 ? (double)__fadd_rn(rew[(int64_t)(L0 - 1) * N + e0], 1e-8f) : 0.0;
-        }
-        float rtg = 0.0f;
+        const int64_t e0 = n0 + (int64_t)(i / E) * E;
+        const int L0 = len[e0];
+        const double K = L0 > 0 ? (double)__fadd_rn(rew[(int64_t)(L0 - 1) * N + e0], 1e-8f) : 0.0;
         double ax = 0.0, ay = 0.0, ayy = 0.0;
-        // the recurrence is serial per env (bit-exact torch rounding forbids re-association), so the memory
-        // parallelism comes from loading ADV_UNROLL reward rows ahead of the dependent chain
-        int t = Lw - 1;
-        for (; t >= ADV_UNROLL - 1; t -= ADV_UNROLL) {
-            float r[ADV_UNROLL];
-#pragma unroll
-            for (int j = 0; j < ADV_UNROLL; ++j) r[j] = (t - j) < L ? rew[(int64_t)(t - j) * N + n] : 0.0f;
-#pragma unroll
-            for (int j = 0; j < ADV_UNROLL; ++j) {
-                if ((t - j) < L) {
-                    rtg = rtg_step(r[j], gamma, rtg);
-                    const double y = (double)__fadd_rn(rtg, 1e-8f) - K;
-                    ax += (double)rtg;
-                    ay += y;
-                    ayy += y * y;
-                }
-            }
-        }
-        for (; t >= 0; --t) {
-            if (t < L) {
-                rtg = rtg_step(rew[(int64_t)t * N + n], gamma, rtg);
-                const double y = (double)__fadd_rn(rtg, 1e-8f) - K;
-                ax += (double)rtg;
-                ay += y;
-                ayy += y * y;
-            }
-        }
-        if (live) { sx[i] = ax; sy[i] = ay; syy[i] = ayy; }
+        if (ragged) grpo_scan_stats<true>(rew, N, n, L, Lw, gamma, K, ax, ay, ayy);
+        else grpo_scan_stats<false>(rew, N, n, L, Lw, gamma, K, ax, ay, ayy);
+        sx[i] = ax; sy[i] = ay; syy[i] = ayy;
     }
     __syncthreads();
     if (threadIdx.x < ng) {
@@ -109,37 +141,15 @@ adv_grpo_kernel(int64_t G, int E, int T, int GC, float gamma, const float *__res
         const int64_t n = n0 + (live ? i : 0);
         const int L = live ? len[n] : 0;
         const int Lw = __reduce_max_sync(0xffffffffu, L);
-        const float mean = live ? gmean[i / E] : 0.0f, sd = live ? gstd[i / E] : 1.0f;
-        if (live) {
-            for (int t = T - 1; t >= Lw; --t) {
-                adv[(int64_t)t * N + n] = 0.0f;
-                if (rtg_out) rtg_out[(int64_t)t * N + n] = 0.0f;
-            }
+        const bool ragged = __any_sync(0xffffffffu, live && L != Lw);
+        if (!live) continue;
+        const float mean = gmean[i / E], sd = gstd[i / E];
+        for (int t = T - 1; t >= Lw; --t) {
+            adv[(int64_t)t * N + n] = 0.0f;
+            if (rtg_out) rtg_out[(int64_t)t * N + n] = 0.0f;
         }
-        float rtg = 0.0f;
-        int t = Lw - 1;
-        for (; t >= ADV_UNROLL - 1; t -= ADV_UNROLL) {
-            float r[ADV_UNROLL];
-#pragma unroll
-            for (int j = 0; j < ADV_UNROLL; ++j) r[j] = (t - j) < L ? rew[(int64_t)(t - j) * N + n] : 0.0f;
-#pragma unroll
-            for (int j = 0; j < ADV_UNROLL; ++j) {
-                const bool in = (t - j) < L;
-                if (in) rtg = rtg_step(r[j], gamma, rtg);
-                if (live) {
-                    adv[(int64_t)(t - j) * N + n] = in ? __fdiv_rn(__fsub_rn(rtg, mean), sd) : 0.0f;
-                    if (rtg_out) rtg_out[(int64_t)(t - j) * N + n] = in ? rtg : 0.0f;
-                }
-            }
-        }
-        for (; t >= 0; --t) {
-            const bool in = t < L;
-            if (in) rtg = rtg_step(rew[(int64_t)t * N + n], gamma, rtg);
-            if (live) {
-                adv[(int64_t)t * N + n] = in ? __fdiv_rn(__fsub_rn(rtg, mean), sd) : 0.0f;
-                if (rtg_out) rtg_out[(int64_t)t * N + n] = in ? rtg : 0.0f;
-            }
-        }
+        if (ragged) grpo_scan_norm<true>(rew, N, n, L, Lw, gamma, mean, sd, adv, rtg_out);
+        else grpo_scan_norm<false>(rew, N, n, L, Lw, gamma, mean, sd, adv, rtg_out);
     }
 }
 

@@ -10,14 +10,18 @@
 //       forward, MN-major chunks for the backward), exactly like the 256-wide rollout kernel; activations go
 //       registers -> tensor memory as the A operand (K halves at W = 256).  The first Linear runs on the
 //       tensor core too (obs hi/lo + ones column carrying the bias).  Per tile the kernel leaves in an HBM
-//       scratch, already hi/lo split and in the operand layout of kernel B:  H1, dZ2, dZ1 (MN-major
-//       SW128_32B, 8-sample sub-blocks) and [x, 1] (K-major).  dWo and dbo (column sums over the tile) stay on register
-//       butterflies here.
+//       scratch, in the operand layout of kernel B:  H1, H2, dZ1 as fp32 (MN-major SW128_32B, 8-sample
+//       sub-blocks) and Y = [x, 1, dmu] hi/lo (K-major).  No column sums over samples are left in this kernel:
+//       round 1 computed dWo = dmu^T . H2 with register butterflies here (40 k of ~100 k clocks per tile at
+//       W = 256, and the reason for its spills); dWo is now one more small GEMM of kernel B.
 //   kernel B  (update_tcw_wgrad_kernel)   split-K weight-gradient GEMMs over the batch's samples:
-//       dW1[half] += dZ2[:, half]^T . H1,   [dW0 | db0][half] += dZ1[:, half]^T . [x, 1],   db1[half] = (dZ2[:, half]^T . [x, 1])[:, ones],
-//       operands streamed from the scratch by TMA (8 samples per stage), accumulators persistent in tensor
-//       memory for all tiles of the launch, added to the CTA-private gradient copy at the end.  One launch
-//       per 128-row half of the outputs (two at W = 256).  HBM-bound by construction (about 8-12 KB per sample).
+//       dW1[half] += dZ2[:, half]^T . H1,   [dW0 | db0][half] += dZ1[:, half]^T . Y,   db1[half] = (dZ2[:, half]^T . Y)[:, ones],
+//       dWo[:, half]^T = (H2[:, half]^T . Y)[:, dmu columns],
+//       operands streamed from the scratch by TMA (8 samples per stage); dZ2 is not stored: the converter warps
+//       rebuild it from H2 and dmu, dZ2 = (Wo^T dmu) * act'(H2), with the operation order of kernel A, while they
+//       split the fp32 rows into tf32 hi/lo.  Accumulators persistent in tensor memory for all tiles of the
+//       launch, added to the CTA-private gradient copy at the end.  One launch per 128-row half of the outputs
+//       (two at W = 256).
 //
 // Tiles are enumerated in length order (tg_order.cu): tile k of the compact list is (step t, sorted
 // positions 128*blk ..), found by binary search in the per-step prefix of live tiles; k beyond the live
@@ -45,9 +49,9 @@ struct TcwScratch {                       // per-tile byte strides / bases insid
     unsigned char *base;
     int64_t tile_bytes;                   // all arrays of one tile
     int64_t arr_bytes;                    // one of H1, dZ2, dZ1 (fp32) per tile = 16 sub-blocks * W/32 KB
-    int64_t x_bytes;                      // one of Xh, Xl per tile = 16 * OKP * 32
+    int64_t x_bytes;                      // one of Yh, Yl per tile = 16 * XKP * 32, XKP = roundup(O + 1 + A, 8)
 };
-// array order inside a tile: H1, dZ2, dZ1 (fp32, MN-major sub-blocks), Xh, Xl
+// array order inside a tile: H1, H2, dZ1 (fp32, MN-major sub-blocks), Yh, Yl  (Y = [x, 1, dmu], K-major)
 
 struct TcwArgs {
     TcwLayout lay;
@@ -60,6 +64,7 @@ struct TcwArgs {
     const int64_t *tstart;                // [T+1] prefix of live tiles per step
     int64_t k_begin, k_count;             // this batch: compact tiles [k_begin, k_begin + k_count)
     const float *packed;
+    const float *params;                  // flat torch-order parameters (kernel B reads Wo from them)
     float inv_sd[TG_MAX_ACT], inv_var[TG_MAX_ACT], log_norm;
     float eps_clip, scale, kl_scale;
     float *gpart;                         // [grid][n_params], accumulated (+=) across launches
@@ -210,25 +215,6 @@ TG_D bool tcw_tile_next(const int64_t *__restrict__ tstart, int T, int64_t k, in
 TG_D void tcw_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 TG_D void tcw_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// butterfly column sum: v[0..32) per lane -> the warp's sum of column `lane`
-template <int HALF, int OFF> TG_D void tcw_colsum_step(float *v, int lane) {
-    const bool up = (lane & OFF) != 0;
-#pragma unroll
-    for (int j = 0; j < HALF; ++j) {
-        const float send = up ? v[j] : v[j + HALF];
-        const float keep = up ? v[j + HALF] : v[j];
-        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
-    }
-}
-TG_D float tcw_colsum32(float *v, int lane) {
-    tcw_colsum_step<16, 16>(v, lane);
-    tcw_colsum_step<8, 8>(v, lane);
-    tcw_colsum_step<4, 4>(v, lane);
-    tcw_colsum_step<2, 2>(v, lane);
-    tcw_colsum_step<1, 1>(v, lane);
-    return v[0];
-}
-
 // byte offset of (sample s, column c) inside one MN-major scratch array of a tile (8-sample sub-blocks)
 template <int W> TG_D uint32_t tcw_sc_off(int s, int c) {
     const int r = s & 7;
@@ -249,33 +235,64 @@ TG_D void ldg256(const void *p, float *v) {
                  : "memory");
 }
 
-// 32 consecutive columns (column block cbk) of sample s: written as fp32 to the scratch array (MN-major sub-block
-// layout; kernel B splits into tf32 hi/lo after its TMA load, which halves the HBM traffic of both kernels) and --
-// when TM -- hi/lo split into the tensor-memory A operand (hi at tm_hi, lo at tm_lo), 16 columns at a time.
-template <int W, bool TM>
-TG_D void tcw_emit32(unsigned char *arr, int s, int cbk, const float *v, uint32_t tm_hi, uint32_t tm_lo) {
+// 32 consecutive columns (column block cbk) of sample s written as fp32 to a scratch array (MN-major sub-block
+// layout; kernel B splits into tf32 hi/lo after its TMA load, which halves the HBM traffic of both kernels)
+template <int W>
+TG_D void tcw_store32(unsigned char *arr, int s, int cbk, const float *v) {
     const int r = s & 7;
     unsigned char *p = arr + (size_t)(s >> 3) * (W / 32 * 1024) + (size_t)cbk * 1024 + (size_t)r * 128;
 #pragma unroll
     for (int c8 = 0; c8 < 4; ++c8)                    // 32-byte chunk (8 columns) c8 of the 128-byte row
         stg256(p + (uint32_t)((c8 ^ (r & 3)) << 5), v + 8 * c8);
-    if (TM) {
+}
+// 32 columns hi/lo split into the tensor-memory A operand (hi at tm_hi, lo at tm_lo), 16 columns at a time
+TG_D void tcw_tm32(const float *v, uint32_t tm_hi, uint32_t tm_lo) {
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            float hi[16], lo[16];
+    for (int hh = 0; hh < 2; ++hh) {
+        float hi[16], lo[16];
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-                hi[jj] = tf32_hi(v[hh * 16 + jj]);
-                lo[jj] = v[hh * 16 + jj] - hi[jj];
-            }
-            tmem_st16(tm_hi + (uint32_t)(hh * 16), hi);
-            tmem_st16(tm_lo + (uint32_t)(hh * 16), lo);
+        for (int jj = 0; jj < 16; ++jj) {
+            hi[jj] = tf32_hi(v[hh * 16 + jj]);
+            lo[jj] = v[hh * 16 + jj] - hi[jj];
         }
+        tmem_st16(tm_hi + (uint32_t)(hh * 16), hi);
+        tmem_st16(tm_lo + (uint32_t)(hh * 16), lo);
     }
 }
-// the same 32 columns read back from the scratch (this thread wrote them), split, into the tensor-memory A operand
+// 16-column pieces (half hh of the 32-column block): the epilogues of kernel A work at this granularity so that a
+// thread holds 16 accumulator values + their hi/lo split (48 registers) instead of 32 + 32 + 32 -- at 96 registers
+// per thread (18 warps) the 32-column form spilled ~0.7 KB per thread
 template <int W>
-TG_D void tcw_reload32(const unsigned char *arr, int s, int cbk, uint32_t tm_hi, uint32_t tm_lo) {
+TG_D void tcw_store16(unsigned char *arr, int s, int cbk, int hh, const float *v) {
+    const int r = s & 7;
+    unsigned char *p = arr + (size_t)(s >> 3) * (W / 32 * 1024) + (size_t)cbk * 1024 + (size_t)r * 128;
+#pragma unroll
+    for (int c8 = 0; c8 < 2; ++c8) stg256(p + (uint32_t)(((hh * 2 + c8) ^ (r & 3)) << 5), v + 8 * c8);
+}
+TG_D void tcw_tm16(const float *v, uint32_t tm_hi, uint32_t tm_lo) {
+    float hi[16], lo[16];
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+        hi[jj] = tf32_hi(v[jj]);
+        lo[jj] = v[jj] - hi[jj];
+    }
+    tmem_st16(tm_hi, hi);
+    tmem_st16(tm_lo, lo);
+}
+// dZ2 = (Wo^T dmu) * act'(H2) for one column: the ONE definition both kernels use (kernel A for the A operand of the
+// backward-data GEMM, kernel B's converter warps for the weight-gradient operand), so the two are bit-identical
+template <int A>
+TG_D float tcw_dz2(float h2, const float *dmu, const float *wo_col, int wo_stride, int act_kind) {
+    float g = 0.0f;
+#pragma unroll
+    for (int o = 0; o < A; ++o) g = fmaf(dmu[o], wo_col[o * wo_stride], g);
+    return g * act_bwd_from_out(h2, act_kind);
+}
+// the same 32 columns read back from the scratch (this thread wrote them), split, into the tensor-memory A operand.
+// DZ2: the scratch holds H2; the operand is dZ2 = (Wo^T dmu) * act'(H2) (wo = this thread's first column of Wo).
+template <int W, int A, bool DZ2>
+TG_D void tcw_reload32(const unsigned char *arr, int s, int cbk, uint32_t tm_hi, uint32_t tm_lo, const float *dmu,
+                       const float *wo, int act_kind) {
     const int r = s & 7;
     const unsigned char *p = arr + (size_t)(s >> 3) * (W / 32 * 1024) + (size_t)cbk * 1024 + (size_t)r * 128;
 #pragma unroll
@@ -285,8 +302,9 @@ TG_D void tcw_reload32(const unsigned char *arr, int s, int cbk, uint32_t tm_hi,
         for (int c8 = 0; c8 < 2; ++c8) ldg256(p + (uint32_t)(((hh * 2 + c8) ^ (r & 3)) << 5), v + 8 * c8);
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
-            hi[jj] = tf32_hi(v[jj]);
-            lo[jj] = v[jj] - hi[jj];
+            const float x = DZ2 ? tcw_dz2<A>(v[jj], dmu, wo + hh * 16 + jj, W, act_kind) : v[jj];
+            hi[jj] = tf32_hi(x);
+            lo[jj] = x - hi[jj];
         }
         tmem_st16(tm_hi + (uint32_t)(hh * 16), hi);
         tmem_st16(tm_lo + (uint32_t)(hh * 16), lo);
@@ -303,6 +321,7 @@ TG_D void tcw_reload32(const unsigned char *arr, int s, int cbk, uint32_t tm_hi,
 template <int O, int A, bool RELU, int W, int NP>
 __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(const __grid_constant__ TcwArgs a) {
     constexpr int HW = W / NP, NCH = HW / 32, OKP = (O + 1 + 7) / 8 * 8, KH = W / 128;
+    constexpr int XKP = (O + 1 + A + 7) / 8 * 8;      // rows of Y = [x, 1, dmu, 0..] handed to kernel B
     constexpr int NCT = NP * 128;                     // compute threads
     constexpr int CNT_ALL = NCT + 32, CNT_H1 = (KH == 2 ? NCT / 2 : NCT) + 32;
     constexpr int NKC = W / 32;                       // K chunks per direction
@@ -315,7 +334,11 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
     __shared__ float muS[NP][A][128];
     __shared__ float dmuS[A][128];
     __shared__ double sred[4][16];
+    // objective / count / ratio / clip statistics of sample row e, accumulated over the CTA's tiles by the part-0
+    // thread of that row (shared memory instead of 8 registers per thread: the epilogues run at the 96-register cap)
+    __shared__ double statS[4][128];
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+    for (int i = threadIdx.x; i < 4 * 128; i += blockDim.x) statS[i / 128][i % 128] = 0.0;
     unsigned char *ring = smem_raw;
     float *Rsm = reinterpret_cast<float *>(smem_raw + TCW_STAGES * CB);
     unsigned char *O_hi = reinterpret_cast<unsigned char *>(Rsm + a.lay.resident);
@@ -453,16 +476,9 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
         const int act_kind = RELU ? TG_ACT_RELU : a.lay.act;
         const float *b1 = Rsm + a.lay.b1 + c0, *wo = Rsm + a.lay.wo + c0, *bo = Rsm + a.lay.bo;
         uint32_t ph_d = 0, ph_k0 = 0;
-        // butterfly partials (this warp's sum over its 32 samples of column c0 + 32*ch + lane)
-        float c_wo[A][NCH], c_bo[A];
-#pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-#pragma unroll
-            for (int j = 0; j < A; ++j) c_wo[j][ch] = 0.0f;
-        }
+        float c_bo[A];                                 // this thread's running sum of dmu (dbo)
 #pragma unroll
         for (int j = 0; j < A; ++j) c_bo[j] = 0.0f;
-        double s_obj = 0.0, s_cnt = 0.0, s_ratio = 0.0, s_clip = 0.0;
 
         // K-half protocol of the TMEM A operand (W = 256): threads whose columns belong to half 0 write it while
         // they process their chunks; threads of half 1 only write the scratch, tell the MMA warp they have read
@@ -470,16 +486,21 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
         // scratch they just wrote (nothing is held in registers across the wait).
         constexpr bool DEFER = KH == 2;
         const bool deferred = DEFER && my_half == 1;
-        auto finish_A = [&](const unsigned char *arr) {
+        float dmu_own[A];                              // d objective / d mu of this thread's sample (epilogue 2b)
+#pragma unroll
+        for (int j = 0; j < A; ++j) dmu_own[j] = 0.0f;
+        auto finish_A = [&](const unsigned char *arr, bool dz2) {
             if (deferred) {
                 tc_fence_before();
                 tcw_arrive(TCW_BAR_K0, CNT_ALL);
                 mbar_wait(&bar_k0, ph_k0);
                 tc_fence_after();
 #pragma unroll
-                for (int ch = 0; ch < NCH; ++ch)
-                    tcw_reload32<W>(arr, e, (c0 >> 5) + ch, my_tm + TM_AHI + acol0 + (uint32_t)(ch * 32),
-                                    my_tm + TM_ALO + acol0 + (uint32_t)(ch * 32));
+                for (int ch = 0; ch < NCH; ++ch) {
+                    const uint32_t th = my_tm + TM_AHI + acol0 + (uint32_t)(ch * 32), tl = my_tm + TM_ALO + acol0 + (uint32_t)(ch * 32);
+                    if (dz2) tcw_reload32<W, A, true>(arr, e, (c0 >> 5) + ch, th, tl, dmu_own, wo + ch * 32, act_kind);
+                    else tcw_reload32<W, A, false>(arr, e, (c0 >> 5) + ch, th, tl, dmu_own, wo, act_kind);
+                }
             }
             ph_k0 ^= 1u;
             tmem_st_wait();
@@ -494,42 +515,23 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
             if (!(first_tile ? tcw_tile_of(a.tstart, a.T, k, &t, &blk) : tcw_tile_next(a.tstart, a.T, k, &t, &blk))) break;
             first_tile = false;
             unsigned char *tile_sc = a.sc.base + (size_t)(k - a.k_begin) * a.sc.tile_bytes;
-            unsigned char *H1s = tile_sc, *Z2s = H1s + a.sc.arr_bytes, *Z1s = Z2s + a.sc.arr_bytes;
+            unsigned char *H1s = tile_sc, *H2s = H1s + a.sc.arr_bytes, *Z1s = H2s + a.sc.arr_bytes;
             unsigned char *Xh = Z1s + a.sc.arr_bytes, *Xl = Xh + a.sc.x_bytes;
             // ---- inputs of this thread's sample (part 0 owns the per-sample scalars)
             const int64_t j = (int64_t)blk * 128 + e;
             const bool valid = j < a.cnt[t];
-            float av[A], adv = 0.f, olp = 0.f;
-            int64_t n_own = 0;
-#pragma unroll
-            for (int jj = 0; jj < A; ++jj) av[jj] = 0.0f;
             if (part == 0) {
                 int64_t n = 0;
                 if (valid) n = a.perm[j];
-                n_own = n;
                 // every global load of the tile first (they are independent gathers, mostly HBM misses), THEN the
                 // stores: interleaved, the compiler must keep each load behind the previous scratch store (possible
                 // aliasing) and the tile start paid O serial DRAM latencies (measured 13-25k clocks per tile)
                 float x[O];
 #pragma unroll
                 for (int i = 0; i < O; ++i) x[i] = valid ? __ldg(a.obs + ((int64_t)t * O + i) * N + n) : 0.0f;
-                if (valid) {
-                    if (a.target != nullptr) {
-                        adv = __ldg(a.target + (int64_t)t * N + n);       // the regression target rides in `adv`
-                    } else if (a.forward_only) {
-                        if (a.act != nullptr) {
-#pragma unroll
-                            for (int jj = 0; jj < A; ++jj) av[jj] = __ldg(a.act + ((int64_t)t * A + jj) * N + n);
-                        }
-                    } else {
-#pragma unroll
-                        for (int jj = 0; jj < A; ++jj) av[jj] = __ldg(a.act + ((int64_t)t * A + jj) * N + n);
-                        adv = __ldg(a.adv + (int64_t)t * N + n);
-                        olp = __ldg(a.oldlp + (int64_t)t * N + n);
-                    }
-                }
-                // [x, 1] operand of kernel B: sub-block e/8, K-major [OKP rows][8 samples]
-                unsigned char *xh = Xh + (size_t)(e >> 3) * (OKP * 32), *xl = Xl + (size_t)(e >> 3) * (OKP * 32);
+                // Y = [x, 1, dmu] operand of kernel B: sub-block e/8, K-major [XKP rows][8 samples]; the dmu rows are
+                // filled in after the objective (epilogue 2a)
+                unsigned char *xh = Xh + (size_t)(e >> 3) * (XKP * 32), *xl = Xl + (size_t)(e >> 3) * (XKP * 32);
 #pragma unroll
                 for (int i = 0; i < O; ++i) {
                     const float xhi = tf32_hi(x[i]);
@@ -540,7 +542,7 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
                     *reinterpret_cast<float *>(xl + xo) = x[i] - xhi;
                 }
 #pragma unroll
-                for (int i = O; i < OKP; ++i) {
+                for (int i = O; i < XKP; ++i) {
                     const uint32_t xo = core_offset(8, i, e & 7);
                     *reinterpret_cast<float *>(xh + xo) = (i == O && valid) ? 1.0f : 0.0f;
                     *reinterpret_cast<float *>(xl + xo) = 0.0f;
@@ -556,20 +558,47 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
             uint32_t m1[NCH];
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
-                float z[32];
-                tmem_ld32(my_tm + TM_D + (uint32_t)(c0 + ch * 32), z);
                 uint32_t m = 0;
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) {
-                    z[jj] = valid ? act_fwd(z[jj], act_kind) : 0.0f;   // padding rows contribute nothing
-                    m |= (z[jj] > 0.0f ? 1u : 0u) << jj;
+                for (int hh = 0; hh < 2; ++hh) {
+                    float z[16];
+                    tmem_ld16(my_tm + TM_D + (uint32_t)(c0 + ch * 32 + hh * 16), z);
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) {
+                        z[jj] = valid ? act_fwd(z[jj], act_kind) : 0.0f;   // padding rows contribute nothing
+                        m |= (z[jj] > 0.0f ? 1u : 0u) << (hh * 16 + jj);
+                    }
+                    tcw_store16<W>(H1s, e, (c0 >> 5) + ch, hh, z);
+                    if (!deferred)
+                        tcw_tm16(z, my_tm + TM_AHI + acol0 + (uint32_t)(ch * 32 + hh * 16),
+                                 my_tm + TM_ALO + acol0 + (uint32_t)(ch * 32 + hh * 16));
                 }
                 m1[ch] = m;
-                const uint32_t th = my_tm + TM_AHI + acol0 + (uint32_t)(ch * 32), tl = my_tm + TM_ALO + acol0 + (uint32_t)(ch * 32);
-                if (deferred) tcw_emit32<W, false>(H1s, e, (c0 >> 5) + ch, z, th, tl);
-                else tcw_emit32<W, true>(H1s, e, (c0 >> 5) + ch, z, th, tl);
             }
-            finish_A(H1s);
+            finish_A(H1s, false);
+            // the per-sample scalars of the objective (action, advantage / regression target, old log-prob): gathered
+            // HERE, in the shadow of the forward GEMM, so that they do not occupy registers during epilogue 1
+            float av[A], adv = 0.f, olp = 0.f;
+            int64_t n_own = 0;
+#pragma unroll
+            for (int jj = 0; jj < A; ++jj) av[jj] = 0.0f;
+            if (part == 0 && valid) {
+                const int64_t n = a.perm[j];
+                n_own = n;
+                if (a.target != nullptr) {
+                    adv = __ldg(a.target + (int64_t)t * N + n);       // the regression target rides in `adv`
+                } else if (a.forward_only) {
+                    if (a.act != nullptr) {
+#pragma unroll
+                        for (int jj = 0; jj < A; ++jj) av[jj] = __ldg(a.act + ((int64_t)t * A + jj) * N + n);
+                    }
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < A; ++jj) av[jj] = __ldg(a.act + ((int64_t)t * A + jj) * N + n);
+                    adv = __ldg(a.adv + (int64_t)t * N + n);
+                    olp = __ldg(a.oldlp + (int64_t)t * N + n);
+                }
+            }
             mbar_wait(&bar_d, ph_d);
             ph_d ^= 1u;
             tc_fence_after();
@@ -579,14 +608,14 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
 #pragma unroll
                 for (int jj = 0; jj < A; ++jj) pm[jj] = 0.0f;
 #pragma unroll
-                for (int ch = 0; ch < NCH; ++ch) {
-                    float z[32];
-                    tmem_ld32(my_tm + TM_D + (uint32_t)(c0 + ch * 32), z);
+                for (int c16 = 0; c16 < 2 * NCH; ++c16) {
+                    float z[16];
+                    tmem_ld16(my_tm + TM_D + (uint32_t)(c0 + c16 * 16), z);
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) {
-                        const float h2 = act_fwd(z[jj] + b1[ch * 32 + jj], act_kind);
+                    for (int jj = 0; jj < 16; ++jj) {
+                        const float h2 = act_fwd(z[jj] + b1[c16 * 16 + jj], act_kind);
 #pragma unroll
-                        for (int o = 0; o < A; ++o) pm[o] = fmaf(h2, wo[o * W + ch * 32 + jj], pm[o]);
+                        for (int o = 0; o < A; ++o) pm[o] = fmaf(h2, wo[o * W + c16 * 16 + jj], pm[o]);
                     }
                 }
 #pragma unroll
@@ -621,8 +650,8 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
                     }
                 } else if (valid && a.target != nullptr) {
                     const float err = mu[0] - adv;                   // MSELoss(V, target), ppo.py:168-169
-                    s_obj += (double)err * err;
-                    s_cnt += 1.0;
+                    statS[0][e] += (double)err * err;
+                    statS[1][e] += 1.0;
                     dmu[0] = 2.0f * a.scale * err;
                     c_bo[0] += dmu[0];
                 } else if (valid) {
@@ -649,75 +678,74 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
                     }
 #pragma unroll
                     for (int jj = 0; jj < A; ++jj) dmu[jj] = dlp * (av[jj] - mu[jj]) * a.inv_var[jj];
-                    s_obj += (double)fminf(s1, s2) * a.scale + (double)a.kl_scale * eo * (olp - lp);
-                    s_cnt += 1.0; s_ratio += ratio; s_clip += in_range ? 0.0 : 1.0;
+                    statS[0][e] += (double)fminf(s1, s2) * a.scale + (double)a.kl_scale * eo * (olp - lp);
+                    statS[1][e] += 1.0; statS[2][e] += ratio; statS[3][e] += in_range ? 0.0 : 1.0;
 #pragma unroll
                     for (int jj = 0; jj < A; ++jj) c_bo[jj] += dmu[jj];
                 }
 #pragma unroll
                 for (int jj = 0; jj < A; ++jj) dmuS[jj][e] = dmu[jj];
+                if (!a.forward_only) {
+                    // dmu rows of Y (kernel B: dWo = H2^T . dmu on the tensor core)
+                    unsigned char *xh = Xh + (size_t)(e >> 3) * (XKP * 32), *xl = Xl + (size_t)(e >> 3) * (XKP * 32);
+#pragma unroll
+                    for (int jj = 0; jj < A; ++jj) {
+                        const uint32_t xo = core_offset(8, O + 1 + jj, e & 7);
+                        const float dh = tf32_hi(dmu[jj]);
+                        *reinterpret_cast<float *>(xh + xo) = dh;
+                        *reinterpret_cast<float *>(xl + xo) = dmu[jj] - dh;
+                    }
+                }
             }
             if (a.forward_only) {           // CTA-uniform: the next tile's L1 GEMM may overwrite D once everybody read it
                 tc_fence_before();
                 continue;
             }
             tcw_sync(q + 1, NP * 32);
-            // ---- epilogue 2b: dZ2 = (Wo^T dmu) * act'(H2); column sums for dWo, db1; scratch dZ2; A operand
+            // ---- epilogue 2b: H2 -> scratch (kernel B: dWo, and dZ2 rebuilt from it); dZ2 = (Wo^T dmu) * act'(H2) -> A operand
             {
-                float dmu[A];
 #pragma unroll
-                for (int jj = 0; jj < A; ++jj) dmu[jj] = dmuS[jj][e];
+                for (int jj = 0; jj < A; ++jj) dmu_own[jj] = dmuS[jj][e];
 #pragma unroll
-                for (int ch = 0; ch < NCH; ++ch) {
-                    float z[32];
-                    tmem_ld32(my_tm + TM_D + (uint32_t)(c0 + ch * 32), z);
-                    // column sums of dmu_j * H2 (dWo) first, then z becomes dZ2 in place
+                for (int c16 = 0; c16 < 2 * NCH; ++c16) {
+                    float z[16];
+                    tmem_ld16(my_tm + TM_D + (uint32_t)(c0 + c16 * 16), z);
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) z[jj] = act_fwd(z[jj] + b1[ch * 32 + jj], act_kind);
+                    for (int jj = 0; jj < 16; ++jj) z[jj] = act_fwd(z[jj] + b1[c16 * 16 + jj], act_kind);
+                    tcw_store16<W>(H2s, e, (c0 >> 5) + (c16 >> 1), c16 & 1, z);
+                    if (!deferred) {
 #pragma unroll
-                    for (int o = 0; o < A; ++o) {
-                        float v[32];
-#pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) v[jj] = dmu[o] * z[jj];
-                        c_wo[o][ch] += tcw_colsum32(v, lane);
+                        for (int jj = 0; jj < 16; ++jj) z[jj] = tcw_dz2<A>(z[jj], dmu_own, wo + c16 * 16 + jj, W, act_kind);
+                        tcw_tm16(z, my_tm + TM_AHI + acol0 + (uint32_t)(c16 * 16), my_tm + TM_ALO + acol0 + (uint32_t)(c16 * 16));
                     }
-#pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) {
-                        float g = 0.0f;
-#pragma unroll
-                        for (int o = 0; o < A; ++o) g = fmaf(dmu[o], wo[o * W + ch * 32 + jj], g);
-                        z[jj] = g * act_bwd_from_out(z[jj], act_kind);
-                    }
-                    const uint32_t th = my_tm + TM_AHI + acol0 + (uint32_t)(ch * 32), tl = my_tm + TM_ALO + acol0 + (uint32_t)(ch * 32);
-                    if (deferred) tcw_emit32<W, false>(Z2s, e, (c0 >> 5) + ch, z, th, tl);
-                    else tcw_emit32<W, true>(Z2s, e, (c0 >> 5) + ch, z, th, tl);
                 }
             }
-            finish_A(Z2s);
+            finish_A(H2s, true);
             mbar_wait(&bar_d, ph_d);
             ph_d ^= 1u;
             tc_fence_after();
             // ---- epilogue 3: dZ1 = D * act'(H1) -> scratch (kernel B turns it into dW0 / db0)
 #pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) {
-                float z[32];
-                tmem_ld32(my_tm + TM_D + (uint32_t)(c0 + ch * 32), z);
+            for (int c16 = 0; c16 < 2 * NCH; ++c16) {
+                const int ch = c16 >> 1, hh = c16 & 1;
+                float z[16];
+                tmem_ld16(my_tm + TM_D + (uint32_t)(c0 + c16 * 16), z);
                 if (RELU) {
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) z[jj] = ((m1[ch] >> jj) & 1u) ? z[jj] : 0.0f;
+                    for (int jj = 0; jj < 16; ++jj) z[jj] = ((m1[ch] >> (hh * 16 + jj)) & 1u) ? z[jj] : 0.0f;
                 } else {
                     // act'(H1) from the H1 this thread stored to the scratch
                     const int r = e & 7;
                     const unsigned char *ph = H1s + (size_t)(e >> 3) * (W / 32 * 1024) + (size_t)((c0 >> 5) + ch) * 1024 + (size_t)r * 128;
 #pragma unroll
-                    for (int c8 = 0; c8 < 4; ++c8) {
+                    for (int c8 = 0; c8 < 2; ++c8) {
                         float hv[8];
-                        ldg256(ph + (uint32_t)((c8 ^ (r & 3)) << 5), hv);
+                        ldg256(ph + (uint32_t)(((hh * 2 + c8) ^ (r & 3)) << 5), hv);
 #pragma unroll
                         for (int jj = 0; jj < 8; ++jj) z[8 * c8 + jj] *= act_bwd_from_out(hv[jj], act_kind);
                     }
                 }
-                tcw_emit32<W, false>(Z1s, e, (c0 >> 5) + ch, z, 0u, 0u);
+                tcw_store16<W>(Z1s, e, (c0 >> 5) + ch, hh, z);
             }
             tc_fence_before();
         }
@@ -725,19 +753,10 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
         // ---- this CTA's butterfly partials and statistics into its private gradient copy (accumulated)
         float *gp = a.gpart + (int64_t)blockIdx.x * a.lay.n_params;
         const int64_t f2 = a.lay.flat_w[2];
-        for (int qs = 0; qs < 4; ++qs) {
-            if (q == qs) {
-#pragma unroll
-                for (int ch = 0; ch < NCH; ++ch) {
-                    const int col = c0 + ch * 32 + lane;
-#pragma unroll
-                    for (int jj = 0; jj < A; ++jj) gp[f2 + (int64_t)jj * W + col] += c_wo[jj][ch];
-                }
-            }
-            asm volatile("bar.sync 8, %0;" ::"n"(NCT) : "memory");     // the 16 compute warps
-        }
         {
-            double v[4] = {s_obj, s_cnt, s_ratio, s_clip};
+            double v[4];
+#pragma unroll
+            for (int kq = 0; kq < 4; ++kq) v[kq] = part == 0 ? statS[kq][e] : 0.0;
 #pragma unroll
             for (int kq = 0; kq < 4; ++kq) {
                 for (int off = 16; off > 0; off >>= 1) v[kq] += __shfl_down_sync(0xffffffffu, v[kq], off);
@@ -773,21 +792,24 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
 
 // ============================================================================
 // kernel B: split-K weight-gradient GEMMs streamed from the scratch
-//   stage = one 8-sample sub-block: Z2h, Z2l (this half: 4 column blocks), H1h, H1l (all), Z1h, Z1l (this half), Xh, Xl
+//   stage = one 8-sample sub-block:
+//     H2h, H2l (this half: 4 column blocks) | Z2h, Z2l (rebuilt from H2 and dmu) | Z1h, Z1l (this half) | H1h, H1l (all) | Yh, Yl
 // ============================================================================
-template <int O, int W>
+template <int O, int A, int W>
 __global__ void __launch_bounds__(320, 1) update_tcw_wgrad_kernel(const __grid_constant__ TcwArgs a) {
     constexpr int NCV = 8;                         // converter warps (0..7); warp 8 = TMA producer, warp 9 = MMA issuer
-    constexpr int OKP = (O + 1 + 7) / 8 * 8;
-    constexpr uint32_t ZB = 4 * 1024, HB = W / 32 * 1024, XB = OKP * 32;        // bytes per stage piece
-    constexpr uint32_t STAGE = 4 * ZB + 2 * HB + 2 * XB;
+    constexpr int XKP = (O + 1 + A + 7) / 8 * 8;   // rows of Y = [x, 1, dmu, 0..]
+    constexpr uint32_t ZB = 4 * 1024, HB = W / 32 * 1024, XB = XKP * 32;        // bytes per stage piece
+    constexpr uint32_t OFF_Z2 = 2 * ZB, OFF_Z1 = 4 * ZB, OFF_H1 = 6 * ZB, OFF_X = 6 * ZB + 2 * HB;
+    constexpr uint32_t STAGE = 6 * ZB + 2 * HB + 2 * XB;
     constexpr uint32_t STAGE_AL = (STAGE + 1023) / 1024 * 1024;
     constexpr int NST = 5;
-    constexpr uint32_t TM_DW = 0u, TM_D0 = (uint32_t)W, TM_D1 = (uint32_t)W + 32u;
+    constexpr uint32_t TM_DW = 0u, TM_D0 = (uint32_t)W, TM_D1 = (uint32_t)W + 32u, TM_D2 = (uint32_t)W + 64u;
     if (a.k_begin + blockIdx.x >= a.tstart[a.T]) return;      // no live tile for this CTA in this batch (CTA-uniform)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[NST], conv_bar[NST], empty_bar[NST], done_bar;
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float WoS[A][128];    // Wo[:, this half's columns] (dZ2 = (Wo^T dmu) * act'(H2))
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
     if (threadIdx.x == 0) {
         for (int i = 0; i < NST; ++i) {
@@ -799,13 +821,15 @@ __global__ void __launch_bounds__(320, 1) update_tcw_wgrad_kernel(const __grid_c
         mbar_fence_init();
     }
     if (threadIdx.x < 32) tmem_alloc(&tmem_slot, 512);
+    const int half = a.half;
+    for (int i = threadIdx.x; i < A * 128; i += blockDim.x)
+        WoS[i / 128][i % 128] = a.params[a.lay.flat_w[2] + (int64_t)(i / 128) * W + half * 128 + (i % 128)];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t k_end = a.k_begin + a.k_count;
-    const int half = a.half;
     bool any = false;
     if (warp == NCV) {
         if (lane == 0) {
@@ -826,17 +850,17 @@ __global__ void __launch_bounds__(320, 1) update_tcw_wgrad_kernel(const __grid_c
                     unsigned char *dst = smem_raw + (size_t)st * STAGE_AL;
                     const size_t sbo = (size_t)sb * HB, ho = (size_t)half * ZB;
                     // fp32 rows land in the "hi" slots; the converter warps split them in place (hi) and into the lo slots
-                    tma_bulk_g2s(dst, arr[1] + sbo + ho, ZB, &full_bar[st]);                 // dZ2 (this half)
-                    tma_bulk_g2s(dst + 2 * ZB, arr[2] + sbo + ho, ZB, &full_bar[st]);        // dZ1 (this half)
-                    tma_bulk_g2s(dst + 4 * ZB, arr[0] + sbo, HB, &full_bar[st]);             // H1 (all columns)
-                    tma_bulk_g2s(dst + 4 * ZB + 2 * HB, Xh + (size_t)sb * XB, XB, &full_bar[st]);
-                    tma_bulk_g2s(dst + 4 * ZB + 2 * HB + XB, Xl + (size_t)sb * XB, XB, &full_bar[st]);
+                    tma_bulk_g2s(dst, arr[1] + sbo + ho, ZB, &full_bar[st]);                 // H2 (this half)
+                    tma_bulk_g2s(dst + OFF_Z1, arr[2] + sbo + ho, ZB, &full_bar[st]);        // dZ1 (this half)
+                    tma_bulk_g2s(dst + OFF_H1, arr[0] + sbo, HB, &full_bar[st]);             // H1 (all columns)
+                    tma_bulk_g2s(dst + OFF_X, Xh + (size_t)sb * XB, XB, &full_bar[st]);
+                    tma_bulk_g2s(dst + OFF_X + XB, Xl + (size_t)sb * XB, XB, &full_bar[st]);
                 }
             }
         }
     } else if (warp == NCV + 1) {
         const uint32_t idesc_w = umma_idesc_tf32(128, W, true, true);
-        const uint32_t idesc_x = umma_idesc_tf32(128, OKP, true, false);
+        const uint32_t idesc_x = umma_idesc_tf32(128, XKP, true, false);
         uint32_t gi = 0, first = 1u;
         int t = 0, blk = 0;
         bool first_tile = true;
@@ -850,8 +874,9 @@ __global__ void __launch_bounds__(320, 1) update_tcw_wgrad_kernel(const __grid_c
                     mbar_wait(&conv_bar[st], ph);             // landed AND split by the converter warps
                     tc_fence_after();
                     const uint32_t base = smem_u32(smem_raw) + st * STAGE_AL;
-                    const uint32_t z2h = base, z2l = base + ZB, z1h = base + 2 * ZB, z1l = base + 3 * ZB;
-                    const uint32_t h1h = base + 4 * ZB, h1l = h1h + HB, xh = h1l + HB, xl = xh + XB;
+                    const uint32_t h2h = base, h2l = base + ZB, z2h = base + OFF_Z2, z2l = z2h + ZB;
+                    const uint32_t z1h = base + OFF_Z1, z1l = z1h + ZB;
+                    const uint32_t h1h = base + OFF_H1, h1l = h1h + HB, xh = base + OFF_X, xl = xh + XB;
                     const uint32_t acc0 = first ? 0u : 1u;
                     // dW1[half] += dZ2^T . H1   (A, B MN-major: 8 reduction rows, 32-column blocks 1 KB apart)
                     umma_tf32(tmem + TM_DW, umma_desc_mn32(z2h, 1024u), umma_desc_mn32(h1h, 1024u), idesc_w, acc0);
@@ -861,9 +886,13 @@ __global__ void __launch_bounds__(320, 1) update_tcw_wgrad_kernel(const __grid_c
                     umma_tf32(tmem + TM_D0, umma_desc_mn32(z1h, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, acc0);
                     umma_tf32(tmem + TM_D0, umma_desc_mn32(z1h, 1024u), umma_operand_desc(xl, 8, false, 0), idesc_x, 1u);
                     umma_tf32(tmem + TM_D0, umma_desc_mn32(z1l, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, 1u);
-                    // db1[half] = column O of dZ2^T . [x, 1] (the ones column is exact in tf32: two passes)
+                    // db1[half] = column O of dZ2^T . Y (the ones column is exact in tf32: two passes)
                     umma_tf32(tmem + TM_D1, umma_desc_mn32(z2h, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, acc0);
                     umma_tf32(tmem + TM_D1, umma_desc_mn32(z2l, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, 1u);
+                    // dWo[:, half]^T = columns O+1 .. O+A of H2^T . Y
+                    umma_tf32(tmem + TM_D2, umma_desc_mn32(h2h, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, acc0);
+                    umma_tf32(tmem + TM_D2, umma_desc_mn32(h2h, 1024u), umma_operand_desc(xl, 8, false, 0), idesc_x, 1u);
+                    umma_tf32(tmem + TM_D2, umma_desc_mn32(h2l, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, 1u);
                     first = 0u;
                     umma_commit(&empty_bar[st]);
                 }
@@ -878,7 +907,8 @@ __global__ void __launch_bounds__(320, 1) update_tcw_wgrad_kernel(const __grid_c
         uint32_t gi = 0;
         int t = 0, blk = 0;
         bool first_tile = true;
-        constexpr int NF4 = (2 * ZB + HB) / 16;            // float4 items per stage: dZ2 | dZ1 | H1
+        constexpr int NF4 = (2 * ZB + HB) / 16;            // float4 items per stage: H2 (-> H2, dZ2) | dZ1 | H1
+        const int act_kind = a.lay.act;
         for (int64_t k = a.k_begin + blockIdx.x; k < k_end; k += gridDim.x) {
             if (!(first_tile ? tcw_tile_of(a.tstart, a.T, k, &t, &blk) : tcw_tile_next(a.tstart, a.T, k, &t, &blk))) break;
             first_tile = false;
@@ -889,17 +919,38 @@ __global__ void __launch_bounds__(320, 1) update_tcw_wgrad_kernel(const __grid_c
 #pragma unroll 2
                 for (int f = threadIdx.x; f < NF4; f += NCV * 32) {
                     const uint32_t b = (uint32_t)f * 16u;
-                    // slot of this item: dZ2 at 0 (lo at ZB), dZ1 at 2 ZB (lo at 3 ZB), H1 at 4 ZB (lo at 4 ZB + HB)
+                    // slot of this item: H2 at 0 (lo at ZB), dZ1 at OFF_Z1 (lo + ZB), H1 at OFF_H1 (lo + HB)
                     unsigned char *hp, *lp;
                     if (b < ZB) { hp = base + b; lp = hp + ZB; }
-                    else if (b < 2 * ZB) { hp = base + 2 * ZB + (b - ZB); lp = hp + ZB; }
-                    else { hp = base + 4 * ZB + (b - 2 * ZB); lp = hp + HB; }
+                    else if (b < 2 * ZB) { hp = base + OFF_Z1 + (b - ZB); lp = hp + ZB; }
+                    else { hp = base + OFF_H1 + (b - 2 * ZB); lp = hp + HB; }
                     const float4 v = *reinterpret_cast<const float4 *>(hp);
                     float4 h4, l4;
                     h4.x = tf32_hi(v.x); h4.y = tf32_hi(v.y); h4.z = tf32_hi(v.z); h4.w = tf32_hi(v.w);
                     l4.x = v.x - h4.x; l4.y = v.y - h4.y; l4.z = v.z - h4.z; l4.w = v.w - h4.w;
                     *reinterpret_cast<float4 *>(hp) = h4;
                     *reinterpret_cast<float4 *>(lp) = l4;
+                    if (b < ZB) {
+                        // the same four elements of dZ2 = (Wo^T dmu) * act'(H2): sample row r of the sub-block, columns
+                        // col .. col+3 of this half (inverse of the MN-major SW128_32B sub-block layout)
+                        const int r = (int)((b & 1023u) >> 7);
+                        const int col = (int)(b >> 10) * 32 + (int)((((b & 127u) >> 5) ^ (uint32_t)(r & 3)) << 3) + (int)((b & 31u) >> 2);
+                        float dmu[A];
+#pragma unroll
+                        for (int o = 0; o < A; ++o) {
+                            const uint32_t xo = OFF_X + core_offset(8, O + 1 + o, r);
+                            dmu[o] = *reinterpret_cast<const float *>(base + xo) + *reinterpret_cast<const float *>(base + xo + XB);
+                        }
+                        float4 d;
+                        d.x = tcw_dz2<A>(v.x, dmu, &WoS[0][col], 128, act_kind);
+                        d.y = tcw_dz2<A>(v.y, dmu, &WoS[0][col + 1], 128, act_kind);
+                        d.z = tcw_dz2<A>(v.z, dmu, &WoS[0][col + 2], 128, act_kind);
+                        d.w = tcw_dz2<A>(v.w, dmu, &WoS[0][col + 3], 128, act_kind);
+                        h4.x = tf32_hi(d.x); h4.y = tf32_hi(d.y); h4.z = tf32_hi(d.z); h4.w = tf32_hi(d.w);
+                        l4.x = d.x - h4.x; l4.y = d.y - h4.y; l4.z = d.z - h4.z; l4.w = d.w - h4.w;
+                        *reinterpret_cast<float4 *>(hp + OFF_Z2) = h4;
+                        *reinterpret_cast<float4 *>(hp + OFF_Z2 + ZB) = l4;
+                    }
                 }
                 fence_proxy_async();
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv_bar[st])) : "memory");
@@ -915,8 +966,8 @@ __global__ void __launch_bounds__(320, 1) update_tcw_wgrad_kernel(const __grid_c
         mbar_wait(&done_bar, 0);
         tc_fence_after();
         float *gp = a.gpart + (int64_t)blockIdx.x * a.lay.n_params;
-        const int64_t f0 = a.lay.flat_w[0], f1 = a.lay.flat_w[1];
-        const int row = half * 128 + warp * 32 + lane;       // out index (dW1) / hidden-1 index (dW0)
+        const int64_t f0 = a.lay.flat_w[0], f1 = a.lay.flat_w[1], f2 = a.lay.flat_w[2];
+        const int row = half * 128 + warp * 32 + lane;       // out index (dW1) / hidden-1 index (dW0) / hidden-2 index (dWo)
         const uint32_t my_tm = tmem + ((uint32_t)(warp * 32) << 16);
         for (int c = 0; c < W; c += 32) {
             float z[32];
@@ -932,6 +983,9 @@ __global__ void __launch_bounds__(320, 1) update_tcw_wgrad_kernel(const __grid_c
             gp[f0 + (int64_t)W * O + row] += z[O];
             tmem_ld32(my_tm + TM_D1, z);
             gp[f1 + (int64_t)W * W + row] += z[O];
+            tmem_ld32(my_tm + TM_D2, z);
+#pragma unroll
+            for (int o = 0; o < A; ++o) gp[f2 + (int64_t)o * W + row] += z[O + 1 + o];
         }
         tc_fence_before();
     }
@@ -945,14 +999,14 @@ __global__ void __launch_bounds__(320, 1) update_tcw_wgrad_kernel(const __grid_c
 // ============================================================================
 template <int O, int A, int W>
 static int launch_tcw(const TcwArgs &a0, int grid, int64_t total_upper, int64_t batch_tiles, cudaStream_t st) {
-    constexpr int OKP = (O + 1 + 7) / 8 * 8;
+    constexpr int OKP = (O + 1 + 7) / 8 * 8, XKP = (O + 1 + A + 7) / 8 * 8;
     const size_t smemA = (size_t)TCW_STAGES * W * 128 + (size_t)a0.lay.resident * 4 + 2 * (size_t)128 * OKP * 4;
-    constexpr uint32_t STAGE = 4 * 4096 + 2 * (W / 32 * 1024) + 2 * (OKP * 32);
+    constexpr uint32_t STAGE = 6 * 4096 + 2 * (W / 32 * 1024) + 2 * (XKP * 32);
     const size_t smemB = (size_t)5 * ((STAGE + 1023) / 1024 * 1024);
     constexpr int NP = W == 256 ? 4 : 2;      // measured: 4 threads per sample wins at 256, 2 at 128
     void (*kA)(const TcwArgs) = a0.lay.act == TG_ACT_RELU ? update_tcw_fwdbwd_kernel<O, A, true, W, NP>
                                                           : update_tcw_fwdbwd_kernel<O, A, false, W, NP>;
-    void (*kB)(const TcwArgs) = update_tcw_wgrad_kernel<O, W>;
+    void (*kB)(const TcwArgs) = update_tcw_wgrad_kernel<O, A, W>;
     TG_CUDA(cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
     TG_CUDA(cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
     for (int64_t k0 = 0; k0 < total_upper; k0 += batch_tiles) {
@@ -1000,7 +1054,7 @@ int tg_policy_grad_tcw(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, con
     if (rc) return rc;
     // per-tile scratch; batch = as many tiles as fit the budget (a multiple of the grid)
     a.sc.arr_bytes = (int64_t)16 * (W / 32) * 1024;
-    a.sc.x_bytes = (int64_t)16 * a.lay.OKP * 32;
+    a.sc.x_bytes = (int64_t)16 * ((O + 1 + A + 7) / 8 * 8) * 32;
     a.sc.tile_bytes = 3 * a.sc.arr_bytes + 2 * a.sc.x_bytes;
     const int64_t NB = (N + 127) / 128;
     const int64_t total_upper = NB * T;                       // live tiles <= this
@@ -1018,6 +1072,7 @@ int tg_policy_grad_tcw(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, con
     a.N = N; a.T = T; a.obs = obs; a.act = act; a.adv = adv; a.oldlp = old_logp; a.target = target;
     a.perm = ctx->perm; a.cnt = ctx->cnt; a.tstart = tstart;
     a.packed = ctx->packed_tc;
+    a.params = params;
     for (int j = 0; j < TG_MAX_ACT; ++j) { a.inv_sd[j] = inv_sd ? inv_sd[j] : 1.0f; a.inv_var[j] = inv_var ? inv_var[j] : 1.0f; }
     a.log_norm = log_norm; a.eps_clip = eps_clip; a.scale = scale; a.kl_scale = kl_scale;
     a.gpart = gpart; a.spart = spart;
@@ -1040,9 +1095,9 @@ extern "C" int tg_policy_grad_scratch_bytes(const tg_ctx *ctx, const tg_mlp_cfg 
     if (!tg_update_tcw_shape_built(mlp) || ctx->math_mode == TG_MATH_FP32) return TG_OK;
     TcwLayout L;
     build_tcw_layout(mlp, &L);
-    const int64_t arr = (int64_t)16 * (L.W / 32) * 1024, xb = (int64_t)16 * L.OKP * 32;
-    *bytes_written = n_tiles * (3 * arr + 2 * xb);                       // kernel A: H1, dZ2, dZ1 (fp32) + [x,1] hi/lo
-    // kernel B, one launch per 128-row half of the outputs: its half of dZ2 and dZ1, all of H1, [x,1] hi/lo
+    const int64_t arr = (int64_t)16 * (L.W / 32) * 1024, xb = (int64_t)16 * ((L.O + 1 + L.A + 7) / 8 * 8) * 32;
+    *bytes_written = n_tiles * (3 * arr + 2 * xb);                       // kernel A: H1, H2, dZ1 (fp32) + [x,1,dmu] hi/lo
+    // kernel B, one launch per 128-row half of the outputs: its half of H2 and dZ1, all of H1, [x,1,dmu] hi/lo
     const int64_t halves = L.W / 128;
     *bytes_read = n_tiles * halves * (2 * (arr / halves) + arr + 2 * xb);
     if (halves == 2) *bytes_read += n_tiles * arr;                       // kernel A: K-half-1 threads reload H1 / dZ2 halves

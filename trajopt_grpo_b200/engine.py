@@ -458,3 +458,93 @@ def export_trajectory(obs, act, length):
         L.check(rc, "tg_export_trajectory")
         _count(1)
     return ids, rows
+
+
+class _DevMem:
+    """A window of C-allocated device memory exposed to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class PeerComm:
+    """tg_comm_*: this rank's gradient window + its peers', for tg_allreduce_adam_step.
+
+    Built collectively by all ranks of an initialised torch.distributed process group (the IPC handles travel through
+    all_gather_object).  `grad_slot()` is a torch view of the slot the next step will sum -- pass it as `out_grad` to
+    policy_grad / value_grad so the gradient is produced in place."""
+
+    def __init__(self, n_floats: int, device=None):
+        import torch.distributed as dist
+        lib = L.load()
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.rank, self.world, self.n = dist.get_rank(), dist.get_world_size(), int(n_floats)
+        hb = lib.tg_comm_handle_bytes()
+        handle = C.create_string_buffer(hb)
+        self._h = L._vp()
+        err = None
+        with torch.cuda.device(self.dev):
+            rc = lib.tg_comm_create(L.ctx(self.dev), self.rank, self.world, self.n, C.byref(self._h), handle)
+        if rc != 0:
+            err = "tg_comm_create: " + lib.tg_last_error().decode(errors="replace")
+            self._h = None
+        allh = [None] * self.world                       # every rank takes part in both exchanges, failed or not
+        dist.all_gather_object(allh, (err, bytes(handle.raw)))
+        if all(a[0] is None for a in allh):
+            blob = C.create_string_buffer(b"".join(a[1] for a in allh), hb * self.world)
+            with torch.cuda.device(self.dev):
+                rc = lib.tg_comm_connect(self._h, blob)
+            if rc != 0:
+                err = "tg_comm_connect: " + lib.tg_last_error().decode(errors="replace")
+        else:
+            err = err or next(a[0] for a in allh if a[0] is not None)
+        errs = [None] * self.world
+        dist.all_gather_object(errs, err)
+        bad = next((x for x in errs if x is not None), None)
+        if bad is not None:
+            self.close()
+            raise L.EngineError("peer-memory gradient window unavailable: " + bad)
+
+    @staticmethod
+    def try_create(n_floats: int, device=None):
+        """Collective constructor that cannot leave the ranks disagreeing: every rank reports whether its window
+        was created and mapped; unless ALL succeeded, every rank drops its window and None is returned (the caller
+        then uses the NCCL allreduce)."""
+        import torch.distributed as dist
+        comm, err = None, None
+        try:
+            comm = PeerComm(n_floats, device)
+        except Exception as ex:  # noqa: BLE001  (EngineError: no P2P access, IPC refused, ...)
+            err = repr(ex)
+        oks = [None] * dist.get_world_size()
+        dist.all_gather_object(oks, err)
+        if any(o is not None for o in oks):
+            if comm is not None:
+                comm.close()
+            PeerComm.last_failure = next(o for o in oks if o is not None)
+            return None
+        return comm
+
+    last_failure = None
+
+    def grad_slot(self) -> torch.Tensor:
+        p = L._vp()
+        L.check(L.load().tg_comm_grad_slot(self._h, C.byref(p)), "tg_comm_grad_slot")
+        return torch.as_tensor(_DevMem(p.value, self.n), device=self.dev)
+
+    def allreduce_adam_step(self, params, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, out_sum=None):
+        lib = L.load()
+        n = params.numel()
+        for t, nm in ((params, "params"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+            _need(t, torch.float32, nm, (n,))
+        with torch.cuda.device(self.dev):
+            rc = lib.tg_allreduce_adam_step(L.ctx(self.dev), self._h, n, L.ptr(params), L.ptr(exp_avg), L.ptr(exp_avg_sq),
+                                            int(step), float(lr), float(beta1), float(beta2), float(eps), L.ptr(out_sum),
+                                            L.stream_ptr())
+        L.check(rc, "tg_allreduce_adam_step")
+        _count(2)
+
+    def close(self):
+        if self._h:
+            L.load().tg_comm_destroy(self._h)
+            self._h = None
