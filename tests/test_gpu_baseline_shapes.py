@@ -25,9 +25,10 @@ pytestmark = pytest.mark.gpu
 
 NEW_ROLLOUTS = ["cartpole_cfg1", "quadpole2d_w128", "quadpole_w256", "pendulum_h1", "cartpole_h3", "pendulum_h0",
                 "cartpole_tanh", "pendulum_mixed_act"]
-# max |g_kernel - g_float64| / max |g_float64|: measured on B200 2.1e-7 .. 8.6e-7 for every width and both
-# arithmetic modes (gpurun_out/r2a_pytest_gpu.log, profiles/README_r2.md); bound with a 6x margin
-GRAD_TOL_F64 = 5e-6
+# max |g_kernel - g_float64| / max |g_float64| measured on B200 (profiles/README_r2.md): FP32 pipe 2.1e-7 .. 8.6e-7 for
+# every width; 3xTF32 tensor cores 1.2e-6 (width 128) and 2.6e-6 (width 256: the weight-gradient operands use the
+# truncating hi/lo split).  Bounds with a 4-6x margin:
+GRAD_TOL_F64 = {"fp32": 5e-6, "3xtf32": 1e-5}
 KINK = 2e-6        # oracle/make_golden.py KINK_MARGIN
 
 
@@ -197,7 +198,7 @@ def test_grpo_gradient_matches_reference_and_float64_oracle(E, golden_dir, name,
                 assert np.abs(part - r).max() <= 3e-4 * max(np.abs(r).max(), 1e-6) + 1e-5, (mode, i)
         record_property(f"grad_err_vs_f64_{mode}", e64)
         print(f"[grad-parity] {name:22s} width {width:3d} {mode:7s} vs float64 oracle {e64:.2e}  vs reference fp32 {e32:.2e}")
-        assert e64 <= GRAD_TOL_F64, (mode, e64)
+        assert e64 <= GRAD_TOL_F64[mode], (mode, e64)
 
 
 @pytest.mark.parametrize("name", NEW_ROLLOUTS)

@@ -12,21 +12,23 @@
 //       tensor core too (obs hi/lo + ones column carrying the bias).  Per tile the kernel leaves in an HBM
 //       scratch, in the operand layout of kernel B:  H1, H2, dZ1 as fp32 (MN-major SW128_32B, 8-sample
 //       sub-blocks) and Y = [x, 1, dmu] hi/lo (K-major).  No column sums over samples are left in this kernel:
-//       round 1 computed dWo = dmu^T . H2 with register butterflies here (40 k of ~100 k clocks per tile at
-//       W = 256, and the reason for its spills); dWo is now one more small GEMM of kernel B.
+//       round 1 computed dWo = dmu^T . H2 with register butterflies here (187 us of 847 us per 2656-tile batch at
+//       W = 256); dWo is now one more small GEMM of kernel B.
 //   kernel B  (update_tcw_wgrad_kernel)   split-K weight-gradient GEMMs over the batch's samples:
 //       dW1[half] += dZ2[:, half]^T . H1,   [dW0 | db0][half] += dZ1[:, half]^T . Y,   db1[half] = (dZ2[:, half]^T . Y)[:, ones],
 //       dWo[:, half]^T = (H2[:, half]^T . Y)[:, dmu columns],
 //       operands streamed from the scratch by TMA (8 samples per stage); dZ2 is not stored: the converter warps
 //       rebuild it from H2 and dmu, dZ2 = (Wo^T dmu) * act'(H2), with the operation order of kernel A, while they
-//       split the fp32 rows into tf32 hi/lo.  Accumulators persistent in tensor memory for all tiles of the
-//       launch, added to the CTA-private gradient copy at the end.  One launch per 128-row half of the outputs
-//       (two at W = 256).
+//       produce the tf32 lo parts (the fp32 rows themselves serve as the hi operands: the tensor core drops the low
+//       13 bits).  Accumulators persistent in tensor memory for all tiles of the launch, added to the CTA-private
+//       gradient copy at the end.  One launch per 128-row half of the outputs (two at W = 256).  Bound by the
+//       converter warps (8 -> 12 -> 16 warps: 293 -> 267 -> 241 us per launch at W = 256).
 //
 // Tiles are enumerated in length order (tg_order.cu): tile k of the compact list is (step t, sorted
 // positions 128*blk ..), found by binary search in the per-step prefix of live tiles; k beyond the live
 // total is a no-op, so the host launches ceil(upper bound / batch) batches without reading anything back.
 #include <math.h>
+#include <stdlib.h>
 
 #include "tg_umma.cuh"
 
@@ -111,6 +113,9 @@ static void build_tcw_layout(const tg_mlp_cfg *mlp, TcwLayout *L) {
     }
     L->n_params = flat;
 }
+
+// the value the tensor core uses for a raw fp32 operand of kind::tf32: the low 13 mantissa bits dropped
+TG_D float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 TG_D float tcw_hi(float w) {
     uint32_t hb;
@@ -212,8 +217,30 @@ TG_D bool tcw_tile_next(const int64_t *__restrict__ tstart, int T, int64_t k, in
     return true;
 }
 
+struct TrueTag { static constexpr bool value = true; };
+struct FalseTag { static constexpr bool value = false; };
+
 TG_D void tcw_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 TG_D void tcw_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// butterfly column sum: v[0..32) per lane -> the warp's sum over its 32 lanes of entry `lane`
+template <int HALF, int OFF> TG_D void tcw_colsum_step(float *v, int lane) {
+    const bool up = (lane & OFF) != 0;
+#pragma unroll
+    for (int j = 0; j < HALF; ++j) {
+        const float send = up ? v[j] : v[j + HALF];
+        const float keep = up ? v[j + HALF] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+    }
+}
+TG_D float tcw_colsum32(float *v, int lane) {
+    tcw_colsum_step<16, 16>(v, lane);
+    tcw_colsum_step<8, 8>(v, lane);
+    tcw_colsum_step<4, 4>(v, lane);
+    tcw_colsum_step<2, 2>(v, lane);
+    tcw_colsum_step<1, 1>(v, lane);
+    return v[0];
+}
 
 // byte offset of (sample s, column c) inside one MN-major scratch array of a tile (8-sample sub-blocks)
 template <int W> TG_D uint32_t tcw_sc_off(int s, int c) {
@@ -270,13 +297,11 @@ TG_D void tcw_store16(unsigned char *arr, int s, int cbk, int hh, const float *v
     for (int c8 = 0; c8 < 2; ++c8) stg256(p + (uint32_t)(((hh * 2 + c8) ^ (r & 3)) << 5), v + 8 * c8);
 }
 TG_D void tcw_tm16(const float *v, uint32_t tm_hi, uint32_t tm_lo) {
-    float hi[16], lo[16];
+    // the raw fp32 value is the hi operand (the tensor core drops its low 13 bits), lo = x - trunc(x)
+    float lo[16];
 #pragma unroll
-    for (int jj = 0; jj < 16; ++jj) {
-        hi[jj] = tf32_hi(v[jj]);
-        lo[jj] = v[jj] - hi[jj];
-    }
-    tmem_st16(tm_hi, hi);
+    for (int jj = 0; jj < 16; ++jj) lo[jj] = v[jj] - tf32_trunc(v[jj]);
+    tmem_st16(tm_hi, v);
     tmem_st16(tm_lo, lo);
 }
 // dZ2 = (Wo^T dmu) * act'(H2) for one column: the ONE definition both kernels use (kernel A for the A operand of the
@@ -555,26 +580,33 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
             ph_d ^= 1u;
             tc_fence_after();
             // ---- epilogue 1: H1 = act(D) (bias folded); scratch H1 hi/lo; act'(H1) mask; A operand
+            // (`deferred` is warp-uniform; the two variants are separate straight-line loops -- with the branch inside
+            // the unrolled body ptxas kept both paths' values alive and spilled the tile to local memory)
             uint32_t m1[NCH];
+            auto epi1 = [&](auto tm_tag) {
+                constexpr bool TM = decltype(tm_tag)::value;
 #pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) {
-                uint32_t m = 0;
+                for (int ch = 0; ch < NCH; ++ch) {
+                    uint32_t m = 0;
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    float z[16];
-                    tmem_ld16(my_tm + TM_D + (uint32_t)(c0 + ch * 32 + hh * 16), z);
+                    for (int hh = 0; hh < 2; ++hh) {
+                        float z[16];
+                        tmem_ld16(my_tm + TM_D + (uint32_t)(c0 + ch * 32 + hh * 16), z);
 #pragma unroll
-                    for (int jj = 0; jj < 16; ++jj) {
-                        z[jj] = valid ? act_fwd(z[jj], act_kind) : 0.0f;   // padding rows contribute nothing
-                        m |= (z[jj] > 0.0f ? 1u : 0u) << (hh * 16 + jj);
+                        for (int jj = 0; jj < 16; ++jj) {
+                            z[jj] = valid ? act_fwd(z[jj], act_kind) : 0.0f;   // padding rows contribute nothing
+                            m |= (z[jj] > 0.0f ? 1u : 0u) << (hh * 16 + jj);
+                        }
+                        tcw_store16<W>(H1s, e, (c0 >> 5) + ch, hh, z);
+                        if (TM)
+                            tcw_tm16(z, my_tm + TM_AHI + acol0 + (uint32_t)(ch * 32 + hh * 16),
+                                     my_tm + TM_ALO + acol0 + (uint32_t)(ch * 32 + hh * 16));
                     }
-                    tcw_store16<W>(H1s, e, (c0 >> 5) + ch, hh, z);
-                    if (!deferred)
-                        tcw_tm16(z, my_tm + TM_AHI + acol0 + (uint32_t)(ch * 32 + hh * 16),
-                                 my_tm + TM_ALO + acol0 + (uint32_t)(ch * 32 + hh * 16));
+                    m1[ch] = m;
                 }
-                m1[ch] = m;
-            }
+            };
+            if (deferred) epi1(FalseTag{});
+            else epi1(TrueTag{});
             finish_A(H1s, false);
             // the per-sample scalars of the objective (action, advantage / regression target, old log-prob): gathered
             // HERE, in the shadow of the forward GEMM, so that they do not occupy registers during epilogue 1
@@ -702,23 +734,28 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
                 continue;
             }
             tcw_sync(q + 1, NP * 32);
-            // ---- epilogue 2b: H2 -> scratch (kernel B: dWo, and dZ2 rebuilt from it); dZ2 = (Wo^T dmu) * act'(H2) -> A operand
+            // ---- epilogue 2b: column sums for dWo (butterflies); dZ2 = (Wo^T dmu) * act'(H2) -> scratch and A operand
             {
 #pragma unroll
                 for (int jj = 0; jj < A; ++jj) dmu_own[jj] = dmuS[jj][e];
+                auto epi2b = [&](auto tm_tag) {
+                    constexpr bool TM = decltype(tm_tag)::value;
 #pragma unroll
-                for (int c16 = 0; c16 < 2 * NCH; ++c16) {
-                    float z[16];
-                    tmem_ld16(my_tm + TM_D + (uint32_t)(c0 + c16 * 16), z);
+                    for (int c16 = 0; c16 < 2 * NCH; ++c16) {
+                        float z[16];
+                        tmem_ld16(my_tm + TM_D + (uint32_t)(c0 + c16 * 16), z);
 #pragma unroll
-                    for (int jj = 0; jj < 16; ++jj) z[jj] = act_fwd(z[jj] + b1[c16 * 16 + jj], act_kind);
-                    tcw_store16<W>(H2s, e, (c0 >> 5) + (c16 >> 1), c16 & 1, z);
-                    if (!deferred) {
+                        for (int jj = 0; jj < 16; ++jj) z[jj] = act_fwd(z[jj] + b1[c16 * 16 + jj], act_kind);
+                        tcw_store16<W>(H2s, e, (c0 >> 5) + (c16 >> 1), c16 & 1, z);
+                        if (TM) {
 #pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) z[jj] = tcw_dz2<A>(z[jj], dmu_own, wo + c16 * 16 + jj, W, act_kind);
-                        tcw_tm16(z, my_tm + TM_AHI + acol0 + (uint32_t)(c16 * 16), my_tm + TM_ALO + acol0 + (uint32_t)(c16 * 16));
+                            for (int jj = 0; jj < 16; ++jj) z[jj] = tcw_dz2<A>(z[jj], dmu_own, wo + c16 * 16 + jj, W, act_kind);
+                            tcw_tm16(z, my_tm + TM_AHI + acol0 + (uint32_t)(c16 * 16), my_tm + TM_ALO + acol0 + (uint32_t)(c16 * 16));
+                        }
                     }
-                }
+                };
+                if (deferred) epi2b(FalseTag{});
+                else epi2b(TrueTag{});
             }
             finish_A(H2s, true);
             mbar_wait(&bar_d, ph_d);
@@ -795,9 +832,12 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
 //   stage = one 8-sample sub-block:
 //     H2h, H2l (this half: 4 column blocks) | Z2h, Z2l (rebuilt from H2 and dmu) | Z1h, Z1l (this half) | H1h, H1l (all) | Yh, Yl
 // ============================================================================
-template <int O, int A, int W>
-__global__ void __launch_bounds__(320, 1) update_tcw_wgrad_kernel(const __grid_constant__ TcwArgs a) {
-    constexpr int NCV = 8;                         // converter warps (0..7); warp 8 = TMA producer, warp 9 = MMA issuer
+// NCV converter warps (0 .. NCV-1); warp NCV = TMA producer, warp NCV+1 = MMA issuer.
+// TRUNC: the fp32 rows stay in place as the "hi" operand -- the tensor core reads only the top 19 bits of a tf32
+// operand, i.e. it uses trunc(x) -- and the converter writes only lo = x - trunc(x) (one store and four cvt fewer per
+// float4 than the round-to-nearest split, whose hi has to be written back).
+template <int O, int A, int W, int NCV, bool TRUNC>
+__global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(const __grid_constant__ TcwArgs a) {
     constexpr int XKP = (O + 1 + A + 7) / 8 * 8;   // rows of Y = [x, 1, dmu, 0..]
     constexpr uint32_t ZB = 4 * 1024, HB = W / 32 * 1024, XB = XKP * 32;        // bytes per stage piece
     constexpr uint32_t OFF_Z2 = 2 * ZB, OFF_Z1 = 4 * ZB, OFF_H1 = 6 * ZB, OFF_X = 6 * ZB + 2 * HB;
@@ -926,9 +966,13 @@ __global__ void __launch_bounds__(320, 1) update_tcw_wgrad_kernel(const __grid_c
                     else { hp = base + OFF_H1 + (b - 2 * ZB); lp = hp + HB; }
                     const float4 v = *reinterpret_cast<const float4 *>(hp);
                     float4 h4, l4;
-                    h4.x = tf32_hi(v.x); h4.y = tf32_hi(v.y); h4.z = tf32_hi(v.z); h4.w = tf32_hi(v.w);
+                    if (TRUNC) {
+                        h4.x = tf32_trunc(v.x); h4.y = tf32_trunc(v.y); h4.z = tf32_trunc(v.z); h4.w = tf32_trunc(v.w);
+                    } else {
+                        h4.x = tf32_hi(v.x); h4.y = tf32_hi(v.y); h4.z = tf32_hi(v.z); h4.w = tf32_hi(v.w);
+                    }
                     l4.x = v.x - h4.x; l4.y = v.y - h4.y; l4.z = v.z - h4.z; l4.w = v.w - h4.w;
-                    *reinterpret_cast<float4 *>(hp) = h4;
+                    if (!TRUNC) *reinterpret_cast<float4 *>(hp) = h4;
                     *reinterpret_cast<float4 *>(lp) = l4;
                     if (b < ZB) {
                         // the same four elements of dZ2 = (Wo^T dmu) * act'(H2): sample row r of the sub-block, columns
@@ -946,9 +990,13 @@ __global__ void __launch_bounds__(320, 1) update_tcw_wgrad_kernel(const __grid_c
                         d.y = tcw_dz2<A>(v.y, dmu, &WoS[0][col + 1], 128, act_kind);
                         d.z = tcw_dz2<A>(v.z, dmu, &WoS[0][col + 2], 128, act_kind);
                         d.w = tcw_dz2<A>(v.w, dmu, &WoS[0][col + 3], 128, act_kind);
-                        h4.x = tf32_hi(d.x); h4.y = tf32_hi(d.y); h4.z = tf32_hi(d.z); h4.w = tf32_hi(d.w);
+                        if (TRUNC) {
+                            h4.x = tf32_trunc(d.x); h4.y = tf32_trunc(d.y); h4.z = tf32_trunc(d.z); h4.w = tf32_trunc(d.w);
+                        } else {
+                            h4.x = tf32_hi(d.x); h4.y = tf32_hi(d.y); h4.z = tf32_hi(d.z); h4.w = tf32_hi(d.w);
+                        }
                         l4.x = d.x - h4.x; l4.y = d.y - h4.y; l4.z = d.z - h4.z; l4.w = d.w - h4.w;
-                        *reinterpret_cast<float4 *>(hp + OFF_Z2) = h4;
+                        *reinterpret_cast<float4 *>(hp + OFF_Z2) = TRUNC ? d : h4;
                         *reinterpret_cast<float4 *>(hp + OFF_Z2 + ZB) = l4;
                     }
                 }
@@ -997,16 +1045,19 @@ __global__ void __launch_bounds__(320, 1) update_tcw_wgrad_kernel(const __grid_c
 // ============================================================================
 // host side
 // ============================================================================
-template <int O, int A, int W>
-static int launch_tcw(const TcwArgs &a0, int grid, int64_t total_upper, int64_t batch_tiles, cudaStream_t st) {
+template <int O, int A, int W, int NP>
+static int launch_tcw_np(const TcwArgs &a0, int grid, int64_t total_upper, int64_t batch_tiles, cudaStream_t st) {
     constexpr int OKP = (O + 1 + 7) / 8 * 8, XKP = (O + 1 + A + 7) / 8 * 8;
     const size_t smemA = (size_t)TCW_STAGES * W * 128 + (size_t)a0.lay.resident * 4 + 2 * (size_t)128 * OKP * 4;
     constexpr uint32_t STAGE = 6 * 4096 + 2 * (W / 32 * 1024) + 2 * (XKP * 32);
     const size_t smemB = (size_t)5 * ((STAGE + 1023) / 1024 * 1024);
-    constexpr int NP = W == 256 ? 4 : 2;      // measured: 4 threads per sample wins at 256, 2 at 128
     void (*kA)(const TcwArgs) = a0.lay.act == TG_ACT_RELU ? update_tcw_fwdbwd_kernel<O, A, true, W, NP>
                                                           : update_tcw_fwdbwd_kernel<O, A, false, W, NP>;
-    void (*kB)(const TcwArgs) = update_tcw_wgrad_kernel<O, A, W>;
+    // converter warps of kernel B: measured on B200 (profiles/README_r2.md) 8 / 12 / 16 warps = 293 / 267 / 241 us per
+    // launch at W = 256 and 12 <= 16 at W = 128
+    constexpr int NCV = W == 256 ? 16 : 12;
+    void (*kB)(const TcwArgs) = update_tcw_wgrad_kernel<O, A, W, NCV, true>;
+    const int threadsB = (NCV + 2) * 32;
     TG_CUDA(cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
     TG_CUDA(cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
     for (int64_t k0 = 0; k0 < total_upper; k0 += batch_tiles) {
@@ -1016,11 +1067,18 @@ static int launch_tcw(const TcwArgs &a0, int grid, int64_t total_upper, int64_t 
         kA<<<grid, NP * 128 + 64, smemA, st>>>(a);
         for (int half = 0; half < (a.forward_only ? 0 : W / 128); ++half) {
             a.half = half;
-            kB<<<grid, 320, smemB, st>>>(a);
+            kB<<<grid, threadsB, smemB, st>>>(a);
         }
     }
     TG_CUDA(cudaGetLastError());
     return TG_OK;
+}
+
+// threads per sample in kernel A: 2 at W = 128 (8 + 2 warps, 168 registers); 4 at W = 256 (16 + 2 warps, 96 registers:
+// measured 660 us per batch against 1041 us with 2 threads per sample, profiles/README_r2.md)
+template <int O, int A, int W>
+static int launch_tcw(const TcwArgs &a0, int grid, int64_t total_upper, int64_t batch_tiles, cudaStream_t st) {
+    return launch_tcw_np<O, A, W, (W == 256 ? 4 : 2)>(a0, grid, total_upper, batch_tiles, st);
 }
 
 static int reserve_bytes(void **p, size_t *cap, size_t bytes) {
