@@ -242,8 +242,9 @@ def test_value_grad_wide_tensor_core_path_matches_fp32_path(O, width, act_name):
 
 
 def test_wide_update_spans_several_scratch_batches():
-    """The streamed 128-wide update at a size whose tiles do not fit one 1 GB scratch batch (6,400 tiles of
-    198 KB), ragged lengths: gradient and statistics vs the FP32-pipe kernel, and run-to-run determinism."""
+    """The streamed 128-wide update at a size whose tiles do not fit one scratch batch (6,400 tiles of ~200 KB
+    against a 256 MB budget set through TG_TCW_SCRATCH_MB: five batches), ragged lengths: gradient and statistics vs
+    the FP32-pipe kernel, and run-to-run determinism."""
     from trajopt_grpo_b200 import engine as E
     rng = np.random.default_rng(77)
     O, A, W = 10, 2, 128
@@ -256,6 +257,8 @@ def test_wide_update_spans_several_scratch_batches():
     adv = torch.randn((T, N), device="cuda", generator=gen)
     olp = -1.5 + 0.1 * torch.randn((T, N), device="cuda", generator=gen)
     ln = torch.randint(1, T + 1, (N,), device="cuda", generator=gen, dtype=torch.int32)
+    import os
+    os.environ["TG_TCW_SCRATCH_MB"] = "256"
     out = {}
     try:
         for mode in ("fp32", "3xtf32", "3xtf32"):
@@ -264,6 +267,7 @@ def test_wide_update_spans_several_scratch_batches():
             torch.cuda.synchronize()
             out.setdefault(mode, []).append((g.clone(), st.clone()))
     finally:
+        os.environ.pop("TG_TCW_SCRATCH_MB", None)
         E.set_math("auto")
     (g1, s1), (g2, s2) = out["3xtf32"]
     assert torch.equal(g1, g2) and torch.equal(s1, s2)            # deterministic

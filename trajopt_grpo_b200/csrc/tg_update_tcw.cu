@@ -1116,7 +1116,11 @@ int tg_policy_grad_tcw(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, con
     a.sc.tile_bytes = 3 * a.sc.arr_bytes + 2 * a.sc.x_bytes;
     const int64_t NB = (N + 127) / 128;
     const int64_t total_upper = NB * T;                       // live tiles <= this
-    const int64_t budget = (int64_t)1 << 30;
+    // 4 GB: one batch = ~10,600 tiles at W = 256; per-batch fixed costs (3 launches, weight staging, 290 KB gradient
+    // read-modify-write per CTA and launch) fall below 1 %.  TG_TCW_SCRATCH_MB overrides it (tests use a small budget
+    // to cover the multi-batch path at small shapes)
+    const char *budget_env = getenv("TG_TCW_SCRATCH_MB");
+    const int64_t budget = budget_env ? ((int64_t)atoll(budget_env) << 20) : ((int64_t)4 << 30);
     int64_t batch_tiles = budget / a.sc.tile_bytes / grid * grid;
     if (batch_tiles < grid) batch_tiles = grid;
     if (batch_tiles > total_upper) batch_tiles = (total_upper + grid - 1) / grid * grid;
