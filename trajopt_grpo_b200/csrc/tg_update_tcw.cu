@@ -956,8 +956,13 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
                 const uint32_t st = gi % NST, ph = (gi / NST) & 1u;
                 mbar_wait(&full_bar[st], ph);
                 unsigned char *base = smem_raw + (size_t)st * STAGE_AL;
+                // item assignment: the 256 items of the H2 piece are the expensive ones (they also rebuild dZ2), one per
+                // thread of warps 0..7; the plain items (dZ1, H1) are spread over the remaining converter warps
+                constexpr int NH2 = (int)(ZB / 16), NREST = NCV * 32 - NH2;
+                static_assert(NREST > 0, "converter warps");
 #pragma unroll 2
-                for (int f = threadIdx.x; f < NF4; f += NCV * 32) {
+                for (int f = (int)threadIdx.x < NH2 ? (int)threadIdx.x : NH2 + ((int)threadIdx.x - NH2); f < NF4;
+                     f += ((int)threadIdx.x < NH2 ? NF4 : NREST)) {
                     const uint32_t b = (uint32_t)f * 16u;
                     // slot of this item: H2 at 0 (lo at ZB), dZ1 at OFF_Z1 (lo + ZB), H1 at OFF_H1 (lo + HB)
                     unsigned char *hp, *lp;
