@@ -51,15 +51,22 @@ WORKLOADS = {
     # BASELINE configs[0]
     "cartpole": dict(kind=0, cls="CartPole", T=500, E=10, G=10, hidden=[128, 128, 128, 128], cov=0.5, gamma=0.5,
                      eps=0.15, lr=3e-4, updates=1, restart=False, desc="CartPole GRPO (scripts/cartpole_nn_grpo.py defaults)"),
-    # BASELINE configs[2] at a quarter of its size per GPU; hover-biased start (output layer zeroed, cov 1e-4):
-    # no stabilising gain was designed for the 2-D vehicle, so this line measures kernels, not a training regime
+    # BASELINE configs[2] at FULL size on one GPU: 1,048,576 envs x 500 steps (29 GB of trajectory), MLP 128x128; cov 0.5, lr 2e-4,
+    # gamma 0.99 as pipelines/quadpole2d_pipeline_ppo.py:54-80 sets them; stabilising start on the vehicle coordinates
+    "quadpole2d_cfg3": dict(kind=2, cls="QuadPole2D", T=500, E=16, G=65536, hidden=[128, 128], cov=0.5, gamma=0.99,
+                            eps=0.2, lr=2e-4, updates=1, start="lqr",
+                            desc="QuadPole2D GRPO, 1,048,576 envs x 500 steps (BASELINE configs[2] at full size), group 16, "
+                                 "MLP 128x128, cov 0.5, stabilising start policy"),
+    # the same with PPO (actor + critic, full batch, Monte-Carlo returns, c1 0.5, kl 0.5: the shipped pipeline's setting; 2 of
+    # its 24 updates per epoch to keep the run short) at a quarter of the size
+    "quadpole2d_ppo": dict(kind=2, cls="QuadPole2D", T=500, E=16, G=16384, hidden=[128, 128], cov=0.5, gamma=0.99,
+                           eps=0.2, lr=2e-4, updates=2, start="lqr", algo="ppo",
+                           desc="QuadPole2D PPO (actor + critic 128x128, full batch), 262,144 envs x 500 steps, cov 0.5, "
+                                "stabilising start policy"),
+    # hover-biased start (output layer zeroed, cov 1e-4): ragged episodes (valid fraction 0.5) for kernel measurements
     "quadpole2d": dict(kind=2, cls="QuadPole2D", T=500, E=16, G=16384, hidden=[128, 128], cov=1e-4, gamma=0.99,
                        eps=0.2, lr=2e-7, updates=2, start="hover",
-                       desc="QuadPole2D GRPO, 262,144 envs x 500 steps, group 16, MLP 128x128, hover-biased start"),
-    "quadpole2d_ppo": dict(kind=2, cls="QuadPole2D", T=500, E=16, G=16384, hidden=[128, 128], cov=1e-4, gamma=0.99,
-                           eps=0.2, lr=2e-7, updates=2, start="hover", algo="ppo",
-                           desc="QuadPole2D PPO (actor + critic 128x128, full batch), 262,144 envs x 500 steps, "
-                                "hover-biased start"),
+                       desc="QuadPole2D GRPO, 262,144 envs x 500 steps, group 16, MLP 128x128, hover-biased start (ragged)"),
     # one eighth of the cfg-4 shard (kernel profiling runs)
     "quadpole": dict(kind=3, cls="QuadPole", T=1000, E=64, G=1024, hidden=[256, 256], cov=0.3, gamma=0.999, eps=0.2,
                      lr=3e-4, updates=1, start="lqr",
@@ -96,7 +103,7 @@ def start_policy_arrays(w, seed=1234):
     if w.get("start") == "hover":
         Ws[-1][:] = 0.0; bs[-1][:] = 0.0
     elif w.get("start") == "lqr":
-        g = json.load(open(os.path.join(ROOT, "bench_assets", "quadpole_lqr_gain.json")))
+        g = json.load(open(os.path.join(ROOT, "bench_assets", {3: "quadpole_lqr_gain.json", 2: "quadpole2d_lqr_gain.json"}[kind])))
         K, sel = np.asarray(g["K"], np.float32), g["sel"]
         nz = len(sel)
         assert len(w["hidden"]) == 2 and min(w["hidden"]) >= 2 * nz
@@ -520,10 +527,13 @@ def run_ours(args, w):
         import gc
         import torch
         gc.collect(); torch.cuda.empty_cache()
-        w2 = WORKLOADS["pendulum"]
-        o2, k2, _ = measure(D, w2, 5, 3, False, args)
-        o2["roofline"] = rooflines(k2, w2, fp32_peak, peaks)
-        others["pendulum (BASELINE configs[1], device-resident arm)"] = o2
+        for key, name, st, wu in (("pendulum", "pendulum (BASELINE configs[1], device-resident arm)", 5, 3),
+                                  ("quadpole2d_cfg3", "quadpole2d_cfg3 (BASELINE configs[2] at full size per GPU, device-resident arm)", 2, 2)):
+            w2 = WORKLOADS[key]
+            o2, k2, _ = measure(D, w2, st, wu, False, args)
+            o2["roofline"] = rooflines(k2, w2, fp32_peak, peaks)
+            others[name] = o2
+            gc.collect(); torch.cuda.empty_cache()
     if D.rank != 0:
         D.close()
         return

@@ -77,7 +77,60 @@ def survival(K, N=2048, T=1000, cov=0.3, seed=0):
     return float(alive.mean()), float(length.mean() / T)
 
 
+# ---- QuadPole2D (BASELINE configs[2]): state feedback on the vehicle only (x, z, vx, vz, sin(theta), theta_dot).
+# The pole starts anywhere on the circle (quadrotor_env.py:951-955) and has no damping, so it keeps swinging; it is
+# treated as a disturbance of the vehicle, which only has to stay inside its +-2 m box (quadrotor_env.py:1020-1022).
+EQ2 = np.zeros(10); EQ2[5] = 1.0; EQ2[8] = 1.0
+SEL2 = [0, 1, 2, 3, 4, 6]
+
+
+def design_2d():
+    def f(z, a):
+        s = np.tile(EQ2, (z.shape[0], 1))
+        s[:, SEL2] += z
+        nxt, _, _ = R.quadpole2d_step(s, a.astype(np.float32), DT, np.float64)
+        return (nxt - EQ2)[:, SEL2]
+    n = len(SEL2)
+    A, B = np.zeros((n, n)), np.zeros((n, 2))
+    z0, a0 = np.zeros((1, n)), np.zeros((1, 2))
+    for i in range(n):
+        e = np.zeros((1, n)); e[0, i] = 1e-4
+        A[:, i] = (f(e, a0) - f(-e, a0))[0] / 2e-4
+    for j in range(2):
+        e = np.zeros((1, 2)); e[0, j] = 1e-2
+        B[:, j] = (f(z0, e) - f(z0, -e))[0] / 2e-2
+    Q, Rm = np.diag([10.0, 10.0, 1.0, 1.0, 10.0, 1.0]), np.eye(2)
+    P = sla.solve_discrete_are(A, B, Q, Rm)
+    return np.linalg.solve(Rm + B.T @ P @ B, B.T @ P @ A)
+
+
+def survival_2d(K, N=2048, T=500, cov=0.5, seed=0):
+    rng = np.random.default_rng(seed)
+    s = R.reset_states(R.ENV_QUADPOLE2D, N, rng)
+    alive, length = np.ones(N, bool), np.zeros(N, int)
+    sd = np.float32(np.sqrt(cov))
+    for _ in range(T):
+        mu = (-((s - EQ2)[:, SEL2] @ K.T)).astype(np.float32)
+        a = mu + sd * rng.standard_normal((N, 2)).astype(np.float32)
+        nxt, _, aux = R.quadpole2d_step(s, a, DT, np.float64)
+        length += alive
+        alive &= ~aux["oob"]
+        s = np.where(alive[:, None], nxt, s)
+    return float(alive.mean()), float(length.mean() / T)
+
+
 def main():
+    K2 = design_2d()
+    alive2, valid2 = survival_2d(K2)
+    _, valid20 = survival_2d(np.zeros_like(K2), N=512)
+    out2 = {"env": "QuadPole2D", "sel": SEL2, "K": K2.tolist(), "cov": 0.5, "horizon": 500,
+            "alive_fraction_oracle": alive2, "valid_fraction_oracle": valid2, "valid_fraction_zero_policy": valid20,
+            "how": "discrete LQR (Q = diag(10 pos, 1 vel, 10 sin(theta), 1 theta_dot), R = I) of the oracle's quadpole2d_step "
+                   "linearised about hover on the vehicle coordinates only; survival measured with oracle/restate.py on 2048 envs"}
+    path2 = os.path.join(os.path.dirname(HERE), "bench_assets", "quadpole2d_lqr_gain.json")
+    with open(path2, "w") as f:
+        json.dump(out2, f, indent=1)
+    print(f"QuadPole2D: alive after 500 steps {alive2:.4f}, valid fraction {valid2:.4f} (zero policy: {valid20:.3f}) -> {path2}")
     A, B = linearise()
     K = lqr(A, B)
     alive, valid = survival(K)
