@@ -1061,7 +1061,7 @@ static int launch_tcw_np(const TcwArgs &a0, int grid, int64_t total_upper, int64
     // converter warps of kernel B: measured on B200 (profiles/README_r2.md) 8 / 12 / 16 warps = 293 / 267 / 241 us per
     // launch at W = 256 and 12 <= 16 at W = 128
     constexpr int NCV = W == 256 ? 16 : 12;
-    void (*kB)(const TcwArgs) = update_tcw_wgrad_kernel<O, A, W, NCV, true>;
+    void (*kB)(const TcwArgs) = update_tcw_wgrad_kernel<O, A, W, NCV, true>;      // (22 warps: no further gain, r2p)
     const int threadsB = (NCV + 2) * 32;
     TG_CUDA(cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
     TG_CUDA(cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
