@@ -287,7 +287,7 @@ def measure(D, w, steps, warmup, full, args):
     env_cls = getattr(tg, w["cls"])
     mgr = tg.RolloutManager(lambda: env_cls(max_steps=T), policy, restart=w.get("restart", True), num_workers=G * world,
                             num_episodes_per_worker=E, use_multiprocessing=False, seed=7, rank=rank, world_size=world,
-                            reuse_buffers=True)
+                            reuse_buffers=True, precision=args.precision)
     buf = tg.Rollout_Buffer(mgr)
     env = mgr.env
     rng = np.random.default_rng(100 + rank)
@@ -296,7 +296,8 @@ def measure(D, w, steps, warmup, full, args):
 
     def host_init():
         s0 = np.repeat(env.sample_initial_states(G, rng), E, axis=0) if restart else env.sample_initial_states(N, rng)
-        return torch.from_numpy(np.ascontiguousarray(s0.T)).to(torch.float32).pin_memory()
+        return torch.from_numpy(np.ascontiguousarray(s0.T)).to(torch.float64 if args.precision == "f64"
+                                                               else torch.float32).pin_memory()
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     chunked = w.get("chunk_groups") is not None
@@ -545,7 +546,7 @@ def run_ours(args, w):
     line = {
         "metric": "policy-in-loop env-steps/sec (rollout + GRPO update epoch)", "value": out["value"], "unit": "env-steps/s",
         "n_gpus": D.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": out["ms_per_step"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": {"workload": w["desc"], "envs_per_gpu": N, "horizon": T, "group_size": w["E"],
                    "mlp": [O] + w["hidden"] + [A], "updates_per_iter": w["updates"], "cov": w["cov"], "lr": w["lr"],
                    "objective_sign": ("ascent (GRPO(maximize=True)); the reference's literal sign descends on J and destroys "
@@ -581,6 +582,8 @@ def main():
     ap.add_argument("--no-other", action="store_true", help="skip the other_configs (Pendulum) line")
     ap.add_argument("--device-only", action="store_true", help="device-resident arm only (profiling runs)")
     ap.add_argument("--sweep-envs-per-gpu", type=int, default=0, help="quadpole_sweep: envs per GPU (multiple of 64)")
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"],
+                    help="env-state arithmetic of the rollout kernel: f32 (throughput mode, default) or f64 (the reference's)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
