@@ -133,6 +133,13 @@ def ctx(device=None) -> C.c_void_p:
     return _ctxs[idx]
 
 
+def is_checkpoint_writer() -> bool:
+    """In a sharded run (torch.distributed initialised) every rank holds the same weights, optimizer state and reward
+    history, and the reference's Pipeline.save would make each of them write the same files: only rank 0 writes."""
+    import torch.distributed as dist
+    return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+
+
 def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 

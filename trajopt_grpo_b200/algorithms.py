@@ -332,7 +332,8 @@ class GRPO(Algorithm):
             self._old_tag = self.old_policy.param_tag()
 
     def save(self, path: str) -> None:
-        torch.save(self.optimizer.state_dict(), os.path.join(path, "optimizer.pth"))
+        if L.is_checkpoint_writer():
+            torch.save(self.optimizer.state_dict(), os.path.join(path, "optimizer.pth"))
 
     def load(self, path: str) -> None:
         """grpo.py:156-160."""
@@ -443,7 +444,8 @@ class PPO(Algorithm):
                 "updates_per_iter": self.updates_per_iter}
 
     def save(self, path: str) -> None:
-        torch.save(self.optimizer.state_dict(), os.path.join(path, "optimizer.pt"))
+        if L.is_checkpoint_writer():
+            torch.save(self.optimizer.state_dict(), os.path.join(path, "optimizer.pt"))
 
     def load(self, path: str) -> None:
         """ppo.py:217-225."""

@@ -155,6 +155,8 @@ class Rollout_Buffer(Buffer):
     def save(self, path: str):
         """rollout_buffer.py:115-126."""
         self._resolve_rewards()
+        if not L.is_checkpoint_writer():
+            return
         with open(os.path.join(path, "reward.csv"), "w") as f:
             for reward in self.avg_reward:
                 f.write(f"{reward}\n")

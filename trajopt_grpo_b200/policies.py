@@ -241,7 +241,8 @@ class GaussianActor_NeuralNetwork(_GaussianBase):
         return self.actor._flat
 
     def save(self, path):
-        torch.save({k: v.cpu() for k, v in self.actor.state_dict().items()}, os.path.join(path, "policy.pt"))
+        if L.is_checkpoint_writer():
+            torch.save({k: v.cpu() for k, v in self.actor.state_dict().items()}, os.path.join(path, "policy.pt"))
 
     def load(self, path):
         """Missing in the reference (GRPO resume raises); added so
@@ -300,5 +301,6 @@ class GaussianActorCritic_NeuralNetwork(_GaussianBase):
         return self._flat_all
 
     def save(self, save_path):
-        sd = {k: {kk: vv.cpu() for kk, vv in v.items()} for k, v in self.state_dict().items()}
-        torch.save(sd, os.path.join(save_path, "policy.pt"))
+        if L.is_checkpoint_writer():
+            sd = {k: {kk: vv.cpu() for kk, vv in v.items()} for k, v in self.state_dict().items()}
+            torch.save(sd, os.path.join(save_path, "policy.pt"))
