@@ -358,13 +358,26 @@ def measure(D, w, steps, warmup, full, args):
     else:
         identical = True
     finite = bool(torch.isfinite(flat).all())
+    # sharded == single GPU, visible to the driver at every N > 1: one small GRPO step (Pendulum, tensor-core kernels) and one
+    # small PPO step (QuadPole2D, FP32-pipe kernels) run sharded over all ranks, and unsharded on rank 0 alone
+    sharded_ok = None
+    if world > 1 and full:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "helpers"))
+        import mgpu_case
+        from trajopt_grpo_b200 import algorithms as _alg
+        got = mgpu_case.run_case(rank, world, groups=8 * world)
+        got.pop("_peer", None)
+        if rank == 0:
+            with _alg.single_process():
+                ref = mgpu_case.run_case(0, 1, groups=8 * world)
+            sharded_ok = all(float(np.abs(got[k] - ref[k]).max()) <= 2e-5 * max(1.0, float(np.abs(ref[k]).max())) for k in got)
 
     out = {
         "workload": w["desc"], "value": value, "unit": "env-steps/s", "ms_per_step": ms_total / steps,
         "slot_steps_per_s": slots_per_step * world / (ms_total / steps * 1e-3),
         "valid_fraction": valid_per_step_rank / slots_per_step, "updates_per_iter": w["updates"],
         "phase_ms": {"rollout": roll_ms, "learn": upd_ms}, "gpu_launches": launches,
-        "rank_weights_identical": identical, "weights_finite": finite,
+        "rank_weights_identical": identical, "weights_finite": finite, "sharded_equals_single_gpu": sharded_ok,
         "rollout_env_steps_per_s": valid_per_step_rank * world / (roll_ms * 1e-3) if not chunked else None,
         "grpo_updates_per_s": w["updates"] / (upd_ms * 1e-3) if not chunked else w["updates"] / (ms_total / steps * 1e-3),
     }
@@ -565,6 +578,7 @@ def run_ours(args, w):
         "rollout_env_steps_per_s": out["rollout_env_steps_per_s"], "grpo_updates_per_s": out["grpo_updates_per_s"],
         "phase_ms": out["phase_ms"], "kernel_ms": {k: out.get(k) for k in ("k1_ms", "k2_ms", "k3_ms")},
         "rank_weights_identical": out["rank_weights_identical"], "weights_finite": out["weights_finite"],
+        "sharded_equals_single_gpu": out.get("sharded_equals_single_gpu"),
         "roofline": roof, "cpu_baseline": cpu, "clocks": out.get("clocks"), "other_configs": others,
     }
     print(json.dumps(line))

@@ -13,7 +13,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
-def run_case(rank: int, world: int) -> dict:
+def run_case(rank: int, world: int, groups: int = 8) -> dict:
     import trajopt_grpo_b200 as tg
     out = {}
     # ---- GRPO, Pendulum, 64x64 policy (tensor-core kernels)
@@ -21,7 +21,7 @@ def run_case(rank: int, world: int) -> dict:
     pol = tg.GaussianActor_NeuralNetwork(3, 1, [64, 64], "ReLU", 0.5)
     opt = torch.optim.Adam(pol.parameters(), lr=1e-3)
     algo = tg.GRPO(0.2, 0.01, 0.99, pol, opt, None, updates_per_iter=3)
-    mgr = tg.RolloutManager(lambda: tg.Pendulum(max_steps=40), pol, restart=True, num_workers=8,
+    mgr = tg.RolloutManager(lambda: tg.Pendulum(max_steps=40), pol, restart=True, num_workers=groups,
                             num_episodes_per_worker=16, use_multiprocessing=False, seed=3, rank=rank, world_size=world)
     buf = tg.Rollout_Buffer(mgr)
     buf.device_rollout = mgr.rollout_device()
@@ -34,7 +34,7 @@ def run_case(rank: int, world: int) -> dict:
     opt2 = torch.optim.Adam(pol2.parameters(), lr=1e-3)
     ppo = tg.PPO(0.2, pol2, opt2, None, 2, c1=0.5, kl_coeff=0.5, gamma=0.99, lam=0.95, entropy=0.01, batch_size=None,
                  monte_carlo=False)
-    mgr2 = tg.RolloutManager(lambda: tg.QuadPole2D(max_steps=30), pol2, restart=False, num_workers=6,
+    mgr2 = tg.RolloutManager(lambda: tg.QuadPole2D(max_steps=30), pol2, restart=False, num_workers=groups if groups != 8 else 6,
                              num_episodes_per_worker=8, use_multiprocessing=False, seed=5, rank=rank, world_size=world)
     buf2 = tg.Rollout_Buffer(mgr2)
     buf2.device_rollout = mgr2.rollout_device()

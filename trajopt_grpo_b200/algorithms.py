@@ -160,7 +160,27 @@ class _FlatOptimizer:
         self.opt.step()
 
 
+_WORLD_OVERRIDE = None
+
+
+class single_process:
+    """with algorithms.single_process(): learn() treats the rollout as unsharded even though a process group is
+    initialised (used to compute the single-GPU reference of a sharded run inside the same process)."""
+
+    def __enter__(self):
+        global _WORLD_OVERRIDE
+        self._prev, _WORLD_OVERRIDE = _WORLD_OVERRIDE, 1
+        return self
+
+    def __exit__(self, *exc):
+        global _WORLD_OVERRIDE
+        _WORLD_OVERRIDE = self._prev
+        return False
+
+
 def _dist_world():
+    if _WORLD_OVERRIDE is not None:
+        return _WORLD_OVERRIDE
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
         return dist.get_world_size()
