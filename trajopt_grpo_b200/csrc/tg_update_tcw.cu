@@ -734,7 +734,7 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
                 continue;
             }
             tcw_sync(q + 1, NP * 32);
-            // ---- epilogue 2b: column sums for dWo (butterflies); dZ2 = (Wo^T dmu) * act'(H2) -> scratch and A operand
+            // ---- epilogue 2b: H2 -> scratch (kernel B: dWo, and dZ2 rebuilt from it); dZ2 = (Wo^T dmu) * act'(H2) -> A operand
             {
 #pragma unroll
                 for (int jj = 0; jj < A; ++jj) dmu_own[jj] = dmuS[jj][e];
