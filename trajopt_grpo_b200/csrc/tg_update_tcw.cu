@@ -829,33 +829,60 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
 
 // ============================================================================
 // kernel B: split-K weight-gradient GEMMs streamed from the scratch
-//   stage = one 8-sample sub-block:
-//     H2h, H2l (this half: 4 column blocks) | Z2h, Z2l (rebuilt from H2 and dmu) | Z1h, Z1l (this half) | H1h, H1l (all) | Yh, Yl
+//   one 8-sample sub-block travels through TWO shared-memory rings:
+//     raw ring     (NR slots, filled by TMA):        H2 (this half: 4 column blocks) | dZ1 (this half) | H1 (all) | Yh | Yl
+//                  -- the fp32 rows stay there and ARE the hi operands
+//     derived ring (NL slots, filled by converters): H2l | Z2h, Z2l (rebuilt from H2 and dmu) | Z1l | H1l
+//   A raw slot is busy from the TMA issue to the end of its MMAs (HBM latency + conversion + tensor time); a derived slot
+//   only from the conversion on.  Two rings put NR = 8 sub-blocks of loads in flight per SM at W = 256 where one ring of
+//   whole stages had room for 5: the kernel is bound by the latency of that pipeline, not by HBM bandwidth, the
+//   converter warps or the tensor pipe (profiles/README_r2.md).
 // ============================================================================
 // NCV converter warps (0 .. NCV-1); warp NCV = TMA producer, warp NCV+1 = MMA issuer.
 // TRUNC: the fp32 rows stay in place as the "hi" operand -- the tensor core reads only the top 19 bits of a tf32
 // operand, i.e. it uses trunc(x) -- and the converter writes only lo = x - trunc(x) (one store and four cvt fewer per
 // float4 than the round-to-nearest split, whose hi has to be written back).
-template <int O, int A, int W, int NCV, bool TRUNC>
+#ifndef TCW_B_GROUPS
+#define TCW_B_GROUPS 2
+#endif
+template <int O, int A, int W> struct TcwBRings {
+    static constexpr int XKP = (O + 1 + A + 7) / 8 * 8;   // rows of Y = [x, 1, dmu, 0..]
+    static constexpr uint32_t ZB = 4 * 1024, HB = W / 32 * 1024, XB = XKP * 32;        // bytes per piece
+    static constexpr uint32_t RAW = 2 * ZB + HB + 2 * XB, RAW_AL = (RAW + 1023) / 1024 * 1024;
+    static constexpr uint32_t DER = 4 * ZB + HB;
+    static constexpr int NL = 3;
+    static constexpr int NR_FIT = (int)((220u * 1024u - NL * DER) / RAW_AL);
+    static constexpr int NR = NR_FIT > 12 ? 12 : NR_FIT;
+    static constexpr size_t BYTES = (size_t)NR * RAW_AL + (size_t)NL * DER;
+};
+
+template <int O, int A, int W, int NCV, bool TRUNC, int NGRP>
 __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(const __grid_constant__ TcwArgs a) {
-    constexpr int XKP = (O + 1 + A + 7) / 8 * 8;   // rows of Y = [x, 1, dmu, 0..]
-    constexpr uint32_t ZB = 4 * 1024, HB = W / 32 * 1024, XB = XKP * 32;        // bytes per stage piece
-    constexpr uint32_t OFF_Z2 = 2 * ZB, OFF_Z1 = 4 * ZB, OFF_H1 = 6 * ZB, OFF_X = 6 * ZB + 2 * HB;
-    constexpr uint32_t STAGE = 6 * ZB + 2 * HB + 2 * XB;
-    constexpr uint32_t STAGE_AL = (STAGE + 1023) / 1024 * 1024;
-    constexpr int NST = 5;
+    using RG = TcwBRings<O, A, W>;
+    static_assert(NCV % NGRP == 0 && (NGRP == 1 || NGRP == 2), "converter groups");
+    constexpr int GT = NCV / NGRP * 32;              // converter threads per group; group g takes sub-blocks g, g + NGRP, ...
+    constexpr int XKP = RG::XKP;
+    constexpr uint32_t ZB = RG::ZB, HB = RG::HB, XB = RG::XB, RAW_AL = RG::RAW_AL, DER = RG::DER;
+    constexpr int NR = RG::NR, NL = RG::NL;
+    static_assert(NR >= 4, "raw ring");
+    // raw slot: H2h | Z1h | H1h | Yh | Yl        derived slot: H2l | Z2h | Z2l | Z1l | H1l
+    constexpr uint32_t R_Z1 = ZB, R_H1 = 2 * ZB, R_X = 2 * ZB + HB;
+    constexpr uint32_t D_Z2H = ZB, D_Z2L = 2 * ZB, D_Z1L = 3 * ZB, D_H1L = 4 * ZB;
     constexpr uint32_t TM_DW = 0u, TM_D0 = (uint32_t)W, TM_D1 = (uint32_t)W + 32u, TM_D2 = (uint32_t)W + 64u;
     if (a.k_begin + blockIdx.x >= a.tstart[a.T]) return;      // no live tile for this CTA in this batch (CTA-uniform)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[NST], conv_bar[NST], empty_bar[NST], done_bar;
+    __shared__ __align__(8) uint64_t full_bar[NR], empty_bar[NR], conv_bar[NL], der_empty_bar[NL], done_bar;
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float WoS[A][128];    // Wo[:, this half's columns] (dZ2 = (Wo^T dmu) * act'(H2))
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NST; ++i) {
+        for (int i = 0; i < NR; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&conv_bar[i], NCV * 32);
             mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < NL; ++i) {
+            mbar_init(&conv_bar[i], GT);
+            mbar_init(&der_empty_bar[i], 1);
         }
         mbar_init(&done_bar, 1);
         mbar_fence_init();
@@ -873,7 +900,7 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
     bool any = false;
     if (warp == NCV) {
         if (lane == 0) {
-            uint32_t gi = 0;
+            uint32_t rs = 0, rph = 0;
             int t = 0, blk = 0;
             bool first_tile = true;
             for (int64_t k = a.k_begin + blockIdx.x; k < k_end; k += gridDim.x) {
@@ -883,25 +910,25 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
                 const unsigned char *arr[3];
                 for (int i = 0; i < 3; ++i) arr[i] = tile_sc + (size_t)i * a.sc.arr_bytes;
                 const unsigned char *Xh = tile_sc + 3 * (size_t)a.sc.arr_bytes, *Xl = Xh + a.sc.x_bytes;
-                for (int sb = 0; sb < 16; ++sb, ++gi) {
-                    const uint32_t st = gi % NST, ph = (gi / NST) & 1u;
-                    mbar_wait(&empty_bar[st], ph ^ 1u);
-                    mbar_expect_tx(&full_bar[st], 2 * ZB + HB + 2 * XB);
-                    unsigned char *dst = smem_raw + (size_t)st * STAGE_AL;
+                for (int sb = 0; sb < 16; ++sb) {
+                    mbar_wait(&empty_bar[rs], rph ^ 1u);
+                    mbar_expect_tx(&full_bar[rs], 2 * ZB + HB + 2 * XB);
+                    unsigned char *dst = smem_raw + (size_t)rs * RAW_AL;
                     const size_t sbo = (size_t)sb * HB, ho = (size_t)half * ZB;
-                    // fp32 rows land in the "hi" slots; the converter warps split them in place (hi) and into the lo slots
-                    tma_bulk_g2s(dst, arr[1] + sbo + ho, ZB, &full_bar[st]);                 // H2 (this half)
-                    tma_bulk_g2s(dst + OFF_Z1, arr[2] + sbo + ho, ZB, &full_bar[st]);        // dZ1 (this half)
-                    tma_bulk_g2s(dst + OFF_H1, arr[0] + sbo, HB, &full_bar[st]);             // H1 (all columns)
-                    tma_bulk_g2s(dst + OFF_X, Xh + (size_t)sb * XB, XB, &full_bar[st]);
-                    tma_bulk_g2s(dst + OFF_X + XB, Xl + (size_t)sb * XB, XB, &full_bar[st]);
+                    // the fp32 rows land in the raw slot and stay there as the hi operands
+                    tma_bulk_g2s(dst, arr[1] + sbo + ho, ZB, &full_bar[rs]);                 // H2 (this half)
+                    tma_bulk_g2s(dst + R_Z1, arr[2] + sbo + ho, ZB, &full_bar[rs]);          // dZ1 (this half)
+                    tma_bulk_g2s(dst + R_H1, arr[0] + sbo, HB, &full_bar[rs]);               // H1 (all columns)
+                    tma_bulk_g2s(dst + R_X, Xh + (size_t)sb * XB, XB, &full_bar[rs]);
+                    tma_bulk_g2s(dst + R_X + XB, Xl + (size_t)sb * XB, XB, &full_bar[rs]);
+                    if (++rs == NR) { rs = 0; rph ^= 1u; }
                 }
             }
         }
     } else if (warp == NCV + 1) {
         const uint32_t idesc_w = umma_idesc_tf32(128, W, true, true);
         const uint32_t idesc_x = umma_idesc_tf32(128, XKP, true, false);
-        uint32_t gi = 0, first = 1u;
+        uint32_t rs = 0, ls = 0, lph = 0, first = 1u;
         int t = 0, blk = 0;
         bool first_tile = true;
         for (int64_t k = a.k_begin + blockIdx.x; k < k_end; k += gridDim.x) {
@@ -909,14 +936,13 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
             first_tile = false;
             any = true;
             if (lane == 0) {
-                for (int sb = 0; sb < 16; ++sb, ++gi) {
-                    const uint32_t st = gi % NST, ph = (gi / NST) & 1u;
-                    mbar_wait(&conv_bar[st], ph);             // landed AND split by the converter warps
+                for (int sb = 0; sb < 16; ++sb) {
+                    mbar_wait(&conv_bar[ls], lph);            // landed AND split by the converter warps
                     tc_fence_after();
-                    const uint32_t base = smem_u32(smem_raw) + st * STAGE_AL;
-                    const uint32_t h2h = base, h2l = base + ZB, z2h = base + OFF_Z2, z2l = z2h + ZB;
-                    const uint32_t z1h = base + OFF_Z1, z1l = z1h + ZB;
-                    const uint32_t h1h = base + OFF_H1, h1l = h1h + HB, xh = base + OFF_X, xl = xh + XB;
+                    const uint32_t raw = smem_u32(smem_raw) + rs * RAW_AL;
+                    const uint32_t der = smem_u32(smem_raw) + NR * RAW_AL + ls * DER;
+                    const uint32_t h2h = raw, z1h = raw + R_Z1, h1h = raw + R_H1, xh = raw + R_X, xl = xh + XB;
+                    const uint32_t h2l = der, z2h = der + D_Z2H, z2l = der + D_Z2L, z1l = der + D_Z1L, h1l = der + D_H1L;
                     const uint32_t acc0 = first ? 0u : 1u;
                     // dW1[half] += dZ2^T . H1   (A, B MN-major: 8 reduction rows, 32-column blocks 1 KB apart)
                     umma_tf32(tmem + TM_DW, umma_desc_mn32(z2h, 1024u), umma_desc_mn32(h1h, 1024u), idesc_w, acc0);
@@ -934,7 +960,10 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
                     umma_tf32(tmem + TM_D2, umma_desc_mn32(h2h, 1024u), umma_operand_desc(xl, 8, false, 0), idesc_x, 1u);
                     umma_tf32(tmem + TM_D2, umma_desc_mn32(h2l, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, 1u);
                     first = 0u;
-                    umma_commit(&empty_bar[st]);
+                    umma_commit(&empty_bar[rs]);              // both slots are free once these MMAs have read them
+                    umma_commit(&der_empty_bar[ls]);
+                    if (++rs == NR) rs = 0;
+                    if (++ls == NL) { ls = 0; lph ^= 1u; }
                 }
             }
             __syncwarp();
@@ -944,31 +973,32 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
     }
     if (warp < NCV) {
         // ===== converter warps: tf32 hi/lo split of the fp32 rows of every stage, in shared memory =====
-        uint32_t gi = 0;
+        const int grp = warp / (NCV / NGRP), tid_g = (int)threadIdx.x - grp * GT;
+        uint32_t rs = (uint32_t)grp, rph = 0, ls = (uint32_t)grp, lph = 0;
         int t = 0, blk = 0;
         bool first_tile = true;
-        constexpr int NF4 = (2 * ZB + HB) / 16;            // float4 items per stage: H2 (-> H2, dZ2) | dZ1 | H1
+        constexpr int NF4 = (2 * ZB + HB) / 16;            // float4 items per sub-block: H2 (-> H2l, dZ2) | dZ1 | H1
         const int act_kind = a.lay.act;
         for (int64_t k = a.k_begin + blockIdx.x; k < k_end; k += gridDim.x) {
             if (!(first_tile ? tcw_tile_of(a.tstart, a.T, k, &t, &blk) : tcw_tile_next(a.tstart, a.T, k, &t, &blk))) break;
             first_tile = false;
-            for (int sb = 0; sb < 16; ++sb, ++gi) {
-                const uint32_t st = gi % NST, ph = (gi / NST) & 1u;
-                mbar_wait(&full_bar[st], ph);
-                unsigned char *base = smem_raw + (size_t)st * STAGE_AL;
-                // item assignment: the 256 items of the H2 piece are the expensive ones (they also rebuild dZ2), one per
-                // thread of warps 0..7; the plain items (dZ1, H1) are spread over the remaining converter warps
+            for (int sb = grp; sb < 16; sb += NGRP) {
+                mbar_wait(&full_bar[rs], rph);
+                mbar_wait(&der_empty_bar[ls], lph ^ 1u);
+                unsigned char *base = smem_raw + (size_t)rs * RAW_AL;
+                unsigned char *der = smem_raw + (size_t)NR * RAW_AL + (size_t)ls * DER;
+                // item assignment.  One group: the 256 items of the H2 piece are the expensive ones (they also rebuild dZ2),
+                // one per thread of warps 0..7, the plain items (dZ1, H1) spread over the remaining converter warps.  Two
+                // groups: a strided walk, every thread starts with H2 items.
                 constexpr int NH2 = (int)(ZB / 16), NREST = NCV * 32 - NH2;
                 static_assert(NREST > 0, "converter warps");
+                const bool h2_thread = NGRP == 1 && (int)threadIdx.x < NH2;
 #pragma unroll 2
-                for (int f = (int)threadIdx.x < NH2 ? (int)threadIdx.x : NH2 + ((int)threadIdx.x - NH2); f < NF4;
-                     f += ((int)threadIdx.x < NH2 ? NF4 : NREST)) {
+                for (int f = NGRP == 1 ? (int)threadIdx.x : tid_g; f < NF4; f += (NGRP == 1 ? (h2_thread ? NF4 : NREST) : GT)) {
                     const uint32_t b = (uint32_t)f * 16u;
-                    // slot of this item: H2 at 0 (lo at ZB), dZ1 at OFF_Z1 (lo + ZB), H1 at OFF_H1 (lo + HB)
-                    unsigned char *hp, *lp;
-                    if (b < ZB) { hp = base + b; lp = hp + ZB; }
-                    else if (b < 2 * ZB) { hp = base + OFF_Z1 + (b - ZB); lp = hp + ZB; }
-                    else { hp = base + OFF_H1 + (b - 2 * ZB); lp = hp + HB; }
+                    // the raw pieces H2 | dZ1 | H1 are contiguous; lo parts: H2l at 0, Z1l at 3 ZB, H1l at 4 ZB of the derived slot
+                    unsigned char *hp = base + b;
+                    unsigned char *lp = der + (b < ZB ? b : b + 2 * ZB);
                     const float4 v = *reinterpret_cast<const float4 *>(hp);
                     float4 h4, l4;
                     if (TRUNC) {
@@ -987,7 +1017,7 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
                         float dmu[A];
 #pragma unroll
                         for (int o = 0; o < A; ++o) {
-                            const uint32_t xo = OFF_X + core_offset(8, O + 1 + o, r);
+                            const uint32_t xo = R_X + core_offset(8, O + 1 + o, r);
                             dmu[o] = *reinterpret_cast<const float *>(base + xo) + *reinterpret_cast<const float *>(base + xo + XB);
                         }
                         float4 d;
@@ -1001,12 +1031,16 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
                             h4.x = tf32_hi(d.x); h4.y = tf32_hi(d.y); h4.z = tf32_hi(d.z); h4.w = tf32_hi(d.w);
                         }
                         l4.x = d.x - h4.x; l4.y = d.y - h4.y; l4.z = d.z - h4.z; l4.w = d.w - h4.w;
-                        *reinterpret_cast<float4 *>(hp + OFF_Z2) = TRUNC ? d : h4;
-                        *reinterpret_cast<float4 *>(hp + OFF_Z2 + ZB) = l4;
+                        *reinterpret_cast<float4 *>(der + D_Z2H + b) = TRUNC ? d : h4;
+                        *reinterpret_cast<float4 *>(der + D_Z2L + b) = l4;
                     }
                 }
                 fence_proxy_async();
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv_bar[st])) : "memory");
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv_bar[ls])) : "memory");
+                rs += NGRP;
+                if (rs >= (uint32_t)NR) { rs -= NR; rph ^= 1u; }
+                ls += NGRP;
+                if (ls >= (uint32_t)NL) { ls -= NL; lph ^= 1u; }
             }
         }
     }
@@ -1054,14 +1088,13 @@ template <int O, int A, int W, int NP>
 static int launch_tcw_np(const TcwArgs &a0, int grid, int64_t total_upper, int64_t batch_tiles, cudaStream_t st) {
     constexpr int OKP = (O + 1 + 7) / 8 * 8, XKP = (O + 1 + A + 7) / 8 * 8;
     const size_t smemA = (size_t)TCW_STAGES * W * 128 + (size_t)a0.lay.resident * 4 + 2 * (size_t)128 * OKP * 4;
-    constexpr uint32_t STAGE = 6 * 4096 + 2 * (W / 32 * 1024) + 2 * (XKP * 32);
-    const size_t smemB = (size_t)5 * ((STAGE + 1023) / 1024 * 1024);
+    const size_t smemB = TcwBRings<O, A, W>::BYTES;
     void (*kA)(const TcwArgs) = a0.lay.act == TG_ACT_RELU ? update_tcw_fwdbwd_kernel<O, A, true, W, NP>
                                                           : update_tcw_fwdbwd_kernel<O, A, false, W, NP>;
     // converter warps of kernel B: measured on B200 (profiles/README_r2.md) 8 / 12 / 16 warps = 293 / 267 / 241 us per
     // launch at W = 256 and 12 <= 16 at W = 128
     constexpr int NCV = W == 256 ? 16 : 12;
-    void (*kB)(const TcwArgs) = update_tcw_wgrad_kernel<O, A, W, NCV, true>;      // (22 warps: no further gain, r2p)
+    void (*kB)(const TcwArgs) = update_tcw_wgrad_kernel<O, A, W, NCV, true, TCW_B_GROUPS>;      // (22 warps: no further gain, r2p)
     const int threadsB = (NCV + 2) * 32;
     TG_CUDA(cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
     TG_CUDA(cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
