@@ -134,12 +134,18 @@ class ClockSampler:
             idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
             h = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            try:
+                self.power_limit_w = pynvml.nvmlDeviceGetEnforcedPowerLimit(h) / 1000.0
+            except Exception:
+                self.power_limit_w = None
+            self.power = []
 
             def loop():
                 while not self.stop_flag:
                     try:
                         self.samples.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM),
                                              pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)))
+                        self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
                     except Exception:
                         pass
                     time.sleep(0.02)
@@ -161,7 +167,8 @@ class ClockSampler:
                 if mask & bit:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": float(np.median(self.power)) if self.power else None, "power_limit_w": self.power_limit_w}
 
 
 # --------------------------------------------------------------------------------------

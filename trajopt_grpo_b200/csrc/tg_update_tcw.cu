@@ -17,12 +17,14 @@
 //   kernel B  (update_tcw_wgrad_kernel)   split-K weight-gradient GEMMs over the batch's samples:
 //       dW1[half] += dZ2[:, half]^T . H1,   [dW0 | db0][half] += dZ1[:, half]^T . Y,   db1[half] = (dZ2[:, half]^T . Y)[:, ones],
 //       dWo[:, half]^T = (H2[:, half]^T . Y)[:, dmu columns],
-//       operands streamed from the scratch by TMA (8 samples per stage); dZ2 is not stored: the converter warps
+//       operands streamed from the scratch by TMA (8 samples at a time, two shared-memory rings: see the kernel);
+//       dZ2 is not stored: the converter warps
 //       rebuild it from H2 and dmu, dZ2 = (Wo^T dmu) * act'(H2), with the operation order of kernel A, while they
 //       produce the tf32 lo parts (the fp32 rows themselves serve as the hi operands: the tensor core drops the low
 //       13 bits).  Accumulators persistent in tensor memory for all tiles of the launch, added to the CTA-private
-//       gradient copy at the end.  One launch per 128-row half of the outputs (two at W = 256).  Bound by the
-//       converter warps (8 -> 12 -> 16 warps: 293 -> 267 -> 241 us per launch at W = 256).
+//       gradient copy at the end.  One launch per 128-row half of the outputs (two at W = 256).  Per launch of 2656
+//       tiles at W = 256: 8 -> 12 -> 16 converter warps 293 -> 267 -> 241 us; deeper raw ring + two converter groups
+//       202 us (ncu, serialised; the live epoch is power-bound).
 //
 // Tiles are enumerated in length order (tg_order.cu): tile k of the compact list is (step t, sorted
 // positions 128*blk ..), found by binary search in the per-step prefix of live tiles; k beyond the live
