@@ -15,8 +15,8 @@
 //       round 1 computed dWo = dmu^T . H2 with register butterflies here (187 us of 847 us per 2656-tile batch at
 //       W = 256); dWo is now one more small GEMM of kernel B.
 //   kernel B  (update_tcw_wgrad_kernel)   split-K weight-gradient GEMMs over the batch's samples:
-//       dW1[half] += dZ2[:, half]^T . H1,   [dW0 | db0][half] += dZ1[:, half]^T . Y,   db1[half] = (dZ2[:, half]^T . Y)[:, ones],
-//       dWo[:, half]^T = (H2[:, half]^T . Y)[:, dmu columns],
+//       dW1[half] += dZ2[:, half]^T . H1,   [dW0 | db0][half] += dZ1[:, half]^T . [x, 1]   on the tensor core;
+//       db1[half] = sum_s dZ2[s, half],   dWo[:, half] = sum_s dmu[s] H2[s, half]   on the FP32 pipe of the converter warps,
 //       operands streamed from the scratch by TMA (8 samples at a time, two shared-memory rings: see the kernel);
 //       dZ2 is not stored: the converter warps
 //       rebuild it from H2 and dmu, dZ2 = (Wo^T dmu) * act'(H2), with the operation order of kernel A, while they
@@ -24,7 +24,7 @@
 //       13 bits).  Accumulators persistent in tensor memory for all tiles of the launch, added to the CTA-private
 //       gradient copy at the end.  One launch per 128-row half of the outputs (two at W = 256).  Per launch of 2656
 //       tiles at W = 256: 8 -> 12 -> 16 converter warps 293 -> 267 -> 241 us; deeper raw ring + two converter groups
-//       202 us (ncu, serialised; the live epoch is power-bound).
+//       202 us; db1 / dWo as register column sums instead of five small MMAs per sub-block 158 us (ncu, serialised).
 //
 // Tiles are enumerated in length order (tg_order.cu): tile k of the compact list is (step t, sorted
 // positions 128*blk ..), found by binary search in the per-step prefix of live tiles; k beyond the live
@@ -833,8 +833,11 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
 // kernel B: split-K weight-gradient GEMMs streamed from the scratch
 //   one 8-sample sub-block travels through TWO shared-memory rings:
 //     raw ring     (NR slots, filled by TMA):        H2 (this half: 4 column blocks) | dZ1 (this half) | H1 (all) | Yh | Yl
-//                  -- the fp32 rows stay there and ARE the hi operands
-//     derived ring (NL slots, filled by converters): H2l | Z2h, Z2l (rebuilt from H2 and dmu) | Z1l | H1l
+//                  -- the fp32 rows of dZ1 and H1 stay there and ARE the hi operands; H2 is read by the converters only
+//     derived ring (NL slots, filled by converters): Z2h, Z2l (dZ2 rebuilt from H2 and dmu) | Z1l | H1l
+//   db1 = sum_s dZ2 and dWo = sum_s dmu H2 are column sums with 1 / A outputs per column: the converter thread that
+//   rebuilds four dZ2 values accumulates them (and dmu x H2) in registers on the FP32 pipe -- as tcgen05 GEMMs against
+//   Y they cost 5 of the 11 MMAs of a sub-block and 40 % of its operand reads for 3 % of its MACs.
 //   A raw slot is busy from the TMA issue to the end of its MMAs (HBM latency + conversion + tensor time); a derived slot
 //   only from the conversion on.  Two rings put NR = 8 sub-blocks of loads in flight per SM at W = 256 where one ring of
 //   whole stages had room for 5: the kernel is bound by the latency of that pipeline, not by HBM bandwidth, the
@@ -851,7 +854,7 @@ template <int O, int A, int W> struct TcwBRings {
     static constexpr int XKP = (O + 1 + A + 7) / 8 * 8;   // rows of Y = [x, 1, dmu, 0..]
     static constexpr uint32_t ZB = 4 * 1024, HB = W / 32 * 1024, XB = XKP * 32;        // bytes per piece
     static constexpr uint32_t RAW = 2 * ZB + HB + 2 * XB, RAW_AL = (RAW + 1023) / 1024 * 1024;
-    static constexpr uint32_t DER = 4 * ZB + HB;
+    static constexpr uint32_t DER = 3 * ZB + HB;
     static constexpr int NL = 3;
     static constexpr int NR_FIT = (int)((220u * 1024u - NL * DER) / RAW_AL);
     static constexpr int NR = NR_FIT > 12 ? 12 : NR_FIT;
@@ -863,14 +866,16 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
     using RG = TcwBRings<O, A, W>;
     static_assert(NCV % NGRP == 0 && (NGRP == 1 || NGRP == 2), "converter groups");
     constexpr int GT = NCV / NGRP * 32;              // converter threads per group; group g takes sub-blocks g, g + NGRP, ...
-    constexpr int XKP = RG::XKP;
     constexpr uint32_t ZB = RG::ZB, HB = RG::HB, XB = RG::XB, RAW_AL = RG::RAW_AL, DER = RG::DER;
     constexpr int NR = RG::NR, NL = RG::NL;
     static_assert(NR >= 4, "raw ring");
-    // raw slot: H2h | Z1h | H1h | Yh | Yl        derived slot: H2l | Z2h | Z2l | Z1l | H1l
+    // raw slot: H2 | Z1h | H1h | Yh | Yl        derived slot: Z2h | Z2l | Z1l | H1l
     constexpr uint32_t R_Z1 = ZB, R_H1 = 2 * ZB, R_X = 2 * ZB + HB;
-    constexpr uint32_t D_Z2H = ZB, D_Z2L = 2 * ZB, D_Z1L = 3 * ZB, D_H1L = 4 * ZB;
-    constexpr uint32_t TM_DW = 0u, TM_D0 = (uint32_t)W, TM_D1 = (uint32_t)W + 32u, TM_D2 = (uint32_t)W + 64u;
+    constexpr uint32_t D_Z2H = 0, D_Z2L = ZB, D_Z1L = 2 * ZB, D_H1L = 3 * ZB;
+    constexpr uint32_t TM_DW = 0u, TM_D0 = (uint32_t)W;
+    constexpr int NF4 = (2 * ZB + HB) / 16;          // float4 items per sub-block: H2 (-> dZ2, dWo, db1) | dZ1 | H1
+    constexpr int NH2 = (int)(ZB / 16);              // the H2 items
+    constexpr int NIT = (NF4 + GT - 1) / GT, NH2_IT = (NH2 + GT - 1) / GT;   // items / H2 items per thread and sub-block
     if (a.k_begin + blockIdx.x >= a.tstart[a.T]) return;      // no live tile for this CTA in this batch (CTA-uniform)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[NR], empty_bar[NR], conv_bar[NL], der_empty_bar[NL], done_bar;
@@ -929,7 +934,7 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
         }
     } else if (warp == NCV + 1) {
         const uint32_t idesc_w = umma_idesc_tf32(128, W, true, true);
-        const uint32_t idesc_x = umma_idesc_tf32(128, XKP, true, false);
+        const uint32_t idesc_x = umma_idesc_tf32(128, (O + 1 + 7) / 8 * 8, true, false);   // rows [x, 1] of Y only
         uint32_t rs = 0, ls = 0, lph = 0, first = 1u;
         int t = 0, blk = 0;
         bool first_tile = true;
@@ -943,24 +948,17 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
                     tc_fence_after();
                     const uint32_t raw = smem_u32(smem_raw) + rs * RAW_AL;
                     const uint32_t der = smem_u32(smem_raw) + NR * RAW_AL + ls * DER;
-                    const uint32_t h2h = raw, z1h = raw + R_Z1, h1h = raw + R_H1, xh = raw + R_X, xl = xh + XB;
-                    const uint32_t h2l = der, z2h = der + D_Z2H, z2l = der + D_Z2L, z1l = der + D_Z1L, h1l = der + D_H1L;
+                    const uint32_t z1h = raw + R_Z1, h1h = raw + R_H1, xh = raw + R_X, xl = xh + XB;
+                    const uint32_t z2h = der + D_Z2H, z2l = der + D_Z2L, z1l = der + D_Z1L, h1l = der + D_H1L;
                     const uint32_t acc0 = first ? 0u : 1u;
                     // dW1[half] += dZ2^T . H1   (A, B MN-major: 8 reduction rows, 32-column blocks 1 KB apart)
                     umma_tf32(tmem + TM_DW, umma_desc_mn32(z2h, 1024u), umma_desc_mn32(h1h, 1024u), idesc_w, acc0);
                     umma_tf32(tmem + TM_DW, umma_desc_mn32(z2h, 1024u), umma_desc_mn32(h1l, 1024u), idesc_w, 1u);
                     umma_tf32(tmem + TM_DW, umma_desc_mn32(z2l, 1024u), umma_desc_mn32(h1h, 1024u), idesc_w, 1u);
-                    // [dW0 | db0][half] += dZ1^T . [x, 1]   (B K-major [OKP][8])
+                    // [dW0 | db0][half] += dZ1^T . [x, 1]   (B K-major [XKP][8]; the dmu columns of Y are not used here)
                     umma_tf32(tmem + TM_D0, umma_desc_mn32(z1h, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, acc0);
                     umma_tf32(tmem + TM_D0, umma_desc_mn32(z1h, 1024u), umma_operand_desc(xl, 8, false, 0), idesc_x, 1u);
                     umma_tf32(tmem + TM_D0, umma_desc_mn32(z1l, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, 1u);
-                    // db1[half] = column O of dZ2^T . Y (the ones column is exact in tf32: two passes)
-                    umma_tf32(tmem + TM_D1, umma_desc_mn32(z2h, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, acc0);
-                    umma_tf32(tmem + TM_D1, umma_desc_mn32(z2l, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, 1u);
-                    // dWo[:, half]^T = columns O+1 .. O+A of H2^T . Y
-                    umma_tf32(tmem + TM_D2, umma_desc_mn32(h2h, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, acc0);
-                    umma_tf32(tmem + TM_D2, umma_desc_mn32(h2h, 1024u), umma_operand_desc(xl, 8, false, 0), idesc_x, 1u);
-                    umma_tf32(tmem + TM_D2, umma_desc_mn32(h2l, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, 1u);
                     first = 0u;
                     umma_commit(&empty_bar[rs]);              // both slots are free once these MMAs have read them
                     umma_commit(&der_empty_bar[ls]);
@@ -979,8 +977,18 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
         uint32_t rs = (uint32_t)grp, rph = 0, ls = (uint32_t)grp, lph = 0;
         int t = 0, blk = 0;
         bool first_tile = true;
-        constexpr int NF4 = (2 * ZB + HB) / 16;            // float4 items per sub-block: H2 (-> H2l, dZ2) | dZ1 | H1
         const int act_kind = a.lay.act;
+        // db1 and dWo on the FP32 pipe: thread <-> (sample row r, 4 columns) of its H2 items is the same in every
+        // sub-block, so the column sums over samples accumulate in registers and are combined over the 8 rows at the end
+        float s_db[NH2_IT][4], s_wo[NH2_IT][A][4];
+#pragma unroll
+        for (int i = 0; i < NH2_IT; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s_db[i][j] = 0.0f;
+#pragma unroll
+                for (int o = 0; o < A; ++o) s_wo[i][o][j] = 0.0f;
+            }
         for (int64_t k = a.k_begin + blockIdx.x; k < k_end; k += gridDim.x) {
             if (!(first_tile ? tcw_tile_of(a.tstart, a.T, k, &t, &blk) : tcw_tile_next(a.tstart, a.T, k, &t, &blk))) break;
             first_tile = false;
@@ -989,31 +997,17 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
                 mbar_wait(&der_empty_bar[ls], lph ^ 1u);
                 unsigned char *base = smem_raw + (size_t)rs * RAW_AL;
                 unsigned char *der = smem_raw + (size_t)NR * RAW_AL + (size_t)ls * DER;
-                // item assignment.  One group: the 256 items of the H2 piece are the expensive ones (they also rebuild dZ2),
-                // one per thread of warps 0..7, the plain items (dZ1, H1) spread over the remaining converter warps.  Two
-                // groups: a strided walk, every thread starts with H2 items.
-                constexpr int NH2 = (int)(ZB / 16), NREST = NCV * 32 - NH2;
-                static_assert(NREST > 0, "converter warps");
-                const bool h2_thread = NGRP == 1 && (int)threadIdx.x < NH2;
-#pragma unroll 2
-                for (int f = NGRP == 1 ? (int)threadIdx.x : tid_g; f < NF4; f += (NGRP == 1 ? (h2_thread ? NF4 : NREST) : GT)) {
+                // a strided walk over the items: every thread starts with its H2 item(s), the expensive ones
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    const int f = tid_g + it * GT;
+                    if (f >= NF4) break;
                     const uint32_t b = (uint32_t)f * 16u;
-                    // the raw pieces H2 | dZ1 | H1 are contiguous; lo parts: H2l at 0, Z1l at 3 ZB, H1l at 4 ZB of the derived slot
-                    unsigned char *hp = base + b;
-                    unsigned char *lp = der + (b < ZB ? b : b + 2 * ZB);
-                    const float4 v = *reinterpret_cast<const float4 *>(hp);
-                    float4 h4, l4;
-                    if (TRUNC) {
-                        h4.x = tf32_trunc(v.x); h4.y = tf32_trunc(v.y); h4.z = tf32_trunc(v.z); h4.w = tf32_trunc(v.w);
-                    } else {
-                        h4.x = tf32_hi(v.x); h4.y = tf32_hi(v.y); h4.z = tf32_hi(v.z); h4.w = tf32_hi(v.w);
-                    }
-                    l4.x = v.x - h4.x; l4.y = v.y - h4.y; l4.z = v.z - h4.z; l4.w = v.w - h4.w;
-                    if (!TRUNC) *reinterpret_cast<float4 *>(hp) = h4;
-                    *reinterpret_cast<float4 *>(lp) = l4;
-                    if (b < ZB) {
-                        // the same four elements of dZ2 = (Wo^T dmu) * act'(H2): sample row r of the sub-block, columns
-                        // col .. col+3 of this half (inverse of the MN-major SW128_32B sub-block layout)
+                    // the raw pieces H2 | dZ1 | H1 are contiguous
+                    const float4 v = *reinterpret_cast<const float4 *>(base + b);
+                    if (it < NH2_IT && b < ZB) {
+                        // four elements of H2: sample row r of the sub-block, columns col .. col+3 of this half (inverse of
+                        // the MN-major SW128_32B sub-block layout); dZ2 = (Wo^T dmu) * act'(H2) in kernel A's operation order
                         const int r = (int)((b & 1023u) >> 7);
                         const int col = (int)(b >> 10) * 32 + (int)((((b & 127u) >> 5) ^ (uint32_t)(r & 3)) << 3) + (int)((b & 31u) >> 2);
                         float dmu[A];
@@ -1022,7 +1016,7 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
                             const uint32_t xo = R_X + core_offset(8, O + 1 + o, r);
                             dmu[o] = *reinterpret_cast<const float *>(base + xo) + *reinterpret_cast<const float *>(base + xo + XB);
                         }
-                        float4 d;
+                        float4 d, h4, l4;
                         d.x = tcw_dz2<A>(v.x, dmu, &WoS[0][col], 128, act_kind);
                         d.y = tcw_dz2<A>(v.y, dmu, &WoS[0][col + 1], 128, act_kind);
                         d.z = tcw_dz2<A>(v.z, dmu, &WoS[0][col + 2], 128, act_kind);
@@ -1035,6 +1029,26 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
                         l4.x = d.x - h4.x; l4.y = d.y - h4.y; l4.z = d.z - h4.z; l4.w = d.w - h4.w;
                         *reinterpret_cast<float4 *>(der + D_Z2H + b) = TRUNC ? d : h4;
                         *reinterpret_cast<float4 *>(der + D_Z2L + b) = l4;
+                        const int ii = it < NH2_IT ? it : 0;
+                        s_db[ii][0] += d.x; s_db[ii][1] += d.y; s_db[ii][2] += d.z; s_db[ii][3] += d.w;
+#pragma unroll
+                        for (int o = 0; o < A; ++o) {
+                            s_wo[ii][o][0] = fmaf(dmu[o], v.x, s_wo[ii][o][0]);
+                            s_wo[ii][o][1] = fmaf(dmu[o], v.y, s_wo[ii][o][1]);
+                            s_wo[ii][o][2] = fmaf(dmu[o], v.z, s_wo[ii][o][2]);
+                            s_wo[ii][o][3] = fmaf(dmu[o], v.w, s_wo[ii][o][3]);
+                        }
+                    } else {
+                        // dZ1 / H1: hi stays in place, lo = x - trunc(x) into the derived slot (Z1l at 2 ZB, H1l at 3 ZB)
+                        float4 h4, l4;
+                        if (TRUNC) {
+                            h4.x = tf32_trunc(v.x); h4.y = tf32_trunc(v.y); h4.z = tf32_trunc(v.z); h4.w = tf32_trunc(v.w);
+                        } else {
+                            h4.x = tf32_hi(v.x); h4.y = tf32_hi(v.y); h4.z = tf32_hi(v.z); h4.w = tf32_hi(v.w);
+                            *reinterpret_cast<float4 *>(base + b) = h4;
+                        }
+                        l4.x = v.x - h4.x; l4.y = v.y - h4.y; l4.z = v.z - h4.z; l4.w = v.w - h4.w;
+                        *reinterpret_cast<float4 *>(der + ZB + b) = l4;
                     }
                 }
                 fence_proxy_async();
@@ -1045,12 +1059,34 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
                 if (ls >= (uint32_t)NL) { ls -= NL; lph ^= 1u; }
             }
         }
+        if (!first_tile) {
+            // this thread's db1 / dWo partials -> table [group][column][sample row][1 + A] in the (now idle) rings
+            mbar_wait(&done_bar, 0);                 // every MMA has read its operands
+            float *tab = reinterpret_cast<float *>(smem_raw);
+#pragma unroll
+            for (int ii = 0; ii < NH2_IT; ++ii) {
+                const int f = tid_g + ii * GT;
+                if (f < NH2) {
+                    const uint32_t b = (uint32_t)f * 16u;
+                    const int r = (int)((b & 1023u) >> 7);
+                    const int col = (int)(b >> 10) * 32 + (int)((((b & 127u) >> 5) ^ (uint32_t)(r & 3)) << 3) + (int)((b & 31u) >> 2);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float *e = tab + (size_t)(((grp * 128 + col + j) * 8 + r) * (A + 1));
+                        e[0] = s_db[ii][j];
+#pragma unroll
+                        for (int o = 0; o < A; ++o) e[1 + o] = s_wo[ii][o][j];
+                    }
+                }
+            }
+        }
     }
     // did this CTA process any tile?  (uniform: its first tile index is live or not)
     {
         int t, blk;
         any = (a.k_begin + blockIdx.x < k_end) && tcw_tile_of(a.tstart, a.T, a.k_begin + blockIdx.x, &t, &blk);
     }
+    __syncthreads();
     if (warp < 4 && any) {
         mbar_wait(&done_bar, 0);
         tc_fence_after();
@@ -1070,11 +1106,20 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
 #pragma unroll
             for (int o = 0; o < O; ++o) gp[f0 + (int64_t)row * O + o] += z[o];
             gp[f0 + (int64_t)W * O + row] += z[O];
-            tmem_ld32(my_tm + TM_D1, z);
-            gp[f1 + (int64_t)W * W + row] += z[O];
-            tmem_ld32(my_tm + TM_D2, z);
+            // db1 / dWo: the converter threads' partial column sums, fixed order (group, sample row)
+            const float *tab = reinterpret_cast<const float *>(smem_raw);
+            float acc[A + 1];
 #pragma unroll
-            for (int o = 0; o < A; ++o) gp[f2 + (int64_t)o * W + row] += z[O + 1 + o];
+            for (int q = 0; q <= A; ++q) acc[q] = 0.0f;
+            for (int g = 0; g < NGRP; ++g)
+                for (int r = 0; r < 8; ++r) {
+                    const float *e = tab + (size_t)(((g * 128 + warp * 32 + lane) * 8 + r) * (A + 1));
+#pragma unroll
+                    for (int q = 0; q <= A; ++q) acc[q] += e[q];
+                }
+            gp[f1 + (int64_t)W * W + row] += acc[0];
+#pragma unroll
+            for (int o = 0; o < A; ++o) gp[f2 + (int64_t)o * W + row] += acc[1 + o];
         }
         tc_fence_before();
     }
@@ -1088,7 +1133,7 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
 // ============================================================================
 template <int O, int A, int W, int NP>
 static int launch_tcw_np(const TcwArgs &a0, int grid, int64_t total_upper, int64_t batch_tiles, cudaStream_t st) {
-    constexpr int OKP = (O + 1 + 7) / 8 * 8, XKP = (O + 1 + A + 7) / 8 * 8;
+    constexpr int OKP = (O + 1 + 7) / 8 * 8;
     const size_t smemA = (size_t)TCW_STAGES * W * 128 + (size_t)a0.lay.resident * 4 + 2 * (size_t)128 * OKP * 4;
     const size_t smemB = TcwBRings<O, A, W>::BYTES;
     void (*kA)(const TcwArgs) = a0.lay.act == TG_ACT_RELU ? update_tcw_fwdbwd_kernel<O, A, true, W, NP>
