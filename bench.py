@@ -395,25 +395,35 @@ def measure(D, w, steps, warmup, full, args):
     # ---------------- per-kernel timing, each alone, CUDA events on its stream -------------
     aflat = policy.actor.flat_params()
 
-    def timeit(fn, warm, reps):
+    kernel_clocks = {}
+
+    def timeit(fn, warm, reps, name=None):
         ts = []
-        for i in range(warm + reps):
+        for i in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(D.local) if (name and rank == 0) else None
+        if sampler:
+            sampler.start()
+        for i in range(reps):
             a, b = ev(), ev()
             a.record()
             fn()
             b.record()
             torch.cuda.synchronize()
-            if i >= warm:
-                ts.append(a.elapsed_time(b))
+            ts.append(a.elapsed_time(b))
+        if sampler:
+            c = sampler.stop()
+            kernel_clocks[name] = {k: c.get(k) for k in ("sm_mhz", "power_w", "reasons")}
         return float(np.mean(ts))
 
     big = slots_per_step > 5e7
     # K1 first: with reuse_buffers the rollout it leaves behind is the one K2 / K3 are then timed on
-    k1_ms = timeit(lambda: mgr.rollout_device(init_state=inits[0]), 1 if big else 2, 2 if big else 3)
+    k1_ms = timeit(lambda: mgr.rollout_device(init_state=inits[0]), 1 if big else 2, 2 if big else 3, "k1")
     r = mgr.last
     adv, _ = engine.advantage(0, r.G, r.E, r.T, w["gamma"], 0.0, r.rew, r.len)
     k3_ms = timeit(lambda: engine.policy_grad(dims, "ReLU", aflat, policy.cov_diag, r.obs, r.act, adv, r.logp, r.len,
-                                              w["eps"], 1.0 / G), 1 if big else 3, 2 if big else 5)
+                                              w["eps"], 1.0 / G), 1 if big else 3, 2 if big else 5, "k3")
     k2_ms = timeit(lambda: engine.advantage(0, r.G, r.E, r.T, w["gamma"], 0.0, r.rew, r.len), 2, 3)
     # env-steps a rollout tile actually executes: a tile of 128 consecutive envs runs until its longest episode ends
     ln_t = r.len.to(torch.int64)
@@ -423,7 +433,7 @@ def measure(D, w, steps, warmup, full, args):
     kern = {"k1_ms": k1_ms, "k2_ms": k2_ms, "k3_ms": k3_ms, "valid_k": valid_k, "k1_exec_steps": k1_exec_steps,
             "P": P, "dims": dims, "N": N, "T": T, "O": O, "A": A,
             "k3_traffic": engine.policy_grad_traffic_bytes(dims, int(valid_k), r.len)}
-    out.update({"k1_ms": k1_ms, "k2_ms": k2_ms, "k3_ms": k3_ms})
+    out.update({"k1_ms": k1_ms, "k2_ms": k2_ms, "k3_ms": k3_ms, "kernel_clocks": kernel_clocks})
     if not full:
         return out, kern, None
 
@@ -583,7 +593,7 @@ def run_ours(args, w):
         "e2e": e2e, "gpu_launches": out["gpu_launches"],
         "slot_steps_per_s": out["slot_steps_per_s"], "valid_fraction": out["valid_fraction"],
         "rollout_env_steps_per_s": out["rollout_env_steps_per_s"], "grpo_updates_per_s": out["grpo_updates_per_s"],
-        "phase_ms": out["phase_ms"], "kernel_ms": {k: out.get(k) for k in ("k1_ms", "k2_ms", "k3_ms")},
+        "phase_ms": out["phase_ms"], "kernel_ms": {k: out.get(k) for k in ("k1_ms", "k2_ms", "k3_ms")}, "kernel_clocks": out.get("kernel_clocks"),
         "rank_weights_identical": out["rank_weights_identical"], "weights_finite": out["weights_finite"],
         "sharded_equals_single_gpu": out.get("sharded_equals_single_gpu"),
         "roofline": roof, "cpu_baseline": cpu, "clocks": out.get("clocks"), "other_configs": others,
