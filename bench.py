@@ -208,17 +208,18 @@ def run_reference(args, w):
     # the variable when it is first imported, which happens inside cpu_leg)
     for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ.pop(k, None)
-    vals, last = [], None
+    vals, ms, last = [], [], None
     for i in range(args.warmup + args.steps):
         last = cpu_leg(w, seed=i)
         if i >= args.warmup:
             vals.append(last["value"])
+            ms.append(1e3 * (last["rollout_s"] + last["learn_s"]))      # one step = one bounded sample (config.cpu_sample)
     v = float(np.mean(vals))
     last["value"] = v
     line = {
         "impl": "reference", "metric": "policy-in-loop env-steps/sec (rollout + GRPO update epoch)", "value": v,
         "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": {"workload": w["desc"], "cpu_sample": last["sample"]},
         "cpu_baseline": last, "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0,
                                       "d2h_bytes_per_step": 0},
