@@ -840,8 +840,8 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
 //   Y they cost 5 of the 11 MMAs of a sub-block and 40 % of its operand reads for 3 % of its MACs.
 //   A raw slot is busy from the TMA issue to the end of its MMAs (HBM latency + conversion + tensor time); a derived slot
 //   only from the conversion on.  Two rings put NR = 8 sub-blocks of loads in flight per SM at W = 256 where one ring of
-//   whole stages had room for 5: the kernel is bound by the latency of that pipeline, not by HBM bandwidth, the
-//   converter warps or the tensor pipe (profiles/README_r2.md).
+//   whole stages had room for 5 (-16 % per launch); with the register column sums below the kernel reads HBM at 76 % of
+//   the measured peak, tensor pipe 41 %, issue slots 42 % (profiles/README_r2.md).
 // ============================================================================
 // NCV converter warps (0 .. NCV-1); warp NCV = TMA producer, warp NCV+1 = MMA issuer.
 // TRUNC: the fp32 rows stay in place as the "hi" operand -- the tensor core reads only the top 19 bits of a tf32
