@@ -11,7 +11,7 @@
 //       registers -> tensor memory as the A operand (K halves at W = 256).  The first Linear runs on the
 //       tensor core too (obs hi/lo + ones column carrying the bias).  Per tile the kernel leaves in an HBM
 //       scratch, in the operand layout of kernel B:  H1, H2, dZ1 as fp32 (MN-major SW128_32B, 8-sample
-//       sub-blocks) and Y = [x, 1, dmu] hi/lo (K-major).  No column sums over samples are left in this kernel:
+//       sub-blocks) and Y = [x, 1, dmu] (fp32, K-major).  No column sums over samples are left in this kernel:
 //       round 1 computed dWo = dmu^T . H2 with register butterflies here (187 us of 847 us per 2656-tile batch at
 //       W = 256); dWo is now one more small GEMM of kernel B.
 //   kernel B  (update_tcw_wgrad_kernel)   split-K weight-gradient GEMMs over the batch's samples:
@@ -53,7 +53,7 @@ struct TcwScratch {                       // per-tile byte strides / bases insid
     unsigned char *base;
     int64_t tile_bytes;                   // all arrays of one tile
     int64_t arr_bytes;                    // one of H1, dZ2, dZ1 (fp32) per tile = 16 sub-blocks * W/32 KB
-    int64_t x_bytes;                      // one of Yh, Yl per tile = 16 * XKP * 32, XKP = roundup(O + 1 + A, 8)
+    int64_t x_bytes;                      // Y per tile = 16 * XKP * 32 (fp32), XKP = roundup(O + 1 + A, 8)
 };
 // array order inside a tile: H1, H2, dZ1 (fp32, MN-major sub-blocks), Yh, Yl  (Y = [x, 1, dmu], K-major)
 
@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
             first_tile = false;
             unsigned char *tile_sc = a.sc.base + (size_t)(k - a.k_begin) * a.sc.tile_bytes;
             unsigned char *H1s = tile_sc, *H2s = H1s + a.sc.arr_bytes, *Z1s = H2s + a.sc.arr_bytes;
-            unsigned char *Xh = Z1s + a.sc.arr_bytes, *Xl = Xh + a.sc.x_bytes;
+            unsigned char *Xs = Z1s + a.sc.arr_bytes;      // Y = [x, 1, dmu] as fp32 (kernel B splits it)
             // ---- inputs of this thread's sample (part 0 owns the per-sample scalars)
             const int64_t j = (int64_t)blk * 128 + e;
             const bool valid = j < a.cnt[t];
@@ -558,22 +558,17 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
                 for (int i = 0; i < O; ++i) x[i] = valid ? __ldg(a.obs + ((int64_t)t * O + i) * N + n) : 0.0f;
                 // Y = [x, 1, dmu] operand of kernel B: sub-block e/8, K-major [XKP rows][8 samples]; the dmu rows are
                 // filled in after the objective (epilogue 2a)
-                unsigned char *xh = Xh + (size_t)(e >> 3) * (XKP * 32), *xl = Xl + (size_t)(e >> 3) * (XKP * 32);
+                unsigned char *xs = Xs + (size_t)(e >> 3) * (XKP * 32);
 #pragma unroll
                 for (int i = 0; i < O; ++i) {
                     const float xhi = tf32_hi(x[i]);
                     *reinterpret_cast<float *>(O_hi + core_offset(OKP, e, i)) = xhi;
                     *reinterpret_cast<float *>(O_lo + core_offset(OKP, e, i)) = x[i] - xhi;
-                    const uint32_t xo = core_offset(8, i, e & 7);
-                    *reinterpret_cast<float *>(xh + xo) = xhi;
-                    *reinterpret_cast<float *>(xl + xo) = x[i] - xhi;
+                    *reinterpret_cast<float *>(xs + core_offset(8, i, e & 7)) = x[i];
                 }
 #pragma unroll
-                for (int i = O; i < XKP; ++i) {
-                    const uint32_t xo = core_offset(8, i, e & 7);
-                    *reinterpret_cast<float *>(xh + xo) = (i == O && valid) ? 1.0f : 0.0f;
-                    *reinterpret_cast<float *>(xl + xo) = 0.0f;
-                }
+                for (int i = O; i < XKP; ++i)
+                    *reinterpret_cast<float *>(xs + core_offset(8, i, e & 7)) = (i == O && valid) ? 1.0f : 0.0f;
             }
             if (part == 0) fence_proxy_async();       // only these threads wrote the shared-memory obs operand
             tc_fence_before();
@@ -720,15 +715,11 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
 #pragma unroll
                 for (int jj = 0; jj < A; ++jj) dmuS[jj][e] = dmu[jj];
                 if (!a.forward_only) {
-                    // dmu rows of Y (kernel B: dWo = H2^T . dmu on the tensor core)
-                    unsigned char *xh = Xh + (size_t)(e >> 3) * (XKP * 32), *xl = Xl + (size_t)(e >> 3) * (XKP * 32);
+                    // dmu rows of Y (kernel B rebuilds dZ2 from them and accumulates dWo = sum dmu H2)
+                    unsigned char *xs = Xs + (size_t)(e >> 3) * (XKP * 32);
 #pragma unroll
-                    for (int jj = 0; jj < A; ++jj) {
-                        const uint32_t xo = core_offset(8, O + 1 + jj, e & 7);
-                        const float dh = tf32_hi(dmu[jj]);
-                        *reinterpret_cast<float *>(xh + xo) = dh;
-                        *reinterpret_cast<float *>(xl + xo) = dmu[jj] - dh;
-                    }
+                    for (int jj = 0; jj < A; ++jj)
+                        *reinterpret_cast<float *>(xs + core_offset(8, O + 1 + jj, e & 7)) = dmu[jj];
                 }
             }
             if (a.forward_only) {           // CTA-uniform: the next tile's L1 GEMM may overwrite D once everybody read it
@@ -853,8 +844,8 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
 template <int O, int A, int W> struct TcwBRings {
     static constexpr int XKP = (O + 1 + A + 7) / 8 * 8;   // rows of Y = [x, 1, dmu, 0..]
     static constexpr uint32_t ZB = 4 * 1024, HB = W / 32 * 1024, XB = XKP * 32;        // bytes per piece
-    static constexpr uint32_t RAW = 2 * ZB + HB + 2 * XB, RAW_AL = (RAW + 1023) / 1024 * 1024;
-    static constexpr uint32_t DER = 3 * ZB + HB;
+    static constexpr uint32_t RAW = 2 * ZB + HB + XB, RAW_AL = (RAW + 1023) / 1024 * 1024;
+    static constexpr uint32_t DER = (3 * ZB + HB + XB + 1023) / 1024 * 1024;
     static constexpr int NL = 3;
     static constexpr int NR_FIT = (int)((220u * 1024u - NL * DER) / RAW_AL);
     static constexpr int NR = NR_FIT > 12 ? 12 : NR_FIT;
@@ -869,11 +860,11 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
     constexpr uint32_t ZB = RG::ZB, HB = RG::HB, XB = RG::XB, RAW_AL = RG::RAW_AL, DER = RG::DER;
     constexpr int NR = RG::NR, NL = RG::NL;
     static_assert(NR >= 4, "raw ring");
-    // raw slot: H2 | Z1h | H1h | Yh | Yl        derived slot: Z2h | Z2l | Z1l | H1l
+    // raw slot: H2 | Z1h | H1h | Yh (fp32 as stored)        derived slot: Z2h | Z2l | Z1l | H1l | Yl
     constexpr uint32_t R_Z1 = ZB, R_H1 = 2 * ZB, R_X = 2 * ZB + HB;
-    constexpr uint32_t D_Z2H = 0, D_Z2L = ZB, D_Z1L = 2 * ZB, D_H1L = 3 * ZB;
+    constexpr uint32_t D_Z2H = 0, D_Z2L = ZB, D_Z1L = 2 * ZB, D_H1L = 3 * ZB, D_XL = 3 * ZB + HB;
     constexpr uint32_t TM_DW = 0u, TM_D0 = (uint32_t)W;
-    constexpr int NF4 = (2 * ZB + HB) / 16;          // float4 items per sub-block: H2 (-> dZ2, dWo, db1) | dZ1 | H1
+    constexpr int NF4 = (2 * ZB + HB + XB) / 16;     // float4 items per sub-block: H2 (-> dZ2, dWo, db1) | dZ1 | H1 | Y
     constexpr int NH2 = (int)(ZB / 16);              // the H2 items
     constexpr int NIT = (NF4 + GT - 1) / GT, NH2_IT = (NH2 + GT - 1) / GT;   // items / H2 items per thread and sub-block
     if (a.k_begin + blockIdx.x >= a.tstart[a.T]) return;      // no live tile for this CTA in this batch (CTA-uniform)
@@ -916,18 +907,17 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
                 const unsigned char *tile_sc = a.sc.base + (size_t)(k - a.k_begin) * a.sc.tile_bytes;
                 const unsigned char *arr[3];
                 for (int i = 0; i < 3; ++i) arr[i] = tile_sc + (size_t)i * a.sc.arr_bytes;
-                const unsigned char *Xh = tile_sc + 3 * (size_t)a.sc.arr_bytes, *Xl = Xh + a.sc.x_bytes;
+                const unsigned char *Xs = tile_sc + 3 * (size_t)a.sc.arr_bytes;
                 for (int sb = 0; sb < 16; ++sb) {
                     mbar_wait(&empty_bar[rs], rph ^ 1u);
-                    mbar_expect_tx(&full_bar[rs], 2 * ZB + HB + 2 * XB);
+                    mbar_expect_tx(&full_bar[rs], 2 * ZB + HB + XB);
                     unsigned char *dst = smem_raw + (size_t)rs * RAW_AL;
                     const size_t sbo = (size_t)sb * HB, ho = (size_t)half * ZB;
                     // the fp32 rows land in the raw slot and stay there as the hi operands
                     tma_bulk_g2s(dst, arr[1] + sbo + ho, ZB, &full_bar[rs]);                 // H2 (this half)
                     tma_bulk_g2s(dst + R_Z1, arr[2] + sbo + ho, ZB, &full_bar[rs]);          // dZ1 (this half)
                     tma_bulk_g2s(dst + R_H1, arr[0] + sbo, HB, &full_bar[rs]);               // H1 (all columns)
-                    tma_bulk_g2s(dst + R_X, Xh + (size_t)sb * XB, XB, &full_bar[rs]);
-                    tma_bulk_g2s(dst + R_X + XB, Xl + (size_t)sb * XB, XB, &full_bar[rs]);
+                    tma_bulk_g2s(dst + R_X, Xs + (size_t)sb * XB, XB, &full_bar[rs]);                 // Y = [x, 1, dmu]
                     if (++rs == NR) { rs = 0; rph ^= 1u; }
                 }
             }
@@ -948,8 +938,8 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
                     tc_fence_after();
                     const uint32_t raw = smem_u32(smem_raw) + rs * RAW_AL;
                     const uint32_t der = smem_u32(smem_raw) + NR * RAW_AL + ls * DER;
-                    const uint32_t z1h = raw + R_Z1, h1h = raw + R_H1, xh = raw + R_X, xl = xh + XB;
-                    const uint32_t z2h = der + D_Z2H, z2l = der + D_Z2L, z1l = der + D_Z1L, h1l = der + D_H1L;
+                    const uint32_t z1h = raw + R_Z1, h1h = raw + R_H1, xh = raw + R_X;
+                    const uint32_t z2h = der + D_Z2H, z2l = der + D_Z2L, z1l = der + D_Z1L, h1l = der + D_H1L, xl = der + D_XL;
                     const uint32_t acc0 = first ? 0u : 1u;
                     // dW1[half] += dZ2^T . H1   (A, B MN-major: 8 reduction rows, 32-column blocks 1 KB apart)
                     umma_tf32(tmem + TM_DW, umma_desc_mn32(z2h, 1024u), umma_desc_mn32(h1h, 1024u), idesc_w, acc0);
@@ -1013,8 +1003,7 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
                         float dmu[A];
 #pragma unroll
                         for (int o = 0; o < A; ++o) {
-                            const uint32_t xo = R_X + core_offset(8, O + 1 + o, r);
-                            dmu[o] = *reinterpret_cast<const float *>(base + xo) + *reinterpret_cast<const float *>(base + xo + XB);
+                            dmu[o] = *reinterpret_cast<const float *>(base + R_X + core_offset(8, O + 1 + o, r));
                         }
                         float4 d, h4, l4;
                         d.x = tcw_dz2<A>(v.x, dmu, &WoS[0][col], 128, act_kind);
@@ -1039,7 +1028,7 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
                             s_wo[ii][o][3] = fmaf(dmu[o], v.w, s_wo[ii][o][3]);
                         }
                     } else {
-                        // dZ1 / H1: hi stays in place, lo = x - trunc(x) into the derived slot (Z1l at 2 ZB, H1l at 3 ZB)
+                        // dZ1 / H1 / Y: hi stays in place, lo = x - trunc(x) into the derived slot (Z1l at 2 ZB, H1l at 3 ZB, Yl after it)
                         float4 h4, l4;
                         if (TRUNC) {
                             h4.x = tf32_trunc(v.x); h4.y = tf32_trunc(v.y); h4.z = tf32_trunc(v.z); h4.w = tf32_trunc(v.w);
@@ -1198,7 +1187,7 @@ int tg_policy_grad_tcw(tg_ctx *ctx, const tg_mlp_cfg *mlp, int64_t N, int T, con
     // per-tile scratch; batch = as many tiles as fit the budget (a multiple of the grid)
     a.sc.arr_bytes = (int64_t)16 * (W / 32) * 1024;
     a.sc.x_bytes = (int64_t)16 * ((O + 1 + A + 7) / 8 * 8) * 32;
-    a.sc.tile_bytes = 3 * a.sc.arr_bytes + 2 * a.sc.x_bytes;
+    a.sc.tile_bytes = 3 * a.sc.arr_bytes + a.sc.x_bytes;
     const int64_t NB = (N + 127) / 128;
     const int64_t total_upper = NB * T;                       // live tiles <= this
     // 4 GB: one batch = ~10,600 tiles at W = 256; per-batch fixed costs (3 launches, weight staging, 290 KB gradient
@@ -1243,10 +1232,10 @@ extern "C" int tg_policy_grad_scratch_bytes(const tg_ctx *ctx, const tg_mlp_cfg 
     TcwLayout L;
     build_tcw_layout(mlp, &L);
     const int64_t arr = (int64_t)16 * (L.W / 32) * 1024, xb = (int64_t)16 * ((L.O + 1 + L.A + 7) / 8 * 8) * 32;
-    *bytes_written = n_tiles * (3 * arr + 2 * xb);                       // kernel A: H1, H2, dZ1 (fp32) + [x,1,dmu] hi/lo
-    // kernel B, one launch per 128-row half of the outputs: its half of H2 and dZ1, all of H1, [x,1,dmu] hi/lo
+    *bytes_written = n_tiles * (3 * arr + xb);                           // kernel A: H1, H2, dZ1, [x,1,dmu], all fp32
+    // kernel B, one launch per 128-row half of the outputs: its half of H2 and dZ1, all of H1, [x,1,dmu]
     const int64_t halves = L.W / 128;
-    *bytes_read = n_tiles * halves * (2 * (arr / halves) + arr + 2 * xb);
+    *bytes_read = n_tiles * halves * (2 * (arr / halves) + arr + xb);
     if (halves == 2) *bytes_read += n_tiles * arr;                       // kernel A: K-half-1 threads reload H1 / dZ2 halves
     return TG_OK;
 }
