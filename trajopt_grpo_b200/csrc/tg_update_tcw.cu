@@ -15,16 +15,17 @@
 //       round 1 computed dWo = dmu^T . H2 with register butterflies here (187 us of 847 us per 2656-tile batch at
 //       W = 256); dWo is now one more small GEMM of kernel B.
 //   kernel B  (update_tcw_wgrad_kernel)   split-K weight-gradient GEMMs over the batch's samples:
-//       dW1[half] += dZ2[:, half]^T . H1,   [dW0 | db0][half] += dZ1[:, half]^T . [x, 1]   on the tensor core;
-//       db1[half] = sum_s dZ2[s, half],   dWo[:, half] = sum_s dmu[s] H2[s, half]   on the FP32 pipe of the converter warps,
-//       operands streamed from the scratch by TMA (8 samples at a time, two shared-memory rings: see the kernel);
-//       dZ2 is not stored: the converter warps
-//       rebuild it from H2 and dmu, dZ2 = (Wo^T dmu) * act'(H2), with the operation order of kernel A, while they
-//       produce the tf32 lo parts (the fp32 rows themselves serve as the hi operands: the tensor core drops the low
-//       13 bits).  Accumulators persistent in tensor memory for all tiles of the launch, added to the CTA-private
-//       gradient copy at the end.  One launch per 128-row half of the outputs (two at W = 256).  Per launch of 2656
-//       tiles at W = 256: 8 -> 12 -> 16 converter warps 293 -> 267 -> 241 us; deeper raw ring + two converter groups
-//       202 us; db1 / dWo as register column sums instead of five small MMAs per sub-block 158 us (ncu, serialised).
+//       dW1 += dZ2^T . H1   and   [dW0 | db0] += dZ1^T . [x, 1]   on the tensor core (fp32 accumulators persistent in tensor
+//       memory for all tiles of the launch, added to the CTA-private gradient copy at the end);
+//       db1 = sum_s dZ2[s, :]   and   dWo = sum_s dmu[s] H2[s, :]   on the FP32 pipe of the converter warps (register column sums).
+//       Operands are streamed from the scratch by TMA, 8 samples at a time, through two shared-memory rings (see the kernel);
+//       dZ2 is not stored: the converter warps rebuild it from H2 and dmu, dZ2 = (Wo^T dmu) * act'(H2), with the operation
+//       order of kernel A, while they produce the tf32 lo parts (the fp32 rows themselves serve as the hi operands: the tensor
+//       core drops the low 13 bits).  W = 128: one launch.  W = 256: the [256 x 256] accumulator of dW1 fills the 512 TMEM
+//       columns, so [dW0 | db0] is a second, light launch over dZ1 and Y; every scratch array is read once per update.
+//       History per 2656 tiles at W = 256 (ncu, serialised): two half-output launches 2 x 241 us (8 -> 16 converter warps
+//       293 -> 241) -> two rings + two converter groups 2 x 202 -> db1 / dWo as register sums 2 x 160 -> one dW1 launch +
+//       one dW0 launch with warp-uniform MMA issue 201 + 80 us.
 //
 // Tiles are enumerated in length order (tg_order.cu): tile k of the compact list is (step t, sorted
 // positions 128*blk ..), found by binary search in the per-step prefix of live tiles; k beyond the live
@@ -73,7 +74,6 @@ struct TcwArgs {
     float eps_clip, scale, kl_scale;
     float *gpart;                         // [grid][n_params], accumulated (+=) across launches
     double *spart;                        // [grid][4], accumulated
-    int half;                             // kernel B: which 128-row half of the outputs
     // forward-only mode (tg_policy_forward_traj: critic values over a rollout ppo.py:93-94, old log-probs
     // ppo.py:142-143 / grpo.py:118-119): kernel A stops after the output layer and writes these; no kernel B
     int forward_only;
@@ -838,40 +838,53 @@ __global__ void __launch_bounds__(NP * 128 + 64, 1) update_tcw_fwdbwd_kernel(con
 // TRUNC: the fp32 rows stay in place as the "hi" operand -- the tensor core reads only the top 19 bits of a tf32
 // operand, i.e. it uses trunc(x) -- and the converter writes only lo = x - trunc(x) (one store and four cvt fewer per
 // float4 than the round-to-nearest split, whose hi has to be written back).
-#ifndef TCW_B_GROUPS
-#define TCW_B_GROUPS 2
-#endif
-template <int O, int A, int W> struct TcwBRings {
+// Geometry of the two rings for one instance.  DO_W1: dW1 (+ db1, dWo in registers); DO_W0: [dW0 | db0].  W = 128 runs both in
+// one launch; at W = 256 the full dW1 accumulator [256 x 256] fills the 512 TMEM columns, so [dW0 | db0] is a second, light
+// launch (it reads only dZ1 and Y) -- and H1 is read and split ONCE per sample instead of once per 128-row half (r2: the two
+// half launches of the previous design read H1 twice and re-split it).
+template <int O, int A, int W, bool DO_W1, bool DO_W0> struct TcwBRings {
     static constexpr int XKP = (O + 1 + A + 7) / 8 * 8;   // rows of Y = [x, 1, dmu, 0..]
-    static constexpr uint32_t ZB = 4 * 1024, HB = W / 32 * 1024, XB = XKP * 32;        // bytes per piece
-    static constexpr uint32_t RAW = 2 * ZB + HB + XB, RAW_AL = (RAW + 1023) / 1024 * 1024;
-    static constexpr uint32_t DER = (3 * ZB + HB + XB + 1023) / 1024 * 1024;
+    static constexpr uint32_t HB = W / 32 * 1024, XB = XKP * 32;        // bytes per piece: all W columns of 8 samples; Y
+    // raw slot (TMA):            H2 | dZ1 | H1 | Y      (pieces of the instance only)
+    static constexpr uint32_t R_H2 = 0, R_Z1 = DO_W1 ? HB : 0, R_H1 = R_Z1 + (DO_W0 ? HB : 0), R_X = R_H1 + (DO_W1 ? HB : 0);
+    static constexpr uint32_t RAW = R_X + XB, RAW_AL = (RAW + 1023) / 1024 * 1024;
+    // derived slot (converters): Z2h | Z2l | Z1l | H1l | Yl
+    static constexpr uint32_t D_Z2H = 0, D_Z2L = HB, D_Z1L = DO_W1 ? 2 * HB : 0, D_H1L = D_Z1L + (DO_W0 ? HB : 0);
+    static constexpr uint32_t D_XL = D_H1L + (DO_W1 ? HB : 0);
+    static constexpr uint32_t DER = (D_XL + (DO_W0 ? XB : 0) + 1023) / 1024 * 1024;
+    // lo part of the plain item at raw byte b (dZ1, H1, Y) sits at derived byte LO_SHIFT + b
+    static constexpr uint32_t LO_SHIFT = DO_W1 ? HB : 0;
+    static_assert(D_Z1L == LO_SHIFT + R_Z1 || !DO_W0, "layout");
+    static_assert(D_H1L == LO_SHIFT + R_H1 || !DO_W1, "layout");
+    static_assert(D_XL == LO_SHIFT + R_X, "layout");
     static constexpr int NL = 3;
     static constexpr int NR_FIT = (int)((220u * 1024u - NL * DER) / RAW_AL);
     static constexpr int NR = NR_FIT > 12 ? 12 : NR_FIT;
     static constexpr size_t BYTES = (size_t)NR * RAW_AL + (size_t)NL * DER;
 };
 
-template <int O, int A, int W, int NCV, bool TRUNC, int NGRP>
+template <int O, int A, int W, int NCV, bool TRUNC, bool DO_W1, bool DO_W0>
 __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(const __grid_constant__ TcwArgs a) {
-    using RG = TcwBRings<O, A, W>;
-    static_assert(NCV % NGRP == 0 && (NGRP == 1 || NGRP == 2), "converter groups");
-    constexpr int GT = NCV / NGRP * 32;              // converter threads per group; group g takes sub-blocks g, g + NGRP, ...
-    constexpr uint32_t ZB = RG::ZB, HB = RG::HB, XB = RG::XB, RAW_AL = RG::RAW_AL, DER = RG::DER;
+    using RG = TcwBRings<O, A, W, DO_W1, DO_W0>;
+    constexpr int NGRP = 2, MB = W / 128;            // converter groups (sub-blocks g, g + 2, ...); 128-row blocks of the outputs
+    static_assert(NCV % NGRP == 0, "converter groups");
+    static_assert(DO_W1 || DO_W0, "nothing to do");
+    constexpr int GT = NCV / NGRP * 32;              // converter threads per group
+    constexpr uint32_t ZB = 4 * 1024, HB = RG::HB, XB = RG::XB, RAW_AL = RG::RAW_AL, DER = RG::DER;
     constexpr int NR = RG::NR, NL = RG::NL;
     static_assert(NR >= 4, "raw ring");
-    // raw slot: H2 | Z1h | H1h | Yh (fp32 as stored)        derived slot: Z2h | Z2l | Z1l | H1l | Yl
-    constexpr uint32_t R_Z1 = ZB, R_H1 = 2 * ZB, R_X = 2 * ZB + HB;
-    constexpr uint32_t D_Z2H = 0, D_Z2L = ZB, D_Z1L = 2 * ZB, D_H1L = 3 * ZB, D_XL = 3 * ZB + HB;
-    constexpr uint32_t TM_DW = 0u, TM_D0 = (uint32_t)W;
-    constexpr int NF4 = (2 * ZB + HB + XB) / 16;     // float4 items per sub-block: H2 (-> dZ2, dWo, db1) | dZ1 | H1 | Y
-    constexpr int NH2 = (int)(ZB / 16);              // the H2 items
-    constexpr int NIT = (NF4 + GT - 1) / GT, NH2_IT = (NH2 + GT - 1) / GT;   // items / H2 items per thread and sub-block
+    constexpr uint32_t R_Z1 = RG::R_Z1, R_H1 = RG::R_H1, R_X = RG::R_X;
+    constexpr uint32_t D_Z2H = RG::D_Z2H, D_Z2L = RG::D_Z2L, D_Z1L = RG::D_Z1L, D_H1L = RG::D_H1L, D_XL = RG::D_XL;
+    constexpr uint32_t TM_DW = 0u, TM_D0 = DO_W1 ? (uint32_t)(MB * W) : 0u;        // D0 block mb at TM_D0 + 32 mb
+    static_assert(TM_D0 + (DO_W0 ? 32 * MB : 0) <= 512, "tensor memory");
+    constexpr int NF4 = (int)((R_X + (DO_W0 ? XB : 0)) / 16);   // float4 items per sub-block: H2 (-> dZ2, dWo, db1) | dZ1 | H1 | Y
+    constexpr int NH2 = DO_W1 ? (int)(HB / 16) : 0;             // the H2 items
+    constexpr int NIT = (NF4 + GT - 1) / GT, NH2_IT = DO_W1 ? (NH2 + GT - 1) / GT : 1;
     if (a.k_begin + blockIdx.x >= a.tstart[a.T]) return;      // no live tile for this CTA in this batch (CTA-uniform)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[NR], empty_bar[NR], conv_bar[NL], der_empty_bar[NL], done_bar;
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(16) float WoS[A][128];    // Wo[:, this half's columns] (dZ2 = (Wo^T dmu) * act'(H2))
+    __shared__ __align__(16) float WoS[DO_W1 ? A : 1][DO_W1 ? W : 4];    // Wo (dZ2 = (Wo^T dmu) * act'(H2))
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
     if (threadIdx.x == 0) {
         for (int i = 0; i < NR; ++i) {
@@ -886,9 +899,8 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
         mbar_fence_init();
     }
     if (threadIdx.x < 32) tmem_alloc(&tmem_slot, 512);
-    const int half = a.half;
-    for (int i = threadIdx.x; i < A * 128; i += blockDim.x)
-        WoS[i / 128][i % 128] = a.params[a.lay.flat_w[2] + (int64_t)(i / 128) * W + half * 128 + (i % 128)];
+    if (DO_W1)
+        for (int i = threadIdx.x; i < A * W; i += blockDim.x) WoS[i / W][i % W] = a.params[a.lay.flat_w[2] + i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -910,13 +922,13 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
                 const unsigned char *Xs = tile_sc + 3 * (size_t)a.sc.arr_bytes;
                 for (int sb = 0; sb < 16; ++sb) {
                     mbar_wait(&empty_bar[rs], rph ^ 1u);
-                    mbar_expect_tx(&full_bar[rs], 2 * ZB + HB + XB);
+                    mbar_expect_tx(&full_bar[rs], RG::RAW);
                     unsigned char *dst = smem_raw + (size_t)rs * RAW_AL;
-                    const size_t sbo = (size_t)sb * HB, ho = (size_t)half * ZB;
+                    const size_t sbo = (size_t)sb * HB;
                     // the fp32 rows land in the raw slot and stay there as the hi operands
-                    tma_bulk_g2s(dst, arr[1] + sbo + ho, ZB, &full_bar[rs]);                 // H2 (this half)
-                    tma_bulk_g2s(dst + R_Z1, arr[2] + sbo + ho, ZB, &full_bar[rs]);          // dZ1 (this half)
-                    tma_bulk_g2s(dst + R_H1, arr[0] + sbo, HB, &full_bar[rs]);               // H1 (all columns)
+                    if (DO_W1) tma_bulk_g2s(dst, arr[1] + sbo, HB, &full_bar[rs]);                    // H2
+                    if (DO_W0) tma_bulk_g2s(dst + R_Z1, arr[2] + sbo, HB, &full_bar[rs]);             // dZ1
+                    if (DO_W1) tma_bulk_g2s(dst + R_H1, arr[0] + sbo, HB, &full_bar[rs]);             // H1
                     tma_bulk_g2s(dst + R_X, Xs + (size_t)sb * XB, XB, &full_bar[rs]);                 // Y = [x, 1, dmu]
                     if (++rs == NR) { rs = 0; rph ^= 1u; }
                 }
@@ -926,43 +938,59 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
         const uint32_t idesc_w = umma_idesc_tf32(128, W, true, true);
         const uint32_t idesc_x = umma_idesc_tf32(128, (O + 1 + 7) / 8 * 8, true, false);   // rows [x, 1] of Y only
         uint32_t rs = 0, ls = 0, lph = 0, first = 1u;
+        const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem, 0), smem_base = __shfl_sync(0xffffffffu, smem_u32(smem_raw), 0);
         int t = 0, blk = 0;
         bool first_tile = true;
         for (int64_t k = a.k_begin + blockIdx.x; k < k_end; k += gridDim.x) {
             if (!(first_tile ? tcw_tile_of(a.tstart, a.T, k, &t, &blk) : tcw_tile_next(a.tstart, a.T, k, &t, &blk))) break;
             first_tile = false;
             any = true;
-            if (lane == 0) {
+            {
+                // the whole warp runs the loop with warp-uniform operands; one elected lane issues (umma_tf32_w)
                 for (int sb = 0; sb < 16; ++sb) {
                     mbar_wait(&conv_bar[ls], lph);            // landed AND split by the converter warps
                     tc_fence_after();
-                    const uint32_t raw = smem_u32(smem_raw) + rs * RAW_AL;
-                    const uint32_t der = smem_u32(smem_raw) + NR * RAW_AL + ls * DER;
-                    const uint32_t z1h = raw + R_Z1, h1h = raw + R_H1, xh = raw + R_X;
-                    const uint32_t z2h = der + D_Z2H, z2l = der + D_Z2L, z1l = der + D_Z1L, h1l = der + D_H1L, xl = der + D_XL;
+                    const uint32_t raw = smem_base + rs * RAW_AL;
+                    const uint32_t der = smem_base + NR * RAW_AL + ls * DER;
                     const uint32_t acc0 = first ? 0u : 1u;
-                    // dW1[half] += dZ2^T . H1   (A, B MN-major: 8 reduction rows, 32-column blocks 1 KB apart)
-                    umma_tf32(tmem + TM_DW, umma_desc_mn32(z2h, 1024u), umma_desc_mn32(h1h, 1024u), idesc_w, acc0);
-                    umma_tf32(tmem + TM_DW, umma_desc_mn32(z2h, 1024u), umma_desc_mn32(h1l, 1024u), idesc_w, 1u);
-                    umma_tf32(tmem + TM_DW, umma_desc_mn32(z2l, 1024u), umma_desc_mn32(h1h, 1024u), idesc_w, 1u);
-                    // [dW0 | db0][half] += dZ1^T . [x, 1]   (B K-major [XKP][8]; the dmu columns of Y are not used here)
-                    umma_tf32(tmem + TM_D0, umma_desc_mn32(z1h, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, acc0);
-                    umma_tf32(tmem + TM_D0, umma_desc_mn32(z1h, 1024u), umma_operand_desc(xl, 8, false, 0), idesc_x, 1u);
-                    umma_tf32(tmem + TM_D0, umma_desc_mn32(z1l, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, 1u);
+                    if (DO_W1) {
+                        // dW1[block mb] += dZ2[:, block mb]^T . H1   (A, B MN-major: 8 reduction rows, 32-column blocks 1 KB apart)
+                        const uint32_t h1h = raw + R_H1, h1l = der + D_H1L;
+#pragma unroll
+                        for (int mb = 0; mb < MB; ++mb) {
+                            const uint32_t z2h = der + D_Z2H + (uint32_t)mb * ZB, z2l = der + D_Z2L + (uint32_t)mb * ZB;
+                            const uint32_t d = tm_u + TM_DW + (uint32_t)(mb * W);
+                            umma_tf32_w(d, umma_desc_mn32(z2h, 1024u), umma_desc_mn32(h1h, 1024u), idesc_w, acc0);
+                            umma_tf32_w(d, umma_desc_mn32(z2h, 1024u), umma_desc_mn32(h1l, 1024u), idesc_w, 1u);
+                            umma_tf32_w(d, umma_desc_mn32(z2l, 1024u), umma_desc_mn32(h1h, 1024u), idesc_w, 1u);
+                        }
+                    }
+                    if (DO_W0) {
+                        // [dW0 | db0][block mb] += dZ1[:, block mb]^T . [x, 1]   (B K-major [XKP][8]; the dmu rows of Y are not used)
+                        const uint32_t xh = raw + R_X, xl = der + D_XL;
+#pragma unroll
+                        for (int mb = 0; mb < MB; ++mb) {
+                            const uint32_t z1h = raw + R_Z1 + (uint32_t)mb * ZB, z1l = der + D_Z1L + (uint32_t)mb * ZB;
+                            const uint32_t d = tm_u + TM_D0 + (uint32_t)(mb * 32);
+                            umma_tf32_w(d, umma_desc_mn32(z1h, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, acc0);
+                            umma_tf32_w(d, umma_desc_mn32(z1h, 1024u), umma_operand_desc(xl, 8, false, 0), idesc_x, 1u);
+                            umma_tf32_w(d, umma_desc_mn32(z1l, 1024u), umma_operand_desc(xh, 8, false, 0), idesc_x, 1u);
+                        }
+                    }
                     first = 0u;
-                    umma_commit(&empty_bar[rs]);              // both slots are free once these MMAs have read them
-                    umma_commit(&der_empty_bar[ls]);
+                    umma_commit_w(&empty_bar[rs]);              // both slots are free once these MMAs have read them
+                    umma_commit_w(&der_empty_bar[ls]);
                     if (++rs == NR) rs = 0;
                     if (++ls == NL) { ls = 0; lph ^= 1u; }
                 }
             }
             __syncwarp();
         }
-        if (lane == 0 && any) umma_commit(&done_bar);
+        if (any) umma_commit_w(&done_bar);
         __syncwarp();
     }
     if (warp < NCV) {
-        // ===== converter warps: tf32 hi/lo split of the fp32 rows of every stage, in shared memory =====
+        // ===== converter warps: tf32 lo parts (and dZ2) of every sub-block, in shared memory =====
         const int grp = warp / (NCV / NGRP), tid_g = (int)threadIdx.x - grp * GT;
         uint32_t rs = (uint32_t)grp, rph = 0, ls = (uint32_t)grp, lph = 0;
         int t = 0, blk = 0;
@@ -993,23 +1021,22 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
                     const int f = tid_g + it * GT;
                     if (f >= NF4) break;
                     const uint32_t b = (uint32_t)f * 16u;
-                    // the raw pieces H2 | dZ1 | H1 are contiguous
+                    // the raw pieces are contiguous
                     const float4 v = *reinterpret_cast<const float4 *>(base + b);
-                    if (it < NH2_IT && b < ZB) {
-                        // four elements of H2: sample row r of the sub-block, columns col .. col+3 of this half (inverse of
-                        // the MN-major SW128_32B sub-block layout); dZ2 = (Wo^T dmu) * act'(H2) in kernel A's operation order
+                    if (DO_W1 && it < NH2_IT && b < HB) {
+                        // four elements of H2: sample row r of the sub-block, columns col .. col+3 (inverse of the MN-major
+                        // SW128_32B sub-block layout); dZ2 = (Wo^T dmu) * act'(H2) in kernel A's operation order
                         const int r = (int)((b & 1023u) >> 7);
                         const int col = (int)(b >> 10) * 32 + (int)((((b & 127u) >> 5) ^ (uint32_t)(r & 3)) << 3) + (int)((b & 31u) >> 2);
                         float dmu[A];
 #pragma unroll
-                        for (int o = 0; o < A; ++o) {
+                        for (int o = 0; o < A; ++o)
                             dmu[o] = *reinterpret_cast<const float *>(base + R_X + core_offset(8, O + 1 + o, r));
-                        }
                         float4 d, h4, l4;
-                        d.x = tcw_dz2<A>(v.x, dmu, &WoS[0][col], 128, act_kind);
-                        d.y = tcw_dz2<A>(v.y, dmu, &WoS[0][col + 1], 128, act_kind);
-                        d.z = tcw_dz2<A>(v.z, dmu, &WoS[0][col + 2], 128, act_kind);
-                        d.w = tcw_dz2<A>(v.w, dmu, &WoS[0][col + 3], 128, act_kind);
+                        d.x = tcw_dz2<A>(v.x, dmu, &WoS[0][col], W, act_kind);
+                        d.y = tcw_dz2<A>(v.y, dmu, &WoS[0][col + 1], W, act_kind);
+                        d.z = tcw_dz2<A>(v.z, dmu, &WoS[0][col + 2], W, act_kind);
+                        d.w = tcw_dz2<A>(v.w, dmu, &WoS[0][col + 3], W, act_kind);
                         if (TRUNC) {
                             h4.x = tf32_trunc(d.x); h4.y = tf32_trunc(d.y); h4.z = tf32_trunc(d.z); h4.w = tf32_trunc(d.w);
                         } else {
@@ -1028,7 +1055,7 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
                             s_wo[ii][o][3] = fmaf(dmu[o], v.w, s_wo[ii][o][3]);
                         }
                     } else {
-                        // dZ1 / H1 / Y: hi stays in place, lo = x - trunc(x) into the derived slot (Z1l at 2 ZB, H1l at 3 ZB, Yl after it)
+                        // dZ1 / H1 / Y: hi stays in place, lo = x - trunc(x) into the derived slot
                         float4 h4, l4;
                         if (TRUNC) {
                             h4.x = tf32_trunc(v.x); h4.y = tf32_trunc(v.y); h4.z = tf32_trunc(v.z); h4.w = tf32_trunc(v.w);
@@ -1037,7 +1064,7 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
                             *reinterpret_cast<float4 *>(base + b) = h4;
                         }
                         l4.x = v.x - h4.x; l4.y = v.y - h4.y; l4.z = v.z - h4.z; l4.w = v.w - h4.w;
-                        *reinterpret_cast<float4 *>(der + ZB + b) = l4;
+                        *reinterpret_cast<float4 *>(der + RG::LO_SHIFT + b) = l4;
                     }
                 }
                 fence_proxy_async();
@@ -1048,7 +1075,7 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
                 if (ls >= (uint32_t)NL) { ls -= NL; lph ^= 1u; }
             }
         }
-        if (!first_tile) {
+        if (DO_W1 && !first_tile) {
             // this thread's db1 / dWo partials -> table [group][column][sample row][1 + A] in the (now idle) rings
             mbar_wait(&done_bar, 0);                 // every MMA has read its operands
             float *tab = reinterpret_cast<float *>(smem_raw);
@@ -1061,7 +1088,7 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
                     const int col = (int)(b >> 10) * 32 + (int)((((b & 127u) >> 5) ^ (uint32_t)(r & 3)) << 3) + (int)((b & 31u) >> 2);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        float *e = tab + (size_t)(((grp * 128 + col + j) * 8 + r) * (A + 1));
+                        float *e = tab + (size_t)(((grp * W + col + j) * 8 + r) * (A + 1));
                         e[0] = s_db[ii][j];
 #pragma unroll
                         for (int o = 0; o < A; ++o) e[1 + o] = s_wo[ii][o][j];
@@ -1081,34 +1108,39 @@ __global__ void __launch_bounds__((NCV + 2) * 32, 1) update_tcw_wgrad_kernel(con
         tc_fence_after();
         float *gp = a.gpart + (int64_t)blockIdx.x * a.lay.n_params;
         const int64_t f0 = a.lay.flat_w[0], f1 = a.lay.flat_w[1], f2 = a.lay.flat_w[2];
-        const int row = half * 128 + warp * 32 + lane;       // out index (dW1) / hidden-1 index (dW0) / hidden-2 index (dWo)
         const uint32_t my_tm = tmem + ((uint32_t)(warp * 32) << 16);
-        for (int c = 0; c < W; c += 32) {
-            float z[32];
-            tmem_ld32(my_tm + TM_DW + (uint32_t)c, z);
+#pragma unroll 1
+        for (int mb = 0; mb < MB; ++mb) {
+            const int row = mb * 128 + warp * 32 + lane;     // out index (dW1) / hidden-1 index (dW0) / hidden-2 index (dWo)
+            if (DO_W1) {
+                for (int c = 0; c < W; c += 32) {
+                    float z[32];
+                    tmem_ld32(my_tm + TM_DW + (uint32_t)(mb * W + c), z);
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) gp[f1 + (int64_t)row * W + c + jj] += z[jj];
-        }
-        {
-            float z[32];
-            tmem_ld32(my_tm + TM_D0, z);
-#pragma unroll
-            for (int o = 0; o < O; ++o) gp[f0 + (int64_t)row * O + o] += z[o];
-            gp[f0 + (int64_t)W * O + row] += z[O];
-            // db1 / dWo: the converter threads' partial column sums, fixed order (group, sample row)
-            const float *tab = reinterpret_cast<const float *>(smem_raw);
-            float acc[A + 1];
-#pragma unroll
-            for (int q = 0; q <= A; ++q) acc[q] = 0.0f;
-            for (int g = 0; g < NGRP; ++g)
-                for (int r = 0; r < 8; ++r) {
-                    const float *e = tab + (size_t)(((g * 128 + warp * 32 + lane) * 8 + r) * (A + 1));
-#pragma unroll
-                    for (int q = 0; q <= A; ++q) acc[q] += e[q];
+                    for (int jj = 0; jj < 32; ++jj) gp[f1 + (int64_t)row * W + c + jj] += z[jj];
                 }
-            gp[f1 + (int64_t)W * W + row] += acc[0];
+                // db1 / dWo: the converter threads' partial column sums, fixed order (group, sample row)
+                const float *tab = reinterpret_cast<const float *>(smem_raw);
+                float acc[A + 1];
 #pragma unroll
-            for (int o = 0; o < A; ++o) gp[f2 + (int64_t)o * W + row] += acc[1 + o];
+                for (int q = 0; q <= A; ++q) acc[q] = 0.0f;
+                for (int g = 0; g < NGRP; ++g)
+                    for (int r = 0; r < 8; ++r) {
+                        const float *e = tab + (size_t)(((g * W + row) * 8 + r) * (A + 1));
+#pragma unroll
+                        for (int q = 0; q <= A; ++q) acc[q] += e[q];
+                    }
+                gp[f1 + (int64_t)W * W + row] += acc[0];
+#pragma unroll
+                for (int o = 0; o < A; ++o) gp[f2 + (int64_t)o * W + row] += acc[1 + o];
+            }
+            if (DO_W0) {
+                float z[32];
+                tmem_ld32(my_tm + TM_D0 + (uint32_t)(mb * 32), z);
+#pragma unroll
+                for (int o = 0; o < O; ++o) gp[f0 + (int64_t)row * O + o] += z[o];
+                gp[f0 + (int64_t)W * O + row] += z[O];
+            }
         }
         tc_fence_before();
     }
@@ -1124,24 +1156,29 @@ template <int O, int A, int W, int NP>
 static int launch_tcw_np(const TcwArgs &a0, int grid, int64_t total_upper, int64_t batch_tiles, cudaStream_t st) {
     constexpr int OKP = (O + 1 + 7) / 8 * 8;
     const size_t smemA = (size_t)TCW_STAGES * W * 128 + (size_t)a0.lay.resident * 4 + 2 * (size_t)128 * OKP * 4;
-    const size_t smemB = TcwBRings<O, A, W>::BYTES;
     void (*kA)(const TcwArgs) = a0.lay.act == TG_ACT_RELU ? update_tcw_fwdbwd_kernel<O, A, true, W, NP>
                                                           : update_tcw_fwdbwd_kernel<O, A, false, W, NP>;
     // converter warps of kernel B: measured on B200 (profiles/README_r2.md) 8 / 12 / 16 warps = 293 / 267 / 241 us per
-    // launch at W = 256 and 12 <= 16 at W = 128
+    // launch at W = 256 and 12 <= 16 at W = 128 (22 warps: no further gain, r2p)
     constexpr int NCV = W == 256 ? 16 : 12;
-    void (*kB)(const TcwArgs) = update_tcw_wgrad_kernel<O, A, W, NCV, true, TCW_B_GROUPS>;      // (22 warps: no further gain, r2p)
+    // W = 128: one launch computes every weight gradient.  W = 256: dW1 (+ db1, dWo) fills tensor memory, [dW0 | db0] follows
+    // in a light second launch that reads only dZ1 and Y.
+    constexpr bool SPLIT = W == 256;
+    void (*kB1)(const TcwArgs) = update_tcw_wgrad_kernel<O, A, W, NCV, true, true, !SPLIT>;
+    void (*kB0)(const TcwArgs) = update_tcw_wgrad_kernel<O, A, W, NCV, true, false, true>;
+    const size_t smemB1 = TcwBRings<O, A, W, true, !SPLIT>::BYTES, smemB0 = TcwBRings<O, A, W, false, true>::BYTES;
     const int threadsB = (NCV + 2) * 32;
     TG_CUDA(cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
-    TG_CUDA(cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+    TG_CUDA(cudaFuncSetAttribute(kB1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB1));
+    if (SPLIT) TG_CUDA(cudaFuncSetAttribute(kB0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB0));
     for (int64_t k0 = 0; k0 < total_upper; k0 += batch_tiles) {
         TcwArgs a = a0;
         a.k_begin = k0;
         a.k_count = (total_upper - k0) < batch_tiles ? (total_upper - k0) : batch_tiles;
         kA<<<grid, NP * 128 + 64, smemA, st>>>(a);
-        for (int half = 0; half < (a.forward_only ? 0 : W / 128); ++half) {
-            a.half = half;
-            kB<<<grid, threadsB, smemB, st>>>(a);
+        if (!a.forward_only) {
+            kB1<<<grid, threadsB, smemB1, st>>>(a);
+            if (SPLIT) kB0<<<grid, threadsB, smemB0, st>>>(a);
         }
     }
     TG_CUDA(cudaGetLastError());
@@ -1233,9 +1270,9 @@ extern "C" int tg_policy_grad_scratch_bytes(const tg_ctx *ctx, const tg_mlp_cfg 
     build_tcw_layout(mlp, &L);
     const int64_t arr = (int64_t)16 * (L.W / 32) * 1024, xb = (int64_t)16 * ((L.O + 1 + L.A + 7) / 8 * 8) * 32;
     *bytes_written = n_tiles * (3 * arr + xb);                           // kernel A: H1, H2, dZ1, [x,1,dmu], all fp32
-    // kernel B, one launch per 128-row half of the outputs: its half of H2 and dZ1, all of H1, [x,1,dmu]
+    // kernel B: H2, H1, dZ1 once each; [x,1,dmu] once per launch (two launches at W = 256: dW1 | dW0)
     const int64_t halves = L.W / 128;
-    *bytes_read = n_tiles * halves * (2 * (arr / halves) + arr + xb);
+    *bytes_read = n_tiles * (3 * arr + halves * xb);
     if (halves == 2) *bytes_read += n_tiles * arr;                       // kernel A: K-half-1 threads reload H1 / dZ2 halves
     return TG_OK;
 }
